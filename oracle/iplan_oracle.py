@@ -1,0 +1,477 @@
+"""TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+
+CPU restatement (PyTorch fp32 on the host cores) of the reference's iPLAN hot
+path.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import this module, and only as
+the checker or the timed CPU baseline; nothing under ``iplan_b200/`` imports it.
+
+Pinning: the reference ships no tests or golden vectors for this path
+(SURVEY.md §4), so the oracle is pinned against outputs of the reference's own
+modules executed in the build container: ``tests/golden/make_golden.py`` imports
+``/root/reference`` and writes ``tests/golden/*.pt``; ``tests/test_oracle_golden.py``
+checks every function below against those fixtures (<=2e-6 abs).
+
+Every function cites the reference lines it restates.  Weights are passed as
+``dict[str, Tensor]`` using the reference modules' ``state_dict`` key names.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------------
+# shared pieces
+# ----------------------------------------------------------------------------------
+
+def neighbour_index(n):
+    """[n, n-1] table j(i, s) = s if s < i else s + 1  (nova/GAT_Net.py:61-66, :111-113)."""
+    i = torch.arange(n).view(n, 1)
+    s = torch.arange(n - 1).view(1, n - 1)
+    return torch.where(s < i, s, s + 1)
+
+
+def gru_cell(x_proj, h, w_hh, b_hh):
+    """One GRU step given the already-projected input ``x_proj = W_ih x + b_ih``.
+    PyTorch gate order r, z, n;  n = tanh(i_n + r * (W_hn h + b_hn));
+    h' = (1 - z) * n + z * h   (torch.nn.GRU / GRUCell semantics used at
+    nova/GAT_Net.py:26,39, nova/behavior_net.py:14, utils/mappo_utils/rnn.py:13)."""
+    hd = h.shape[-1]
+    gh = h @ w_hh.t() + b_hh
+    r = torch.sigmoid(x_proj[..., :hd] + gh[..., :hd])
+    z = torch.sigmoid(x_proj[..., hd:2 * hd] + gh[..., hd:2 * hd])
+    n = torch.tanh(x_proj[..., 2 * hd:] + r * gh[..., 2 * hd:])
+    return (1.0 - z) * n + z * h
+
+
+def gumbel_from_exponential(e):
+    """F.gumbel_softmax draws ``-empty_like(logits).exponential_().log()``
+    (torch/nn/functional.py); the reference calls it at nova/GAT_Net.py:93."""
+    return -e.log()
+
+
+def draw_gumbel(rows, generator=None):
+    """Noise with the reference's draw order: one [rows, 2] exponential tensor per
+    GAT_Net.forward call, rows ordered ((b*N + i)*(N-1) + s)  (nova/GAT_Net.py:85-93)."""
+    e = torch.empty(rows, 2).exponential_(generator=generator)
+    return gumbel_from_exponential(e)
+
+
+# ----------------------------------------------------------------------------------
+# a2  GAT_Net.forward  (nova/GAT_Net.py:41-142)
+# ----------------------------------------------------------------------------------
+
+def gat_forward(p, obs, h_prev, gumbel, tau=0.01, return_parts=False):
+    """obs [B, N, in], h_prev [B*N, D], gumbel [B, N, N-1, 2] -> new hidden [B*N, D].
+
+    Vectorised restatement; uses the factorised input projection
+    W_ih [h_i; h_j] = W_ih[:, :H] h_i + W_ih[:, H:] h_j  (SURVEY Appendix A)."""
+    B, N, _ = obs.shape
+    H = p["encoding.weight"].shape[0]
+    D = p["q.weight"].shape[0]
+    enc = F.relu(obs @ p["encoding.weight"].t() + p["encoding.bias"])            # :50
+    idx = neighbour_index(N)                                                     # [N, N-1]
+
+    outs = []
+    for sfx, order in (("", range(N - 1)), ("_reverse", range(N - 2, -1, -1))):  # :26, :83
+        w_ih = p["hard_bi_GRU.weight_ih_l0" + sfx]
+        w_hh = p["hard_bi_GRU.weight_hh_l0" + sfx]
+        b_ih = p["hard_bi_GRU.bias_ih_l0" + sfx]
+        b_hh = p["hard_bi_GRU.bias_hh_l0" + sfx]
+        ego = enc @ w_ih[:, :H].t() + b_ih                                       # [B, N, 3H]
+        nbr = enc @ w_ih[:, H:].t()                                              # [B, N, 3H]
+        h = torch.zeros(B, N, H)                                                 # :78
+        out = torch.empty(B, N, N - 1, H)
+        for s in order:
+            gi = ego + nbr[:, idx[:, s], :]
+            h = gru_cell(gi, h, w_hh, b_hh)
+            out[:, :, s] = h
+        outs.append(out)
+    hh = torch.cat(outs, dim=-1)                                                 # [B,N,N-1,2H]
+    logits = hh @ p["hard_encoding.weight"].t() + p["hard_encoding.bias"]        # :91
+    hard = torch.softmax((logits + gumbel) / tau, dim=-1)[..., 1]                # :93-95
+
+    h_out = enc.reshape(-1, H)
+    q = (h_out @ p["q.weight"].t()).view(B, N, D)                                # :101
+    k = (h_out @ p["k.weight"].t()).view(B, N, D)                                # :103
+    v = F.relu(h_out @ p["v.weight"].t() + p["v.bias"]).view(B, N, D)            # :105
+    score = torch.einsum("bid,bjd->bij", q, k) / float(math.sqrt(D))             # :123-126
+    score = torch.gather(score, 2, idx.unsqueeze(0).expand(B, -1, -1))           # drop j == i
+    soft = torch.softmax(score, dim=-1)                                          # :129
+    w = soft * hard                                                              # :132 (no renorm)
+    x = torch.einsum("bis,bisd->bid", w, v[:, idx, :])                           # [B, N, D]
+    x = x.reshape(-1, D)
+    gi = x @ p["rnn.weight_ih"].t() + p["rnn.bias_ih"]                           # :140 GRUCell
+    new_h = gru_cell(gi, h_prev, p["rnn.weight_hh"], p["rnn.bias_hh"])
+    if return_parts:
+        return new_h, dict(enc=enc, logits=logits, hard=hard, soft=soft, x=x)
+    return new_h
+
+
+def gat_forward_loops(p, obs, h_prev, gumbel, tau=0.01):
+    """Same result as ``gat_forward`` but executing the op sequence the reference
+    executes on the CPU (per-ego Python loops that cat/stack [h_i, h_j] pairs, one
+    bidirectional nn.GRU over the N-1 axis, per-ego attention loop:
+    nova/GAT_Net.py:57-75, :83, :107-133).  Used only as the timed CPU baseline,
+    because that op sequence — not the arithmetic — is where the reference spends
+    its time."""
+    B, N, _ = obs.shape
+    H = p["encoding.weight"].shape[0]
+    D = p["q.weight"].shape[0]
+    enc = F.relu(F.linear(obs, p["encoding.weight"], p["encoding.bias"]))
+    pair_seqs = []
+    for i in range(N):
+        ego = enc[:, i]
+        pairs = [torch.cat([ego, enc[:, j]], dim=-1) for j in range(N) if j != i]
+        pair_seqs.append(torch.stack(pairs, dim=0))
+    seq = torch.stack(pair_seqs, dim=-2).view(N - 1, -1, 2 * H)
+    flat = [p["hard_bi_GRU.weight_ih_l0"], p["hard_bi_GRU.weight_hh_l0"],
+            p["hard_bi_GRU.bias_ih_l0"], p["hard_bi_GRU.bias_hh_l0"],
+            p["hard_bi_GRU.weight_ih_l0_reverse"], p["hard_bi_GRU.weight_hh_l0_reverse"],
+            p["hard_bi_GRU.bias_ih_l0_reverse"], p["hard_bi_GRU.bias_hh_l0_reverse"]]
+    h0 = torch.zeros(2, B * N, H)
+    hh, _ = torch._VF.gru(seq, h0, flat, True, 1, 0.0, False, True, False)
+    hh = hh.permute(1, 0, 2).reshape(-1, 2 * H)
+    logits = F.linear(hh, p["hard_encoding.weight"], p["hard_encoding.bias"])
+    hard = torch.softmax((logits + gumbel.reshape(-1, 2)) / tau, dim=-1)[:, 1]
+    hard = hard.view(-1, N, 1, N - 1).permute(1, 0, 2, 3)
+    flat_enc = enc.reshape(-1, H)
+    q = F.linear(flat_enc, p["q.weight"]).reshape(-1, N, D)
+    k = F.linear(flat_enc, p["k.weight"]).reshape(-1, N, D)
+    v = F.relu(F.linear(flat_enc, p["v.weight"], p["v.bias"])).reshape(-1, N, D)
+    xs = []
+    for i in range(N):
+        q_i = q[:, i].view(-1, 1, D)
+        k_i = torch.stack([k[:, j] for j in range(N) if j != i], dim=0).permute(1, 2, 0)
+        v_i = torch.stack([v[:, j] for j in range(N) if j != i], dim=0).permute(1, 2, 0)
+        soft = torch.softmax(torch.matmul(q_i, k_i) / float(math.sqrt(D)), dim=-1)
+        xs.append((v_i * soft * hard[i]).sum(dim=-1))
+    x = torch.stack(xs, dim=1).reshape(-1, D)
+    gi = F.linear(x, p["rnn.weight_ih"], p["rnn.bias_ih"])
+    return gru_cell(gi, h_prev, p["rnn.weight_hh"], p["rnn.bias_hh"])
+
+
+def gat_latent_update(gat_params, history_single, encoder_hidden, behavior_latent, gumbel,
+                      loops=False):
+    """a1  Prediction_policy.GAT_latent_update (nova/prediction_policy.py:92-118).
+    history_single [B,A,N,o], encoder_hidden [B,A,N,D], behavior_latent [B,A,N,L],
+    gumbel [A,B,N,N-1,2] -> [B,A,N,D]."""
+    hs = torch.as_tensor(history_single, dtype=torch.float32)
+    eh = torch.as_tensor(encoder_hidden, dtype=torch.float32)
+    bl = torch.as_tensor(behavior_latent, dtype=torch.float32)
+    B, A, N, _ = hs.shape
+    D = eh.shape[-1]
+    fn = gat_forward_loops if loops else gat_forward
+    outs = []
+    for a in range(A):
+        x = torch.cat([hs[:, a], bl[:, a]], dim=-1)                              # :104-105
+        h = eh[:, a].reshape(B * N, D)                                           # :107-108
+        outs.append(fn(gat_params[a], x, h, gumbel[a]).view(B, 1, N, D))         # :110-113
+    return torch.cat(outs, dim=1)
+
+
+# ----------------------------------------------------------------------------------
+# a3  EncoderRNN.forward + Behavior_policy.latent_update
+# ----------------------------------------------------------------------------------
+
+def behavior_encoder(p, window, hidden):
+    """nova/behavior_net.py:17-22.  window [M, W, o], hidden [M, E] ->
+    (new hidden [M, E], latent [M, L])."""
+    u = F.relu(window @ p["linear.weight"].t() + p["linear.bias"])
+    h = hidden
+    for t in range(window.shape[1]):
+        gi = u[:, t] @ p["rnn.weight_ih_l0"].t() + p["rnn.bias_ih_l0"]
+        h = gru_cell(gi, h, p["rnn.weight_hh_l0"], p["rnn.bias_hh_l0"])
+    latent = torch.softmax(h @ p["out.weight"].t() + p["out.bias"], dim=-1)
+    return h, latent
+
+
+def behavior_latent_update(enc_params, history, encoder_hidden, prev_latent, coef=0.1):
+    """nova/stable_behavior_policy.py:83-123.  history [B,A,N,W,o],
+    encoder_hidden [B,1,A,N,E], prev_latent [B,A,N,L] ->
+    (new latent [B,A,N,L] = (1-coef)*prev + coef*latent, new hidden [B,1,A,N,E])."""
+    hist = torch.as_tensor(history, dtype=torch.float32)
+    hid = torch.as_tensor(encoder_hidden, dtype=torch.float32)
+    prev = torch.as_tensor(prev_latent, dtype=torch.float32)
+    B, A, N, W, o = hist.shape
+    E = hid.shape[-1]
+    lat, newh = [], []
+    for a in range(A):
+        h, z = behavior_encoder(enc_params[a], hist[:, a].reshape(B * N, W, o),
+                                hid[:, 0, a].reshape(B * N, E))
+        lat.append(z.view(B, 1, N, -1))
+        newh.append(h.view(B, 1, 1, N, E))
+    new_latent = torch.cat(lat, dim=1)
+    new_latent = (1 - coef) * prev + new_latent * coef                           # :118
+    return new_latent, torch.cat(newh, dim=2)
+
+
+# ----------------------------------------------------------------------------------
+# a4-a7  controller: input assembly, actor, critic
+# ----------------------------------------------------------------------------------
+
+def build_inputs_step(history, attention, behavior, last_onehot, n_agents):
+    """DcntrlMAC._build_inputs (controllers/dcntrl_controller.py:187-213) for one
+    timestep.  history [B,A,N,o], attention [B,A,N,D], behavior [B,A,N,L],
+    last_onehot [B,A,n_act] (zeros at t == 0) -> [B, A, F]."""
+    B = history.shape[0]
+    slots = torch.cat([history, attention, behavior], dim=-1).reshape(B, n_agents, -1)
+    eye = torch.eye(n_agents).unsqueeze(0).expand(B, -1, -1)
+    return torch.cat([slots, last_onehot.reshape(B, n_agents, -1), eye], dim=2)
+
+
+def build_inputs_train(agent_id, history, attention, behavior, actions_onehot, n_agents):
+    """DcntrlMAC._build_inputs_ippo (:87-115) for one agent, all timesteps.
+    history [Bf,T+1,N,o] ..., actions_onehot [Bf,T+1,n_act] -> [Bf, T+1, F].
+    Quirk kept: the "last action" at t = 0 is the action taken AT t = 0 (:107)."""
+    bs, ts = history.shape[:2]
+    slots = torch.cat([history, attention, behavior], dim=-1).reshape(bs, ts, -1)
+    last = torch.cat([actions_onehot[:, 0:1], actions_onehot[:, :-1]], dim=1)
+    ident = torch.zeros(bs, ts, n_agents)
+    ident[:, :, agent_id] = 1
+    return torch.cat([slots, last, ident], dim=-1)
+
+
+def trunk_forward(p, obs, h0):
+    """MLPBase + RNNLayer (utils/mappo_utils/mlp.py:50-56, :24-28; rnn.py:24-78) for
+    rows of length-1 sequences: obs [R, F], h0 [R, Rh] -> (features [R, Rh], h1 [R, Rh]).
+    ``fc_h`` exists in the state_dict but is never called (mlp.py:20-27)."""
+    x = F.layer_norm(obs, obs.shape[-1:], p["base.feature_norm.weight"],
+                     p["base.feature_norm.bias"], 1e-5)
+    x = F.relu(x @ p["base.mlp.fc1.0.weight"].t() + p["base.mlp.fc1.0.bias"])
+    x = F.layer_norm(x, x.shape[-1:], p["base.mlp.fc1.2.weight"], p["base.mlp.fc1.2.bias"], 1e-5)
+    x = F.relu(x @ p["base.mlp.fc2.0.0.weight"].t() + p["base.mlp.fc2.0.0.bias"])
+    x = F.layer_norm(x, x.shape[-1:], p["base.mlp.fc2.0.2.weight"], p["base.mlp.fc2.0.2.bias"], 1e-5)
+    gi = x @ p["rnn.rnn.weight_ih_l0"].t() + p["rnn.rnn.bias_ih_l0"]
+    h1 = gru_cell(gi, h0, p["rnn.rnn.weight_hh_l0"], p["rnn.rnn.bias_hh_l0"])
+    feat = F.layer_norm(h1, h1.shape[-1:], p["rnn.norm.weight"], p["rnn.norm.bias"], 1e-5)
+    return feat, h1
+
+
+def actor_logits(p, obs, h0, avail=None):
+    """R_Actor trunk + Categorical head (modules/agents/ippo_actor.py:43-72,
+    utils/mappo_utils/distributions.py:64-68): masked logits [R, n_act], h1."""
+    feat, h1 = trunk_forward(p, obs, h0)
+    logits = feat @ p["act.action_out.linear.weight"].t() + p["act.action_out.linear.bias"]
+    if avail is not None:
+        logits = torch.where(avail == 0, torch.full_like(logits, -1e10), logits)
+    return logits, h1
+
+
+def categorical_stats(logits, actions=None):
+    """torch.distributions.Categorical(logits=...) quantities used by
+    FixedCategorical (distributions.py:14-28): normalised log-probs, log_prob of
+    ``actions`` [R] and entropy [R]."""
+    logp_all = logits - logits.logsumexp(dim=-1, keepdim=True)
+    probs = logp_all.exp()
+    min_real = torch.finfo(logp_all.dtype).min
+    ent = -(torch.clamp(logp_all, min=min_real) * probs).sum(-1)
+    lp = None
+    if actions is not None:
+        lp = logp_all.gather(-1, actions.long().view(-1, 1)).squeeze(-1)
+    return logp_all, lp, ent
+
+
+def critic_value(p, obs, h0):
+    """R_Critic.forward (modules/critics/ippo_critic.py:47-65); PopArt is a plain
+    Linear here (utils/mappo_utils/popart.py:41-46)."""
+    feat, h1 = trunk_forward(p, obs, h0)
+    v = feat @ p["v_out.weight"].t() + p["v_out.bias"]
+    return v.squeeze(-1), h1
+
+
+def select_actions(actor_params, critic_params, inputs, avail, rnn_a, rnn_c,
+                   test_mode=False, uniforms=None):
+    """a5  DcntrlMAC.select_actions_ippo (controllers/dcntrl_controller.py:27-58) with
+    the sampling noise made explicit: ``uniforms`` [B, A] in [0,1) select the action by
+    inverse CDF over the probabilities (the reference samples with torch.multinomial;
+    parity tests compare logits / log-probs / values / hidden states and use
+    test_mode=True for the argmax path).  inputs [B,A,F], avail [B,A,n_act],
+    rnn_* [B,A,R] -> dict."""
+    B, A, _ = inputs.shape
+    out = dict(values=[], actions=[], logp=[], rnn_a=[], rnn_c=[], logits=[])
+    for a in range(A):
+        logits, h1 = actor_logits(actor_params[a], inputs[:, a], rnn_a[:, a], avail[:, a])
+        logp_all, _, _ = categorical_stats(logits)
+        probs = logp_all.exp()
+        if test_mode or uniforms is None:
+            act = probs.argmax(dim=-1)                                           # mode()
+        else:
+            cdf = probs.cumsum(-1)
+            act = (uniforms[:, a:a + 1] >= cdf).sum(-1).clamp(max=probs.shape[-1] - 1)
+        out["logits"].append(logits)
+        out["actions"].append(act)
+        out["logp"].append(logp_all.gather(-1, act.view(-1, 1)).squeeze(-1))
+        out["rnn_a"].append(h1)
+        v, hc = critic_value(critic_params[a], inputs[:, a], rnn_c[:, a])
+        out["values"].append(v)
+        out["rnn_c"].append(hc)
+    return {k: torch.stack(v, dim=1) for k, v in out.items()}
+
+
+# ----------------------------------------------------------------------------------
+# a11-a16  learner
+# ----------------------------------------------------------------------------------
+
+def gae_returns(values_all, rewards, alive_all, gamma=0.99, lam=0.95):
+    """IPPOLearner.compute_returns (learners/ippo_learner.py:344-365), GAE branch.
+    values_all [Bf,T+1], rewards [Bf,T], alive_all [Bf,T+1] -> returns [Bf,T]."""
+    T = rewards.shape[1]
+    ret = torch.empty_like(rewards)
+    gae = torch.zeros(rewards.shape[0])
+    for t in reversed(range(T)):
+        delta = rewards[:, t] + gamma * values_all[:, t + 1] * alive_all[:, t + 1] - values_all[:, t]
+        gae = delta + gamma * lam * alive_all[:, t + 1] * gae
+        ret[:, t] = gae + values_all[:, t]
+    return ret
+
+
+def normalised_advantages(returns, values, alive):
+    """learners/ippo_learner.py:272-279: zero where the agent is not alive, then
+    (x - mean) / (std + 1e-5) with the UNBIASED std over every entry incl. the zeros."""
+    adv = (returns - values).clone()
+    adv[alive == 0.0] = 0.0
+    std, mean = torch.std_mean(adv)
+    return (adv - mean) / (std + 1e-5)
+
+
+def huber_one_sided(e, d):
+    """utils/mappo_utils/util.py:33-36 — as written: e < -d contributes 0."""
+    a = (e.abs() <= d).float()
+    b = (e > d).float()
+    return a * e ** 2 / 2 + b * d * (e.abs() - d / 2)
+
+
+def policy_loss_terms(logp, old_logp, adv, alive, clip=0.2):
+    """learners/ippo_learner.py:185-197."""
+    ratio = torch.exp(logp - old_logp)
+    surr1 = ratio * adv
+    surr2 = torch.clamp(ratio, 1.0 - clip, 1.0 + clip) * adv
+    loss = (-torch.min(surr1, surr2) * alive).sum() / alive.sum()
+    return loss, ratio
+
+
+def value_loss_terms(values, old_values, returns, alive, clip=0.2, delta=10.0):
+    """IPPOLearner.cal_value_loss (learners/ippo_learner.py:128-159), huber + clipped
+    + active masks."""
+    v_clip = old_values + (values - old_values).clamp(-clip, clip)
+    l_clip = huber_one_sided(returns - v_clip, delta)
+    l_orig = huber_one_sided(returns - values, delta)
+    loss = torch.max(l_orig, l_clip)
+    return (loss * alive).sum() / alive.sum()
+
+
+ACTOR_TRAINABLE = [
+    "base.feature_norm.weight", "base.feature_norm.bias",
+    "base.mlp.fc1.0.weight", "base.mlp.fc1.0.bias", "base.mlp.fc1.2.weight", "base.mlp.fc1.2.bias",
+    "base.mlp.fc2.0.0.weight", "base.mlp.fc2.0.0.bias", "base.mlp.fc2.0.2.weight", "base.mlp.fc2.0.2.bias",
+    "rnn.rnn.weight_ih_l0", "rnn.rnn.weight_hh_l0", "rnn.rnn.bias_ih_l0", "rnn.rnn.bias_hh_l0",
+    "rnn.norm.weight", "rnn.norm.bias",
+    "act.action_out.linear.weight", "act.action_out.linear.bias",
+]
+CRITIC_TRAINABLE = ACTOR_TRAINABLE[:-2] + ["v_out.weight", "v_out.bias"]
+
+
+class AdamState:
+    """torch.optim.Adam(lr, eps, betas=(0.9, 0.999), wd=0) restated on a list of
+    tensors (learners/ippo_learner.py:74-81); bias correction as torch does it:
+    step_size = lr / (1 - b1^t); denom = sqrt(v) / sqrt(1 - b2^t) + eps."""
+
+    def __init__(self, params, lr, eps, b1=0.9, b2=0.999):
+        self.params, self.lr, self.eps, self.b1, self.b2 = params, lr, eps, b1, b2
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.t = 0
+
+    def step(self, grads):
+        self.t += 1
+        bc1 = 1 - self.b1 ** self.t
+        bc2 = 1 - self.b2 ** self.t
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            m.mul_(self.b1).add_(g, alpha=1 - self.b1)
+            v.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+            denom = (v.sqrt() / math.sqrt(bc2)).add_(self.eps)
+            p.addcdiv_(m, denom, value=-self.lr / bc1)
+
+
+def clip_grads(grads, max_norm):
+    """nn.utils.clip_grad_norm_ (learners/ippo_learner.py:205, :219): total 2-norm,
+    scale by max_norm / (norm + 1e-6) clamped to 1."""
+    total = torch.sqrt(sum((g.detach() ** 2).sum() for g in grads))
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return [g * coef for g in grads], total
+
+
+def train_agent(actor_p, critic_p, batch, agent_id, args, opt_a=None, opt_c=None,
+                perms=None):
+    """One agent's share of IPPOLearner.train (learners/ippo_learner.py:249-312).
+
+    ``batch`` holds the per-agent SeparatedReplayBuffer.get_batch() tensors
+    (utils/mappo_utils/separated_buffer.py:71-94): history [Bf,T+1,N,o],
+    attention_latent, behavior_latent, actions [Bf,T+1,1] (long), actions_onehot,
+    available_actions, reward [Bf,T+1,1], terminated_masks [Bf,T+1,1] (alive = 1),
+    rnn_states_actor / rnn_states_critic [Bf,T+1,R].
+    Updates ``actor_p`` / ``critic_p`` in place; returns per-update stats and the
+    pre-update tensors (returns, advantages, old log-probs, values)."""
+    T = args.episode_limit
+    nb = args.batch_size                      # episodes actually trained on (:371)
+    rows = nb * T
+    obs_all = build_inputs_train(agent_id, batch["history"], batch["attention_latent"],
+                                 batch["behavior_latent"], batch["actions_onehot"], args.n_agents)
+    Bf = obs_all.shape[0]
+    Fdim = obs_all.shape[-1]
+    alive_all = batch["terminated_masks"].squeeze(-1).float()
+    rewards = batch["reward"][:, :-1].squeeze(-1)
+    actions = batch["actions"][:, :-1].squeeze(-1)
+    avail = batch["available_actions"][:, :-1]
+    rnn_a = batch["rnn_states_actor"][:, :-1]
+    rnn_c_all = batch["rnn_states_critic"]
+
+    with torch.no_grad():
+        v_all, _ = critic_value(critic_p, obs_all.reshape(-1, Fdim), rnn_c_all.reshape(-1, rnn_c_all.shape[-1]))
+        v_all = v_all.view(Bf, T + 1)
+        returns = gae_returns(v_all, rewards, alive_all, args.gamma, args.gae_lambda)
+        cur_v = v_all[:, :T]
+        alive = alive_all[:, :T]
+        adv = normalised_advantages(returns, cur_v, alive)
+        obs = obs_all[:, :T].reshape(-1, Fdim)
+        logits, _ = actor_logits(actor_p, obs, rnn_a.reshape(-1, rnn_a.shape[-1]),
+                                 avail.reshape(-1, avail.shape[-1]))
+        _, old_lp, _ = categorical_stats(logits, actions.reshape(-1))
+
+    a_tr = [actor_p[k].requires_grad_(True) for k in ACTOR_TRAINABLE]
+    c_tr = [critic_p[k].requires_grad_(True) for k in CRITIC_TRAINABLE]
+    opt_a = opt_a or AdamState(a_tr, args.lr, args.optim_eps)
+    opt_c = opt_c or AdamState(c_tr, args.critic_lr, args.optim_eps)
+
+    flat = dict(obs=obs, rnn_a=rnn_a.reshape(Bf * T, -1), rnn_c=rnn_c_all[:, :T].reshape(Bf * T, -1),
+                act=actions.reshape(-1), avail=avail.reshape(Bf * T, -1),
+                ret=returns.reshape(-1), alive=alive.reshape(-1), old_lp=old_lp,
+                adv=adv.reshape(-1), old_v=cur_v.reshape(-1))
+    stats = []
+    for ep in range(args.ppo_epoch):
+        # generate_data (:368-424): one minibatch = a permutation of the first
+        # batch_size*T rows; available_actions loses its LAST EPISODE (:394) which is
+        # consistent with indices < batch_size*T when batch_size <= Bf - 1.
+        idx = perms[ep] if perms is not None else torch.randperm(rows)
+        mb = {k: v[idx] for k, v in flat.items()}
+        logits, _ = actor_logits(actor_p, mb["obs"], mb["rnn_a"], mb["avail"])
+        _, lp, ent = categorical_stats(logits, mb["act"])
+        ent_mean = ent.mean()                                                    # act.py:164 (unmasked)
+        values, _ = critic_value(critic_p, mb["obs"], mb["rnn_c"])
+        pol_loss, ratio = policy_loss_terms(lp, mb["old_lp"], mb["adv"], mb["alive"], args.clip_param)
+        g_a = torch.autograd.grad(pol_loss - ent_mean * args.entropy_coef, a_tr)
+        g_a, n_a = clip_grads(g_a, args.max_grad_norm)
+        v_loss = value_loss_terms(values, mb["old_v"], mb["ret"], mb["alive"],
+                                  args.clip_param, args.huber_delta)
+        g_c = torch.autograd.grad(v_loss * args.value_loss_coef, c_tr)
+        g_c, n_c = clip_grads(g_c, args.max_grad_norm)
+        with torch.no_grad():
+            opt_a.step(g_a)
+            opt_c.step(g_c)
+        stats.append(dict(value_loss=v_loss.item(), policy_loss=pol_loss.item(),
+                          dist_entropy=ent_mean.item(), actor_grad_norm=n_a.item(),
+                          critic_grad_norm=n_c.item(), ratio=ratio.mean().item()))
+    for t in a_tr + c_tr:
+        t.requires_grad_(False)
+    pre = dict(values_all=v_all, returns=returns, advantages=adv, old_logp=old_lp.view(Bf, T))
+    return stats, pre, opt_a, opt_c
