@@ -1,0 +1,123 @@
+/*
+ * iplan_b200 — C ABI of the B200-native iPLAN hot path (libiplan_b200.so).
+ *
+ * The reference (wuxiyang1996/iPLAN) has no FFI layer: its operator boundary is
+ * the Python object API of Prediction_policy / Behavior_policy / DcntrlMAC /
+ * IPPOLearner.  The host-side mirrors of those classes live in
+ * iplan_b200/ (Python, same names and signatures) and bind the entry points
+ * below with ctypes; every entry point names the reference function it replaces.
+ *
+ * Conventions
+ *  - plain C: device pointers, sizes, a CUDA stream handle (void* == cudaStream_t);
+ *    no torch types.  All tensors fp32 unless stated; all pointers DEVICE memory.
+ *  - every call is asynchronous on `stream`; return value 0 == OK, otherwise a
+ *    cudaError_t / negative argument-check code; iplan_last_error() has the text.
+ *  - "view" = base pointer + element strides, so the same kernel reads either the
+ *    reference's [B, A, N, *] staging layout or the packed episode store.
+ */
+#ifndef IPLAN_B200_H
+#define IPLAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPLAN_ABI_VERSION 1
+#define IPLAN_MAX_SLOTS 64        /* N  (max_vehicle_num) supported by the GAT kernel */
+#define IPLAN_HID 32              /* GAT_hidden_dim == attention_dim == encoder_rnn_dim */
+#define IPLAN_RNN 64              /* rnn_hidden_dim == mlp_hidden_dim */
+#define IPLAN_MAX_ACT 8           /* n_actions upper bound */
+
+/* element [agent][env][slot][0..dim) of a strided fp32 array */
+typedef struct {
+    float*  ptr;
+    int64_t stride_agent;
+    int64_t stride_env;
+    int64_t stride_slot;
+} iplan_view;
+
+int         iplan_abi_version(void);
+const char* iplan_last_error(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t     iplan_launch_count(void);
+
+/* ---- flat parameter layouts ---------------------------------------------------
+ * Each network's parameters are one fp32 buffer per agent: the module's
+ * state_dict tensors in state_dict order, each tensor start rounded up to a
+ * multiple of 4 floats.  The functions return the per-agent length and fill
+ * `offsets` (one per tensor, in floats). */
+#define IPLAN_GAT_NTENSORS 20     /* nova/GAT_Net.py:18-39 */
+#define IPLAN_BEH_NTENSORS 8      /* nova/behavior_net.py:12-15 */
+#define IPLAN_ACTOR_NTENSORS 22   /* modules/agents/ippo_actor.py:32-40 */
+#define IPLAN_CRITIC_NTENSORS 26  /* modules/critics/ippo_critic.py:32-43 (+4 PopArt buffers) */
+int64_t iplan_gat_layout(int in_dim, int64_t* offsets);
+int64_t iplan_beh_layout(int obs_dim, int latent_dim, int64_t* offsets);
+int64_t iplan_actor_layout(int feat_dim, int n_actions, int64_t* offsets);
+int64_t iplan_critic_layout(int feat_dim, int64_t* offsets);
+
+/* ---- K1: fused GAT step --------------------------------------------------------
+ * replaces Prediction_policy.GAT_latent_update (nova/prediction_policy.py:92-118)
+ * = per agent-net GAT_Net.forward (nova/GAT_Net.py:41-142): encode, hard attention
+ * (bidirectional GRU over the N-1 neighbours, gumbel-softmax tau), soft attention,
+ * GRUCell.  One CTA per (env, agent-net).
+ *   hist      [a][b][n][obs_dim]      history_single at time t
+ *   beh_prev  [a][b][n][latent_dim]   behaviour latent of time t-1
+ *   h_prev    [a][b][n][32]           attention latent of time t-1
+ *   out       [a][b][n][32]           attention latent of time t (may alias nothing)
+ *   gumbel    NULL -> in-kernel Philox logistic noise keyed by (seed, counter);
+ *             else [A][B][N][N-1][2] gumbel pairs (parity mode, reference draw order)
+ *   dbg_hard  NULL or [A][B][N][N-1] hard-attention weights (debug/parity) */
+int iplan_gat_step(const float* gat_params, int64_t param_stride,
+                   iplan_view hist, iplan_view beh_prev, iplan_view h_prev, iplan_view out,
+                   const float* gumbel, uint64_t seed, uint64_t counter,
+                   float tau, float* dbg_hard,
+                   int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
+                   void* stream);
+
+/* ---- K1b: behaviour-encoder step -----------------------------------------------
+ * replaces Behavior_policy.latent_update (nova/stable_behavior_policy.py:83-123)
+ * = EncoderRNN.forward (nova/behavior_net.py:17-22) over the history window from the
+ * carried hidden state, softmax latent, soft update (1-c)*prev + c*new.
+ *   window    [a][b][n][hist_len*obs_dim]
+ *   hid_io    [a][b][n][32]  GRU hidden, updated in place
+ *   lat_prev  [a][b][n][latent_dim];  lat_out likewise (may alias lat_prev) */
+int iplan_behavior_step(const float* beh_params, int64_t param_stride,
+                        iplan_view window, iplan_view hid_io, iplan_view lat_prev, iplan_view lat_out,
+                        float soft_coef,
+                        int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int hist_len,
+                        void* stream);
+
+/* ---- K1c: controller step (actor + critic, one timestep) -------------------------
+ * replaces DcntrlMAC.select_actions_ippo (controllers/dcntrl_controller.py:27-58):
+ * LayerNorm(F) -> fc1 -> ReLU -> LN -> fc2 -> ReLU -> LN -> 1-step GRU -> LN ->
+ * Categorical head (masked logits, sample / mode, log-prob) and value head.
+ *   feat      [A][B][row_stride] controller input rows (feature order of
+ *             _build_inputs, :187-213), row pitch `feat_stride_env`, agent pitch
+ *             `feat_stride_agent` (floats)
+ *   rnn_*_in/out  [A][B][64] with the given agent/env strides (separate for in and out)
+ *   avail     NULL (all available) or uint8 [A][B][n_actions]
+ *   uniforms  NULL -> Philox(seed, counter); else [A][B] in [0,1) (parity mode)
+ *   greedy    1 -> mode() (test_mode=True)
+ *   outputs   actions int32 [A][B], logp [A][B], values [A][B], logits [A][B][n_actions] (or NULL)
+ *   next_onehot  NULL or pointer to the last-action columns of the NEXT timestep's
+ *             rows (same strides as feat); the chosen action's one-hot is written there */
+int iplan_controller_step(const float* actor_params, int64_t actor_stride,
+                          const float* critic_params, int64_t critic_stride,
+                          const float* feat, int64_t feat_stride_agent, int64_t feat_stride_env,
+                          const float* rnn_a_in, const float* rnn_c_in,
+                          float* rnn_a_out, float* rnn_c_out,
+                          int64_t rnn_stride_agent, int64_t rnn_stride_env,
+                          int64_t rnn_out_stride_agent, int64_t rnn_out_stride_env,
+                          const uint8_t* avail, const float* uniforms,
+                          uint64_t seed, uint64_t counter, int greedy,
+                          int32_t* actions, float* logp, float* values, float* logits,
+                          float* next_onehot, float* this_onehot,
+                          int n_envs, int n_agents, int feat_dim, int n_actions,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPLAN_B200_H */

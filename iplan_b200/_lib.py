@@ -1,0 +1,94 @@
+"""ctypes binding of libiplan_b200.so (include/iplan_b200.h).
+
+The CUDA library is the product: there is NO fallback.  If the shared object is
+missing this module raises at import; if a call fails it raises RuntimeError with
+the library's error text.  torch is used only for device memory and streams.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "build", "libiplan_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise RuntimeError(
+        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(or `make -C iplan_b200/csrc`).  iplan_b200 has no CPU / PyTorch fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+
+class View(C.Structure):
+    """iplan_view: element [agent][env][slot][0..dim) of a strided fp32 array."""
+    _fields_ = [("ptr", C.c_void_p), ("stride_agent", C.c_int64),
+                ("stride_env", C.c_int64), ("stride_slot", C.c_int64)]
+
+
+_p, _i, _i64, _u64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
+
+_SIGNATURES = {
+    "iplan_abi_version": (C.c_int, []),
+    "iplan_last_error": (C.c_char_p, []),
+    "iplan_launch_count": (_i64, []),
+    "iplan_gat_layout": (_i64, [_i, _p]),
+    "iplan_beh_layout": (_i64, [_i, _i, _p]),
+    "iplan_actor_layout": (_i64, [_i, _i, _p]),
+    "iplan_critic_layout": (_i64, [_i, _p]),
+    "iplan_gat_step": (_i, [_p, _i64, View, View, View, View, _p, _u64, _u64, _f, _p,
+                            _i, _i, _i, _i, _i, _p]),
+    "iplan_behavior_step": (_i, [_p, _i64, View, View, View, View, _f, _i, _i, _i, _i, _i, _i, _p]),
+    "iplan_controller_step": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64,
+                                   _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p,
+                                   _i, _i, _i, _i, _p]),
+}
+
+
+def _bind(signatures):
+    for name, (res, args) in signatures.items():
+        fn = getattr(lib, name)         # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+
+
+_bind(_SIGNATURES)
+
+ABI_VERSION = lib.iplan_abi_version()
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise RuntimeError(f"iplan_b200 {what} failed (rc={rc}): {lib.iplan_last_error().decode()}")
+
+
+def launch_count():
+    return int(lib.iplan_launch_count())
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda, "iplan_b200 kernels take CUDA tensors only"
+    return C.c_void_p(t.data_ptr())
+
+
+def view(t):
+    """[A, B, N, dim] fp32 CUDA tensor (any strides, innermost contiguous) -> iplan_view."""
+    assert t.is_cuda and t.dtype == torch.float32 and t.dim() == 4, (t.shape, t.dtype, t.device)
+    assert t.stride(3) == 1 or t.shape[3] == 1, "innermost dimension must be contiguous"
+    return View(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def layout(kind, *dims):
+    """(total floats per agent, [offsets]) of a flat parameter buffer."""
+    n = {"gat": 20, "beh": 8, "actor": 22, "critic": 26}[kind]
+    arr = (C.c_int64 * n)()
+    fn = getattr(lib, f"iplan_{kind}_layout")
+    total = fn(*dims, C.cast(arr, C.c_void_p))
+    return int(total), [int(x) for x in arr]

@@ -1,0 +1,272 @@
+// K1c — controller step: actor and critic forward for one timestep.
+//
+// Replaces DcntrlMAC.select_actions_ippo (reference controllers/dcntrl_controller.py:27-58):
+// per agent  R_Actor.forward (modules/agents/ippo_actor.py:43-72) and R_Critic.forward
+// (modules/critics/ippo_critic.py:47-65), i.e. for both nets
+//   LN(F) -> Linear(F,64) -> ReLU -> LN -> Linear(64,64) -> ReLU -> LN      (mlp.py:24-56)
+//   -> 1-step GRU(64) from the stored hidden -> LN                             (rnn.py:24-78)
+//   actor: Linear(64,n_act), logits[avail==0] = -1e10, Categorical sample/mode, log-prob
+//          (act.py:81-85, distributions.py:14-28,64-68);  critic: Linear(64,1) (popart.py:41-46)
+// One CTA handles CTRL_ROWS envs of one agent; both nets share the staged input rows.
+#include "common.cuh"
+
+namespace iplan {
+
+constexpr int R = IPLAN_RNN;            // 64
+constexpr int CTRL_THREADS = 256;
+constexpr int CTRL_WARPS = CTRL_THREADS / 32;
+constexpr int CTRL_ROWS = 8;
+constexpr float LN_EPS = 1e-5f;
+
+struct CtrlArgs {
+    const float* actor; int64_t actor_stride;
+    const float* critic; int64_t critic_stride;
+    const float* feat; int64_t feat_sa, feat_se;
+    const float* rnn_a_in; const float* rnn_c_in; float* rnn_a_out; float* rnn_c_out;
+    int64_t rnn_sa, rnn_se, rnn_osa, rnn_ose;
+    const uint8_t* avail; const float* uniforms;
+    uint64_t seed, counter; int greedy;
+    int32_t* actions; float* logp; float* values; float* logits;
+    float* next_onehot; float* this_onehot;
+    int n_envs, feat_dim, feat_ld, n_actions;
+};
+
+// y[k] = b[k] + sum_j W[k][j] * x[j]  for one output row k (64 inputs, x in shared memory)
+__device__ __forceinline__ float dot64(const float* __restrict__ wrow, const float* x, float acc) {
+    const float4* w4 = reinterpret_cast<const float4*>(wrow);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+#pragma unroll
+    for (int q = 0; q < R / 4; ++q) {
+        const float4 w = __ldg(w4 + q);
+        const float4 v = x4[q];
+        acc = fmaf(w.x, v.x, acc); acc = fmaf(w.y, v.y, acc);
+        acc = fmaf(w.z, v.z, acc); acc = fmaf(w.w, v.w, acc);
+    }
+    return acc;
+}
+
+// LayerNorm over 64 features held as (v0 = feature lane, v1 = feature lane+32)
+__device__ __forceinline__ void ln64(float& v0, float& v1, const float* __restrict__ g, const float* __restrict__ bta, int lane) {
+    const float mean = warp_sum(v0 + v1) * (1.0f / R);
+    const float d0 = v0 - mean, d1 = v1 - mean;
+    const float var = warp_sum(d0 * d0 + d1 * d1) * (1.0f / R);
+    const float rstd = 1.0f / sqrtf(var + LN_EPS);
+    v0 = d0 * rstd * g[lane] + bta[lane];
+    v1 = d1 * rstd * g[lane + 32] + bta[lane + 32];
+}
+
+__global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int ag = blockIdx.y, b0 = blockIdx.x * CTRL_ROWS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int F = a.feat_dim, LD = a.feat_ld;
+    float* s_x = smem;                          // [ROWS][LD] raw rows
+    float* s_y = s_x + CTRL_ROWS * LD;          // [ROWS][LD] normalised rows for the current net
+    float* s_z = s_y + CTRL_ROWS * LD;          // [2][ROWS][64] fc1 pre-activations
+    float* s_act = s_z + 2 * CTRL_ROWS * R;     // [2*ROWS][64] per-task activation buffer
+    float* s_h0 = s_act + 2 * CTRL_ROWS * R;    // [2*ROWS][64] per-task hidden input
+    float* s_stat = s_h0 + 2 * CTRL_ROWS * R;   // [ROWS][2] mean, rstd
+
+    // ---- stage rows, LayerNorm statistics over the F input features -----------------
+    for (int r = 0; r < CTRL_ROWS; ++r) {
+        const int b = min(b0 + r, a.n_envs - 1);
+        const float* src = a.feat + ag * a.feat_sa + b * a.feat_se;
+        for (int f = tid; f < LD; f += CTRL_THREADS) s_x[r * LD + f] = f < F ? src[f] : 0.0f;
+    }
+    __syncthreads();
+    {
+        const int r = warp;                     // CTRL_WARPS == CTRL_ROWS
+        float s = 0.0f;
+        for (int f = lane; f < F; f += 32) s += s_x[r * LD + f];
+        const float mean = warp_sum(s) / (float)F;
+        float v = 0.0f;
+        for (int f = lane; f < F; f += 32) { const float d = s_x[r * LD + f] - mean; v = fmaf(d, d, v); }
+        const float var = warp_sum(v) / (float)F;
+        if (lane == 0) { s_stat[2 * r] = mean; s_stat[2 * r + 1] = 1.0f / sqrtf(var + LN_EPS); }
+    }
+    __syncthreads();
+
+    // ---- fc1 for both nets ------------------------------------------------------------
+    for (int net = 0; net < 2; ++net) {
+        const float* P = net == 0 ? a.actor + (int64_t)ag * a.actor_stride : a.critic + (int64_t)ag * a.critic_stride;
+        const TrunkLayout L = trunk_layout(F, net == 0 ? a.n_actions : 1, net == 1);
+        for (int f = tid; f < LD; f += CTRL_THREADS) {
+            const float g = f < F ? P[L.ln0_w + f] : 0.0f;
+            const float bt = f < F ? P[L.ln0_b + f] : 0.0f;
+#pragma unroll
+            for (int r = 0; r < CTRL_ROWS; ++r)
+                s_y[r * LD + f] = (s_x[r * LD + f] - s_stat[2 * r]) * s_stat[2 * r + 1] * g + bt;
+        }
+        __syncthreads();
+        float acc[8][CTRL_ROWS];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int r = 0; r < CTRL_ROWS; ++r) acc[k][r] = 0.0f;
+        const float* w1 = P + L.fc1_w + (int64_t)(warp * 8) * F;
+        for (int f = lane; f < F; f += 32) {
+            float yv[CTRL_ROWS];
+#pragma unroll
+            for (int r = 0; r < CTRL_ROWS; ++r) yv[r] = s_y[r * LD + f];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float w = __ldg(w1 + (int64_t)k * F + f);
+#pragma unroll
+                for (int r = 0; r < CTRL_ROWS; ++r) acc[k][r] = fmaf(w, yv[r], acc[k][r]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int r = 0; r < CTRL_ROWS; ++r) {
+                const float t = warp_sum(acc[k][r]);
+                if (lane == 0) s_z[(net * CTRL_ROWS + r) * R + warp * 8 + k] = t + P[L.fc1_b + warp * 8 + k];
+            }
+        __syncthreads();
+    }
+
+    // ---- tails: 2*ROWS (net,row) tasks, one warp each ---------------------------------
+    for (int task = warp; task < 2 * CTRL_ROWS; task += CTRL_WARPS) {
+        const int net = task / CTRL_ROWS, r = task % CTRL_ROWS;
+        const int b = b0 + r;
+        const bool live = b < a.n_envs;          // warp-uniform
+        const int bc = live ? b : a.n_envs - 1;
+        const float* P = net == 0 ? a.actor + (int64_t)ag * a.actor_stride : a.critic + (int64_t)ag * a.critic_stride;
+        const TrunkLayout L = trunk_layout(F, net == 0 ? a.n_actions : 1, net == 1);
+        float* act = s_act + task * R;
+        float* h0 = s_h0 + task * R;
+        const float* hin = (net == 0 ? a.rnn_a_in : a.rnn_c_in) + ag * a.rnn_sa + bc * a.rnn_se;
+        h0[lane] = hin[lane]; h0[lane + 32] = hin[lane + 32];
+
+        float v0 = fmaxf(s_z[task * R + lane], 0.0f), v1 = fmaxf(s_z[task * R + lane + 32], 0.0f);
+        ln64(v0, v1, P + L.ln1_w, P + L.ln1_b, lane);
+        act[lane] = v0; act[lane + 32] = v1;
+        __syncwarp();
+        v0 = fmaxf(dot64(P + L.fc2_w + lane * R, act, P[L.fc2_b + lane]), 0.0f);
+        v1 = fmaxf(dot64(P + L.fc2_w + (lane + 32) * R, act, P[L.fc2_b + lane + 32]), 0.0f);
+        ln64(v0, v1, P + L.ln2_w, P + L.ln2_b, lane);
+        __syncwarp();
+        act[lane] = v0; act[lane + 32] = v1;
+        __syncwarp();
+        // GRU step: hidden units c = lane, lane+32; gate rows r: c, z: 64+c, n: 128+c
+        float hn[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = lane + 32 * u;
+            const float gi_r = dot64(P + L.wih + (c) * R, act, P[L.bih + c]);
+            const float gi_z = dot64(P + L.wih + (R + c) * R, act, P[L.bih + R + c]);
+            const float gi_n = dot64(P + L.wih + (2 * R + c) * R, act, P[L.bih + 2 * R + c]);
+            const float gh_r = dot64(P + L.whh + (c) * R, h0, P[L.bhh + c]);
+            const float gh_z = dot64(P + L.whh + (R + c) * R, h0, P[L.bhh + R + c]);
+            const float gh_n = dot64(P + L.whh + (2 * R + c) * R, h0, P[L.bhh + 2 * R + c]);
+            const float rg = sigmoidf_acc(gi_r + gh_r);
+            const float zg = sigmoidf_acc(gi_z + gh_z);
+            const float ng = tanhf_acc(gi_n + rg * gh_n);
+            hn[u] = (1.0f - zg) * ng + zg * h0[c];
+        }
+        if (live) {
+            float* hout = (net == 0 ? a.rnn_a_out : a.rnn_c_out) + ag * a.rnn_osa + b * a.rnn_ose;
+            hout[lane] = hn[0]; hout[lane + 32] = hn[1];
+        }
+        v0 = hn[0]; v1 = hn[1];
+        ln64(v0, v1, P + L.ln3_w, P + L.ln3_b, lane);
+        __syncwarp();
+        act[lane] = v0; act[lane + 32] = v1;
+        __syncwarp();
+        const int64_t ob = (int64_t)ag * a.n_envs + bc;
+        if (net == 1) {
+            const float val = warp_sum(v0 * P[L.head_w + lane] + v1 * P[L.head_w + lane + 32]) + P[L.head_b];
+            if (live && lane == 0) a.values[ob] = val;
+        } else {
+            const int nA = a.n_actions;
+            float lg = -INFINITY;
+            if (lane < nA) {
+                lg = dot64(P + L.head_w + lane * R, act, P[L.head_b + lane]);
+                if (a.avail && a.avail[ob * nA + lane] == 0) lg = -1e10f;
+            }
+            const float mx = warp_max(lg);
+            const float ex = lane < nA ? expf(lg - mx) : 0.0f;
+            const float den = warp_sum(ex);
+            const float lp = lg - mx - logf(den);            // log-softmax
+            const float pr = lane < nA ? expf(lp) : 0.0f;
+            int action;
+            if (a.greedy) {
+                const float pmx = warp_max(pr);
+                const unsigned m = __ballot_sync(0xffffffffu, lane < nA && pr == pmx);
+                action = __ffs(m) - 1;                       // first maximal index (argmax)
+            } else {
+                float uu;
+                if (a.uniforms) uu = a.uniforms[ob];
+                else {
+                    const uint4 rnd = philox4x32(make_uint4((uint32_t)ob, (uint32_t)(ob >> 32), (uint32_t)a.counter,
+                                                            (uint32_t)(a.counter >> 32)),
+                                                 make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32) ^ 0x5bd1e995u));
+                    uu = u01(rnd.x);
+                }
+                float cdf = pr;                              // inclusive scan over the first lanes
+#pragma unroll
+                for (int o = 1; o < IPLAN_MAX_ACT; o <<= 1) {
+                    const float t = __shfl_up_sync(0xffffffffu, cdf, o);
+                    if (lane >= o) cdf += t;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, lane < nA && uu >= cdf);
+                action = min(__popc(m), nA - 1);
+            }
+            const float lp_a = __shfl_sync(0xffffffffu, lp, action);
+            if (live) {
+                if (lane == 0) { a.actions[ob] = action; a.logp[ob] = lp_a; }
+                if (a.logits && lane < nA) a.logits[ob * nA + lane] = lg;
+                if (lane < nA) {
+                    const float oh = lane == action ? 1.0f : 0.0f;
+                    if (a.next_onehot) a.next_onehot[ag * a.feat_sa + b * a.feat_se + lane] = oh;
+                    if (a.this_onehot) a.this_onehot[ag * a.feat_sa + b * a.feat_se + lane] = oh;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace iplan
+
+extern "C" int iplan_controller_step(const float* actor_params, int64_t actor_stride,
+                                     const float* critic_params, int64_t critic_stride,
+                                     const float* feat, int64_t feat_stride_agent, int64_t feat_stride_env,
+                                     const float* rnn_a_in, const float* rnn_c_in,
+                                     float* rnn_a_out, float* rnn_c_out,
+                                     int64_t rnn_stride_agent, int64_t rnn_stride_env,
+                                     int64_t rnn_out_stride_agent, int64_t rnn_out_stride_env,
+                                     const uint8_t* avail, const float* uniforms,
+                                     uint64_t seed, uint64_t counter, int greedy,
+                                     int32_t* actions, float* logp, float* values, float* logits,
+                                     float* next_onehot, float* this_onehot,
+                                     int n_envs, int n_agents, int feat_dim, int n_actions,
+                                     void* stream) {
+    using namespace iplan;
+    IPLAN_REQUIRE(n_actions > 0 && n_actions <= IPLAN_MAX_ACT, "controller_step: n_actions %d not in [1,%d]", n_actions, IPLAN_MAX_ACT);
+    IPLAN_REQUIRE(n_envs > 0 && n_agents > 0 && n_agents <= 65535 && feat_dim > 0, "controller_step: bad sizes");
+    IPLAN_REQUIRE(actor_params && critic_params && feat && rnn_a_in && rnn_c_in && rnn_a_out && rnn_c_out && actions && logp && values,
+                  "controller_step: null pointer");
+    CtrlArgs a;
+    a.actor = actor_params; a.actor_stride = actor_stride; a.critic = critic_params; a.critic_stride = critic_stride;
+    a.feat = feat; a.feat_sa = feat_stride_agent; a.feat_se = feat_stride_env;
+    a.rnn_a_in = rnn_a_in; a.rnn_c_in = rnn_c_in; a.rnn_a_out = rnn_a_out; a.rnn_c_out = rnn_c_out;
+    a.rnn_sa = rnn_stride_agent; a.rnn_se = rnn_stride_env;
+    a.rnn_osa = rnn_out_stride_agent; a.rnn_ose = rnn_out_stride_env;
+    a.avail = avail; a.uniforms = uniforms; a.seed = seed; a.counter = counter; a.greedy = greedy;
+    a.actions = actions; a.logp = logp; a.values = values; a.logits = logits;
+    a.next_onehot = next_onehot; a.this_onehot = this_onehot;
+    a.n_envs = n_envs; a.feat_dim = feat_dim; a.feat_ld = (feat_dim + 3) & ~3; a.n_actions = n_actions;
+    const size_t smem = ((size_t)2 * CTRL_ROWS * a.feat_ld + 6 * CTRL_ROWS * R + 2 * CTRL_ROWS) * sizeof(float);
+    IPLAN_REQUIRE(smem <= 227 * 1024, "controller_step: feat_dim %d needs %zu B of shared memory", feat_dim, smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(controller_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("controller_step: smem attr %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
+        configured = smem;
+    }
+    dim3 grid((n_envs + CTRL_ROWS - 1) / CTRL_ROWS, n_agents);
+    controller_step_kernel<<<grid, CTRL_THREADS, smem, (cudaStream_t)stream>>>(a);
+    count_launch();
+    return check_launch("controller_step");
+}

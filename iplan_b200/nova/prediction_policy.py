@@ -1,0 +1,91 @@
+"""Instant-incentive (GAT) module — host-side mirror of the reference's
+``Prediction_policy`` (/root/reference/nova/prediction_policy.py:14-118) for the rollout
+entry point ``GAT_latent_update``; the arithmetic is kernel K1 (csrc/gat_step.cu).
+
+Same constructor, same ``GAT_latent_update(history_single, encoder_hidden,
+behavior_latent) -> np.float32 [B, A, N, D]`` contract, same ``pred_GAT[i]`` modules
+(state_dict keys/shapes) and ``pred_GAT_{i}.th`` checkpoint files.  The auxiliary
+trajectory-prediction learner (``learn``, reference :168-253) is a "next" row of the
+scope table and is not built.
+"""
+import copy
+import os
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..modules.flat import ParamStack
+
+
+class Prediction_policy:
+    def __init__(self, args, logger=None):
+        self.device = torch.device("cuda" if args.use_cuda else "cpu")
+        if self.device.type != "cuda":
+            raise RuntimeError("iplan_b200.Prediction_policy runs on CUDA only (no CPU path); set args.use_cuda=True")
+        self.args = args
+        self.logger = logger
+        self.n_agents = args.n_agents
+        self.max_vehicle_num = args.max_vehicle_num
+        self.obs_shape = args.obs_shape_single
+        if not getattr(args, "GAT_use_behavior", True):
+            raise NotImplementedError("only the full iPLAN setting (GAT_use_behavior=True) is built")
+        assert args.GAT_hidden_dim == 32 and args.attention_dim == 32, "kernel K1 is built for H = D = 32"
+        self.GAT_input_dim = args.obs_shape_single + args.latent_dim          # reference :53-56
+        self.stack = ParamStack("gat", self.n_agents, (self.GAT_input_dim,), device=self.device)
+        self.pred_GAT = self.stack.nets
+        self.tau = 0.01                                                       # nova/GAT_Net.py:93
+        self.seed = int(getattr(args, "seed", 112358))
+        self.calls = 0              # Philox counter: a fresh noise stream per call
+        self.debug_gumbel = None    # [A,B,N,N-1,2] explicit gumbel noise for the next call (parity tests)
+        self.capture_hard = False   # keep the hard-attention weights of the last call in .last_hard
+        self.last_hard = None
+
+    # ---- device path: tensors laid out [A, B, N, *] (any strides) ------------------
+    def gat_step(self, hist, beh_prev, h_prev, out, gumbel=None, dbg_hard=None):
+        """out[a,b,n,:] = GAT_a(hist[a,b], beh_prev[a,b], h_prev[a,b]); all CUDA fp32."""
+        A, B, N, o = hist.shape
+        if gumbel is not None:
+            assert gumbel.is_contiguous() and tuple(gumbel.shape) == (A, B, N, N - 1, 2), gumbel.shape
+        rc = _lib.lib.iplan_gat_step(
+            _lib.ptr(self.stack.flat), self.stack.stride(),
+            _lib.view(hist), _lib.view(beh_prev), _lib.view(h_prev), _lib.view(out),
+            _lib.ptr(gumbel), self.seed, self.calls, self.tau, _lib.ptr(dbg_hard),
+            B, A, N, o, beh_prev.shape[-1], _lib.stream())
+        _lib.check(rc, "gat_step")
+        self.calls += 1
+        return out
+
+    # ---- reference-compatible numpy entry point (reference :92-118) -----------------
+    def GAT_latent_update(self, history_single, encoder_hidden, behavior_latent=None):
+        dev = self.device
+        hs = torch.as_tensor(np.asarray(history_single), dtype=torch.float32).to(dev, non_blocking=True)
+        eh = torch.as_tensor(np.asarray(encoder_hidden), dtype=torch.float32).to(dev, non_blocking=True)
+        bl = torch.as_tensor(np.asarray(behavior_latent), dtype=torch.float32).to(dev, non_blocking=True)
+        out = torch.empty_like(eh)
+        perm = (1, 0, 2, 3)       # [B,A,N,*] -> [A,B,N,*] views, no copy
+        gum = self.debug_gumbel
+        self.debug_gumbel = None
+        dbg = None
+        if self.capture_hard:
+            B, A, N, _ = hs.shape
+            dbg = torch.zeros(A, B, N, N - 1, device=dev)
+            self.last_hard = dbg
+        self.gat_step(hs.permute(perm), bl.permute(perm), eh.permute(perm), out.permute(perm), gum, dbg)
+        return out.cpu().numpy()
+
+    def learn(self, batch, t_env):
+        raise NotImplementedError("Prediction_policy.learn (aux trajectory-prediction loss, reference "
+                                  "nova/prediction_policy.py:168-253) is outside the built hot path (SURVEY §8f)")
+
+    # ---- checkpoints (reference :256-285) ----------------------------------------
+    def save_models(self, path):
+        for i, net in enumerate(self.pred_GAT):
+            torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/pred_GAT_{i}.th")
+
+    def load_models(self, paths, load_optimisers=False):
+        if len(paths) == 1:
+            paths = [copy.copy(paths[0]) for _ in range(self.n_agents)]
+        for i, net in enumerate(self.pred_GAT):
+            net.load_state_dict(torch.load(os.path.join(paths[i], f"pred_GAT_{i}.th"),
+                                           map_location="cpu", weights_only=False))

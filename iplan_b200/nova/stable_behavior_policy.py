@@ -1,0 +1,81 @@
+"""Behavioural-incentive module (soft-update variant = iPLAN) — host-side mirror of the
+reference's ``Behavior_policy`` (/root/reference/nova/stable_behavior_policy.py:13-123) for
+the rollout entry point ``latent_update``; the arithmetic is kernel K1b
+(csrc/behavior_step.cu).
+
+Same constructor, same ``latent_update(history, encoder_hidden, prev_latent) ->
+(np latent [B,A,N,L], torch hidden [B,1,A,N,E])`` contract (the reference returns the
+hidden state as a torch tensor and accepts numpy on the first call / a tensor
+afterwards, :101-121), same ``behavior_encoder[i]`` state_dict keys and
+``behavior_encoder_{i}.th`` files.  The auxiliary reconstruction learner (``learn``,
+reference :161-279) is a "next" row of the scope table and is not built.
+"""
+import copy
+import os
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..modules.flat import ParamStack
+
+
+class Behavior_policy:
+    def __init__(self, args, logger=None):
+        self.device = torch.device("cuda" if args.use_cuda else "cpu")
+        if self.device.type != "cuda":
+            raise RuntimeError("iplan_b200.Behavior_policy runs on CUDA only (no CPU path); set args.use_cuda=True")
+        self.args = args
+        self.logger = logger
+        self.n_agents = args.n_agents
+        self.max_vehicle_num = args.max_vehicle_num
+        self.max_history_len = args.max_history_len
+        self.latent_dim = args.latent_dim
+        self.soft_update_coef = args.soft_update_coef
+        assert args.encoder_rnn_dim == 32 and args.num_encoder_layer == 1, "kernel K1b is built for E = 32, one layer"
+        self.stack = ParamStack("beh", self.n_agents, (args.obs_shape_single, args.latent_dim), device=self.device)
+        self.behavior_encoder = self.stack.nets
+
+    # ---- device path: tensors laid out [A, B, N, *] ----------------------------------
+    def behavior_step(self, window, hid_io, lat_prev, lat_out):
+        """window [A,B,N,W*o], hid_io [A,B,N,E] (in place), lat_prev/lat_out [A,B,N,L]."""
+        A, B, N, _ = window.shape
+        rc = _lib.lib.iplan_behavior_step(
+            _lib.ptr(self.stack.flat), self.stack.stride(),
+            _lib.view(window), _lib.view(hid_io), _lib.view(lat_prev), _lib.view(lat_out),
+            float(self.soft_update_coef), B, A, N, self.args.obs_shape_single, self.latent_dim,
+            self.max_history_len, _lib.stream())
+        _lib.check(rc, "behavior_step")
+        return lat_out, hid_io
+
+    # ---- reference-compatible entry point (reference :83-123) -------------------------
+    def latent_update(self, history, encoder_hidden, prev_latent):
+        dev = self.device
+        hist = torch.as_tensor(np.asarray(history), dtype=torch.float32).to(dev, non_blocking=True)
+        B, A, N, W, o = hist.shape
+        if torch.is_tensor(encoder_hidden):
+            hid = encoder_hidden.detach().to(dev, torch.float32).clone()
+        else:
+            hid = torch.as_tensor(np.asarray(encoder_hidden), dtype=torch.float32).to(dev)
+        prev = torch.as_tensor(np.asarray(prev_latent), dtype=torch.float32).to(dev, non_blocking=True)
+        new = torch.empty_like(prev)
+        hid_v = hid[:, 0].permute(1, 0, 2, 3)                    # [B,1,A,N,E] -> [A,B,N,E] view
+        self.behavior_step(hist.reshape(B, A, N, W * o).permute(1, 0, 2, 3), hid_v,
+                           prev.permute(1, 0, 2, 3), new.permute(1, 0, 2, 3))
+        return new.cpu().numpy(), hid
+
+    def learn(self, batch, t_env):
+        raise NotImplementedError("Behavior_policy.learn (aux reconstruction loss, reference "
+                                  "nova/stable_behavior_policy.py:161-279) is outside the built hot path (SURVEY §8f)")
+
+    # ---- checkpoints (reference :282-312) -------------------------------------------
+    def save_models(self, path):
+        for i, net in enumerate(self.behavior_encoder):
+            torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/behavior_encoder_{i}.th")
+
+    def load_models(self, paths, load_optimisers=False):
+        if len(paths) == 1:
+            paths = [copy.copy(paths[0]) for _ in range(self.n_agents)]
+        for i, net in enumerate(self.behavior_encoder):
+            net.load_state_dict(torch.load(os.path.join(paths[i], f"behavior_encoder_{i}.th"),
+                                           map_location="cpu", weights_only=False))

@@ -1,0 +1,79 @@
+"""CPU-side checks of the C-ABI library: it loads without a GPU, exports every symbol
+include/iplan_b200.h declares, and its parameter layouts agree with the host-side
+module specs.  No compute calls."""
+import ctypes
+import os
+import re
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from iplan_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "iplan_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(iplan_[a-z0-9_]+)\s*\(", header))
+    assert len(names) >= 10
+    for n in sorted(names):
+        assert hasattr(_lib.lib, n), f"{n} declared in include/iplan_b200.h but not exported"
+        assert n in _lib._SIGNATURES, f"{n} has no ctypes signature in iplan_b200/_lib.py"
+    assert _lib.ABI_VERSION == int(re.search(r"#define IPLAN_ABI_VERSION (\d+)", header).group(1))
+
+
+def test_layouts_match_module_specs():
+    from iplan_b200.modules.flat import ParamStack
+    for kind, dims in (("gat", (13,)), ("beh", (5, 8)), ("actor", (2485, 5)), ("critic", (2485,)),
+                       ("actor", (272, 5)), ("gat", (12,))):
+        s = ParamStack(kind, 2, dims)
+        end = 0
+        for (name, shape), off in zip(s.spec, s.offsets):
+            n = 1
+            for d in shape:
+                n *= d
+            assert off % 4 == 0 and off >= end, (kind, name)
+            end = off + n
+        assert end <= s.total and s.total % 4 == 0
+        sd = s.nets[1].state_dict()
+        assert [k for k in sd] == [n for n, _ in s.spec]
+    # parameter counts of the reference modules
+    a = ParamStack("actor", 1, (2485, 5))
+    assert sum(p.numel() for p in a.nets[0].parameters()) == 198191
+    c = ParamStack("critic", 1, (2485,))
+    assert sum(p.numel() for p in c.nets[0].parameters()) == 197935      # incl. 4 frozen PopArt scalars
+    g = ParamStack("gat", 1, (13,))
+    assert sum(p.numel() for p in g.nets[0].parameters()) == 28834
+
+
+def test_state_dict_roundtrip_with_reference_checkpoint_format(tmp_path, golden_dir):
+    from iplan_b200.modules.flat import ParamStack
+    g = torch.load(os.path.join(golden_dir, "rollout_modules.pt"), weights_only=False)["mpe"]
+    s = ParamStack("critic", 3, (272,))
+    s.nets[2].load_state_dict(g["critics"][2])
+    torch.save(s.nets[2].state_dict(), tmp_path / "critic_2.th")
+    back = torch.load(tmp_path / "critic_2.th", weights_only=False)
+    for k, v in g["critics"][2].items():
+        assert torch.equal(back[k], v), k
+
+
+def test_episode_batch_cpu_semantics():
+    """Non-packed (CPU) EpisodeBatch keeps the reference's update/view_as/filled semantics."""
+    from iplan_b200.components.episode_buffer import EpisodeBatch
+    from iplan_b200.components.transforms import OneHot
+    scheme = {"actions": {"vshape": (1,), "group": "agents", "dtype": torch.long},
+              "rnn": {"vshape": (4,), "group": "agents"}, "reward": {"vshape": (1,), "group": "agents"}}
+    b = EpisodeBatch(scheme, {"agents": 2}, 3, 5, preprocess={"actions": ("actions_onehot", [OneHot(3)])})
+    b.update({"rnn": torch.arange(24.).view(1, 3, 2, 4)}, ts=1)         # [1,B,A,R] -> [B,1,A,R]
+    assert torch.equal(b["rnn"][:, 1], torch.arange(24.).view(3, 2, 4))
+    assert b["filled"][:, 1].sum() == 3 and b["filled"].sum() == 3 and int(b.max_t_filled()) == 1
+    b.update({"actions": [[1, 2], [0, 0], [2, 1]]}, ts=0, mark_filled=False)
+    assert b["actions_onehot"][0, 0].tolist() == [[0, 1, 0], [0, 0, 1]]
+    assert b["filled"].sum() == 3
+    sub = b[1:3, 0:2]
+    assert sub.batch_size == 2 and sub.max_seq_length == 2 and sub["rnn"].shape == (2, 2, 2, 4)
+    try:
+        b.update({"nope": 1})
+        assert False
+    except KeyError:
+        pass

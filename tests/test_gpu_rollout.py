@@ -1,0 +1,254 @@
+"""Parity of the CUDA rollout kernels (K1 GAT, K1b behaviour encoder, K1c controller),
+called through the reference-facing classes / the C ABI, against
+ (1) the committed golden outputs of the reference's own modules, and
+ (2) the CPU oracle on seeded inputs at the Highway shape.
+Tolerance: 1e-4 (north_star: logits / values within 1e-4 rel fp32)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def maxdiff(a, b):
+    a = torch.as_tensor(np.asarray(a.detach().cpu()) if torch.is_tensor(a) else np.asarray(a)).double()
+    b = torch.as_tensor(np.asarray(b.detach().cpu()) if torch.is_tensor(b) else np.asarray(b)).double()
+    return float((a - b).abs().max())
+
+
+def args_from(d, **over):
+    from iplan_b200.config import make_args
+    env = d.get("env", "highway")
+    a = make_args(env)
+    for k, v in d.items():
+        setattr(a, k, v)
+    a.use_cuda, a.device = True, "cuda"
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+def make_scheme(args):
+    from iplan_b200.components.transforms import OneHot
+    scheme = {
+        "state": {"vshape": args.state_shape},
+        "obs": {"vshape": args.obs_shape, "group": "agents"},
+        "actions": {"vshape": (1,), "group": "agents", "dtype": torch.long},
+        "rnn_states_actors": {"vshape": (args.rnn_hidden_dim,), "group": "agents"},
+        "rnn_states_critics": {"vshape": (args.rnn_hidden_dim,), "group": "agents"},
+        "history": {"vshape": (args.max_vehicle_num, args.obs_shape_single,), "group": "agents"},
+        "behavior_latent": {"vshape": (args.max_vehicle_num, args.latent_dim,), "group": "agents"},
+        "attention_latent": {"vshape": (args.max_vehicle_num, args.attention_dim,), "group": "agents"},
+        "avail_actions": {"vshape": (args.n_actions,), "group": "agents", "dtype": torch.int},
+        "reward": {"vshape": (1,), "group": "agents"},
+        "speed": {"vshape": (1,), "group": "agents"},
+        "terminated": {"vshape": (1,), "group": "agents", "dtype": torch.uint8},
+    }
+    return scheme, {"agents": args.n_agents}, {"actions": ("actions_onehot", [OneHot(out_dim=args.n_actions)])}
+
+
+# ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["mpe", "highway"])
+def test_gat_kernel_vs_reference_golden(golden_dir, case):
+    """GAT_Net.forward golden (one agent-net) through the raw C ABI."""
+    _need_gpu()
+    from iplan_b200 import _lib
+    from iplan_b200.modules.flat import ParamStack
+    g = load(golden_dir, "gat_net.pt")[case]
+    d = g["dims"]
+    B, N, o, L, D = d["B"], d["N"], d["o"], d["L"], d["D"]
+    stack = ParamStack("gat", 1, (o + L,), device="cuda")
+    stack.nets[0].load_state_dict(g["params"])
+    obs = g["obs"].cuda()
+    hist = obs[..., :o].contiguous().view(1, B, N, o)
+    beh = obs[..., o:].contiguous().view(1, B, N, L)
+    hprev = g["h_prev"].cuda().view(1, B, N, D)
+    out = torch.zeros(1, B, N, D, device="cuda")
+    hard = torch.zeros(1, B, N, N - 1, device="cuda")
+    gum = g["gumbel"].cuda().view(1, B, N, N - 1, 2).contiguous()
+    rc = _lib.lib.iplan_gat_step(_lib.ptr(stack.flat), stack.stride(), _lib.view(hist), _lib.view(beh),
+                                 _lib.view(hprev), _lib.view(out), _lib.ptr(gum), 1, 0, 0.01, _lib.ptr(hard),
+                                 B, 1, N, o, L, _lib.stream())
+    _lib.check(rc, "gat_step")
+    torch.cuda.synchronize()
+    from oracle import iplan_oracle as O
+    _, parts = O.gat_forward(g["params"], g["obs"], g["h_prev"], g["gumbel"], return_parts=True)
+    dh = maxdiff(hard.view(B, N, N - 1), parts["hard"])
+    dout = maxdiff(out.view(B * N, D), g["out"])
+    print(f"[gat {case}] max|hard diff|={dh:.3e} max|out diff|={dout:.3e}")
+    assert dout < TOL, (dh, dout)
+
+
+def test_rollout_modules_vs_reference_golden(golden_dir):
+    """Prediction_policy.GAT_latent_update -> Behavior_policy.latent_update ->
+    EpisodeBatch.update -> DcntrlMAC.select_actions_ippo, three consecutive steps, both
+    golden cases, through the reference-facing numpy API."""
+    _need_gpu()
+    from iplan_b200.components.episode_buffer import EpisodeBatch
+    from iplan_b200.controllers.dcntrl_controller import DcntrlMAC
+    from iplan_b200.nova.prediction_policy import Prediction_policy
+    from iplan_b200.nova.stable_behavior_policy import Behavior_policy
+    for case in ("mpe", "highway"):
+        g = load(golden_dir, "rollout_modules.pt")[case]
+        args = args_from(g["args"])
+        A = args.n_agents
+        B = args.batch_size_run
+        T = args.episode_limit
+        pred, beh = Prediction_policy(args, None), Behavior_policy(args, None)
+        scheme, groups, pre = make_scheme(args)
+        batch = EpisodeBatch(scheme, groups, B, T + 1, preprocess=pre, device="cuda")
+        mac = DcntrlMAC(batch.scheme, groups, args)
+        for i in range(A):
+            pred.pred_GAT[i].load_state_dict(g["gat"][i])
+            beh.behavior_encoder[i].load_state_dict(g["beh"][i])
+            mac.agents[i].load_state_dict(g["actors"][i])
+            mac.critics[i].load_state_dict(g["critics"][i])
+        assert batch.packed is not None
+        for t, st in enumerate(g["steps"]):
+            pred.debug_gumbel = st["gumbel"].cuda().contiguous()
+            att = pred.GAT_latent_update(st["history_single"], st["att_in"], st["beh_in"])
+            d_att = maxdiff(att, st["att_out"])
+            beh_now = st["beh_in"]
+            d_beh = d_hid = 0.0
+            if "beh_out" in st:
+                beh_now, hid = beh.latent_update(st["window"], st["enc_rnn_in"], st["beh_in"])
+                d_beh, d_hid = maxdiff(beh_now, st["beh_out"]), maxdiff(hid, st["enc_rnn_out"])
+            batch.update({"avail_actions": g["avail"], "rnn_states_actors": st["rnn_a_in"],
+                          "rnn_states_critics": st["rnn_c_in"], "history": st["history_single"],
+                          "behavior_latent": st["beh_out"] if "beh_out" in st else st["beh_in"],
+                          "attention_latent": st["att_out"]}, ts=t)
+            # the packed rows must equal the reference's _build_inputs output
+            F = mac.input_shape
+            rows = batch.packed[:, :, t, :F].permute(1, 0, 2)
+            d_in = maxdiff(rows, st["inputs"])
+            mac.capture_logits = True
+            values, actions, logps, rnn_a, rnn_c = mac.select_actions_ippo(batch, t_ep=t, test_mode=True)
+            d_v = maxdiff(values, st["values"])
+            d_lp = maxdiff(torch.cat(logps, dim=1), st["logp"].reshape(B, A))
+            d_ra, d_rc = maxdiff(rnn_a, st["rnn_a_out"]), maxdiff(rnn_c, st["rnn_c_out"])
+            print(f"[rollout {case} t={t}] att {d_att:.2e} beh {d_beh:.2e} hid {d_hid:.2e} in {d_in:.2e} "
+                  f"val {d_v:.2e} logp {d_lp:.2e} rnn {d_ra:.2e}/{d_rc:.2e}")
+            assert d_att < TOL and d_beh < TOL and d_hid < TOL and d_in < 1e-6
+            assert d_v < TOL and d_lp < TOL and d_ra < TOL and d_rc < TOL
+            assert (actions == st["actions"]).all()
+            assert rnn_a.shape == st["rnn_a_out"].shape and values.shape == st["values"].shape
+            batch.update({"actions": st["actions"]}, ts=t, mark_filled=False)
+
+
+def test_gat_highway_shape_vs_oracle():
+    """B=6 envs x 5 agent-nets x 55 slots (Highway), seeded inputs, explicit noise:
+    CUDA vs the CPU oracle.  Reports ill-conditioned edges (hard weight strictly inside
+    (0.01, 0.99)) separately, as SURVEY §7 asks."""
+    _need_gpu()
+    from iplan_b200.config import make_args
+    from iplan_b200.nova.prediction_policy import Prediction_policy
+    from oracle import iplan_oracle as O
+    args = make_args("highway")
+    B, A, N, o, L, D = 6, args.n_agents, args.max_vehicle_num, args.obs_shape_single, args.latent_dim, args.attention_dim
+    torch.manual_seed(5)
+    pred = Prediction_policy(args, None)
+    params = [{k: v.detach().cpu().clone() for k, v in net.state_dict().items()} for net in pred.pred_GAT]
+    rng = np.random.default_rng(3)
+    hist = rng.uniform(-1, 1, size=(B, A, N, o)).astype(np.float32)
+    hist[..., 0] = 1.0
+    hist[:, :, 30:] = 0.0
+    beh = rng.dirichlet(np.ones(L), size=(B, A, N)).astype(np.float32)
+    att = rng.uniform(-1, 1, size=(B, A, N, D)).astype(np.float32)
+    gum = torch.stack([O.draw_gumbel(B * N * (N - 1)).view(B, N, N - 1, 2) for _ in range(A)])
+    ref = O.gat_latent_update(params, hist, att, beh, gum)
+    pred.debug_gumbel = gum.cuda().contiguous()
+    pred.capture_hard = True
+    out = pred.GAT_latent_update(hist, att, beh)
+    d = np.abs(out - ref.numpy())
+    hard = pred.last_hard.cpu()
+    frac_mid = float(((hard > 0.01) & (hard < 0.99)).float().mean())
+    print(f"[gat highway] max {d.max():.3e} mean {d.mean():.3e} ill-conditioned edge fraction {frac_mid:.4f}")
+    assert out.dtype == np.float32 and out.shape == (B, A, N, D)
+    assert d.max() < TOL
+    # production noise path: statistically the same gate-open rate as the parity path
+    pred.debug_gumbel = None
+    out2 = pred.GAT_latent_update(hist, att, beh)
+    hard2 = pred.last_hard.cpu()
+    assert np.isfinite(out2).all()
+    assert abs(float(hard2.mean()) - float(hard.mean())) < 0.02
+
+
+def test_behavior_and_controller_highway_shape_vs_oracle():
+    _need_gpu()
+    from iplan_b200.config import controller_input_dim, make_args
+    from iplan_b200.controllers.dcntrl_controller import DcntrlMAC
+    from iplan_b200.nova.stable_behavior_policy import Behavior_policy
+    from oracle import iplan_oracle as O
+    args = make_args("highway")
+    B, A, N, o, L, E, W = 19, args.n_agents, args.max_vehicle_num, args.obs_shape_single, args.latent_dim, 32, args.max_history_len
+    torch.manual_seed(11)
+    beh = Behavior_policy(args, None)
+    bp = [{k: v.detach().cpu().clone() for k, v in net.state_dict().items()} for net in beh.behavior_encoder]
+    rng = np.random.default_rng(8)
+    window = rng.uniform(-1, 1, size=(B, A, N, W, o))
+    hid = rng.uniform(-1, 1, size=(B, 1, A, N, E)).astype(np.float32)
+    prev = rng.dirichlet(np.ones(L), size=(B, A, N)).astype(np.float32)
+    ref_lat, ref_hid = O.behavior_latent_update(bp, window, hid, prev)
+    lat, new_hid = beh.latent_update(window, hid, prev)
+    assert torch.is_tensor(new_hid) and tuple(new_hid.shape) == (B, 1, A, N, E)
+    assert maxdiff(lat, ref_lat) < TOL and maxdiff(new_hid, ref_hid) < TOL
+
+    scheme, groups, pre = make_scheme(args)
+    from iplan_b200.components.episode_buffer import EpisodeBatch
+    batch = EpisodeBatch(scheme, groups, B, 3, preprocess=pre, device="cuda")
+    mac = DcntrlMAC(batch.scheme, groups, args)
+    F = controller_input_dim(args)
+    assert mac.input_shape == F == 2485
+    with torch.no_grad():
+        for net in mac.agents:
+            net.act.action_out.linear.weight.mul_(50.0)
+        mac.actor_stack.flat[:, :2 * F].uniform_(0.5, 1.5)        # feature_norm weight|bias away from (1, 0)
+        mac.critic_stack.flat[:, :2 * F].uniform_(0.5, 1.5)
+    ap = [{k: v.detach().cpu().clone() for k, v in n.state_dict().items()} for n in mac.agents]
+    cp = [{k: v.detach().cpu().clone() for k, v in n.state_dict().items()} for n in mac.critics]
+    x = torch.tensor(rng.uniform(-1, 1, size=(B, A, F)).astype(np.float32))
+    x[..., 700:1500] = 0.0
+    feat = x.permute(1, 0, 2).contiguous().cuda()
+    ra = torch.tensor(rng.uniform(-1, 1, size=(B, A, 64)).astype(np.float32))
+    rc_ = torch.tensor(rng.uniform(-1, 1, size=(B, A, 64)).astype(np.float32))
+    avail = torch.ones(B, A, args.n_actions, dtype=torch.int64)
+    avail[3, 1, 2] = 0
+    uni = torch.tensor(rng.uniform(0, 1, size=(B, A)).astype(np.float32))
+    ref = O.select_actions(ap, cp, x, avail, ra, rc_, test_mode=False, uniforms=uni)
+    na, nc = torch.empty(A, B, 64, device="cuda"), torch.empty(A, B, 64, device="cuda")
+    logits = torch.empty(A, B, args.n_actions, device="cuda")
+    actions, logp, values = mac.controller_step(
+        feat, ra.permute(1, 0, 2).contiguous().cuda(), rc_.permute(1, 0, 2).contiguous().cuda(), na, nc,
+        (avail != 0).permute(1, 0, 2).contiguous().to(torch.uint8).cuda(), test_mode=False,
+        uniforms=uni.t().contiguous().cuda(), logits=logits)
+    torch.cuda.synchronize()
+    keep = ref["logits"] > -1e9
+    assert maxdiff(logits.permute(1, 0, 2).cpu()[keep], ref["logits"][keep]) < TOL
+    assert maxdiff(values.t(), ref["values"]) < TOL
+    assert maxdiff(na.permute(1, 0, 2), ref["rnn_a"]) < TOL and maxdiff(nc.permute(1, 0, 2), ref["rnn_c"]) < TOL
+    same = (actions.t().cpu().long() == ref["actions"])
+    assert same.float().mean() > 0.97          # a uniform within 1e-6 of a CDF edge may flip
+    assert maxdiff(logp.t().cpu()[same], ref["logp"][same]) < TOL
+
+
+def test_argument_checks_fail_loudly():
+    _need_gpu()
+    from iplan_b200 import _lib
+    z = _lib.View(0, 0, 0, 0)
+    rc = _lib.lib.iplan_gat_step(None, 0, z, z, z, z, None, 0, 0, 0.01, None, 1, 1, 200, 5, 8, None)
+    assert rc != 0 and b"n_slots" in _lib.lib.iplan_last_error()
+    with pytest.raises(RuntimeError):
+        _lib.check(rc, "gat_step")
