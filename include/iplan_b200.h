@@ -117,6 +117,69 @@ int iplan_controller_step(const float* actor_params, int64_t actor_stride,
                           int n_envs, int n_agents, int feat_dim, int n_actions,
                           void* stream);
 
+/* ==== IPPO learner (IPPOLearner.train, learners/ippo_learner.py:227-317) ===============
+ * All agents are processed together.  Agent a's input matrix is X_a[rows][ldx] with
+ * rows = n_eps*(T+1), row (b,t) at index b*(T+1)+t — the packed EpisodeBatch layout.
+ * Gradient buffers have the SAME flat layout as the parameter buffers. */
+
+/* LayerNorm(F) statistics of every input row (parameter-free; once per train()):
+ * stat [A][rows][2] = (mean, 1/sqrt(var+1e-5)).  utils/mappo_utils/mlp.py:45,51 */
+int iplan_learner_row_stats(const float* X, int64_t x_stride_agent, int ldx, int feat_dim, int64_t rows,
+                            int n_agents, float* stat, void* stream);
+
+/* feature LayerNorm + fc1 of actor and critic as ONE product over X (mlp.py:50-56):
+ * Z1 [A][rows][128] (actor 0..63 | critic 64..127).  Wp [A][128][ldx], ws/cc [A][128] scratch. */
+int iplan_learner_fc1_forward(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
+                              const float* X, int64_t x_stride_agent, int ldx, int feat_dim, int64_t rows, int n_agents,
+                              const float* stat, float* Wp, float* ws, float* cc, float* Z1, void* stream);
+
+typedef struct {
+    const float* actor; const float* critic; int64_t actor_stride, critic_stride;   /* parameters */
+    float* g_actor; float* g_critic;                                                /* gradients (train) */
+    int feat_dim, n_actions, n_agents, T1, n_eps, n_train_eps;
+    const float* rnn_a; const float* rnn_c; int64_t rnn_stride_agent; int rnn_ld;   /* stored GRU inputs [a][row][64] */
+    const int32_t* actions;        /* [A][rows] */
+    const uint8_t* avail;          /* NULL or [A][rows][n_actions] */
+    float* Z1; float* A1; float* Z2; float* A2; float* GI; float* GH;  /* work: [A][rows][128], 3x[A][2][rows][64], 2x[A][2][rows][192] */
+    const float* stat; float* SM;  /* row stats; [A][2][128] scratch (zeroed by the caller each epoch) */
+    float* logp_out; float* ent_out; float* value_out;                  /* eval outputs [A][rows] (NULL ok) */
+    const float* old_logp; const float* old_value; const float* returns; const float* adv_raw; const float* alive; /* [A][rows] */
+    const float* norm;             /* [A][4] from iplan_learner_adv_finalize */
+    float* stats;                  /* [A][8] += policy loss, value loss, entropy, ratio, actor |g|, critic |g| */
+    float clip, ent_coef, v_coef, huber_delta;
+} iplan_learner_ctx;
+
+/* Z1 -> LN/ReLU -> fc2 -> LN/ReLU -> GRU step -> LN -> heads (R_Actor.evaluate_actions,
+ * ippo_actor.py:74-102; R_Critic.forward, ippo_critic.py:47-65).
+ * train == 0: writes logp_out / ent_out / value_out.
+ * train != 0: K2b — fuses the PPO losses (ppo_update :185-197, cal_value_loss :128-159,
+ *   entropy bonus) with their backward; leaves dZ1*rstd in Z1 and every gradient except
+ *   fc1.weight / feature_norm in g_actor / g_critic. */
+int iplan_learner_tail(const iplan_learner_ctx* ctx, int train, void* stream);
+
+/* fc1.weight and feature_norm gradients from dZ1 (left in Z1 by the train tail). G [A][128][ldx] scratch. */
+int iplan_learner_fc1_backward(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
+                               float* g_actor, float* g_critic,
+                               const float* X, int64_t x_stride_agent, int ldx, int feat_dim, int64_t rows, int n_agents,
+                               const float* dZ1, const float* SM, float* G, void* stream);
+
+/* K2a: GAE backward scan (compute_returns :344-365), raw advantages zeroed where the agent is
+ * dead (:273-277) and their moments: moments [A][4] = (sum, sum of squares, count, sum of
+ * alive over the training rows) in double — all-reduce them across ranks, then finalise:
+ * norm [A][4] = (mean, 1/(unbiased std + 1e-5), 1/sum alive, 1/n_train_rows_global)  (:278-279) */
+int iplan_learner_gae(const float* values, const float* reward, const float* alive, float gamma, float lam,
+                      int T1, int n_eps, int n_train_eps, int n_agents,
+                      float* returns, float* adv_raw, double* moments, void* stream);
+int iplan_learner_adv_finalize(const double* moments, double n_train_rows_global, float* norm, int n_agents, void* stream);
+
+/* clip_grad_norm_(max_norm) + torch.optim.Adam step (:205-223, :74-81) on a flat [A][total]
+ * buffer; `mask` [total] is 1 where the optimiser owns the value. Adds the pre-clip norm to
+ * stats[a][stat_col] when stats != NULL. */
+int iplan_learner_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* mask,
+                       float* sqnorm_scratch, int64_t stride, int64_t total, int n_agents,
+                       float lr, float beta1, float beta2, float eps, int step, float max_norm,
+                       float* stats, int stat_col, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,7 +42,29 @@ _SIGNATURES = {
     "iplan_controller_step": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64,
                                    _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p,
                                    _i, _i, _i, _i, _p]),
+    "iplan_learner_row_stats": (_i, [_p, _i64, _i, _i, _i64, _i, _p, _p]),
+    "iplan_learner_fc1_forward": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "iplan_learner_tail": (_i, [_p, _i, _p]),
+    "iplan_learner_fc1_backward": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p]),
+    "iplan_learner_gae": (_i, [_p, _p, _p, _f, _f, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "iplan_learner_adv_finalize": (_i, [_p, C.c_double, _p, _i, _p]),
+    "iplan_learner_adam": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _f, _f, _i, _f, _p, _i, _p]),
 }
+
+
+class LearnerCtx(C.Structure):
+    """iplan_learner_ctx (include/iplan_b200.h)."""
+    _fields_ = [("actor", _p), ("critic", _p), ("actor_stride", _i64), ("critic_stride", _i64),
+                ("g_actor", _p), ("g_critic", _p),
+                ("feat_dim", _i), ("n_actions", _i), ("n_agents", _i), ("T1", _i), ("n_eps", _i), ("n_train_eps", _i),
+                ("rnn_a", _p), ("rnn_c", _p), ("rnn_stride_agent", _i64), ("rnn_ld", _i),
+                ("actions", _p), ("avail", _p),
+                ("Z1", _p), ("A1", _p), ("Z2", _p), ("A2", _p), ("GI", _p), ("GH", _p),
+                ("stat", _p), ("SM", _p),
+                ("logp_out", _p), ("ent_out", _p), ("value_out", _p),
+                ("old_logp", _p), ("old_value", _p), ("returns", _p), ("adv_raw", _p), ("alive", _p),
+                ("norm", _p), ("stats", _p),
+                ("clip", _f), ("ent_coef", _f), ("v_coef", _f), ("huber_delta", _f)]
 
 
 def _bind(signatures):

@@ -1,0 +1,147 @@
+"""Parity of the CUDA learner (K2a GAE/advantage moments, fused forward, K2b PPO losses +
+backward, fc1 products, clip + Adam) through IPPOLearner.insert_episode_batch / train against
+ (1) the golden post-update weights and logged statistics produced by the reference's own
+     IPPOLearner.train (tests/golden/learner.pt), and
+ (2) the CPU oracle at a larger, Highway-shaped case."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from tests.test_gpu_rollout import args_from, load, make_scheme, maxdiff
+
+pytestmark = pytest.mark.gpu
+
+
+class Log:
+    def __init__(self):
+        self.stats = {}
+
+    def log_stat(self, k, v, t):
+        self.stats[k] = float(v)
+
+
+def build(args, data, actors, critics):
+    from iplan_b200.components.episode_buffer import EpisodeBatch
+    from iplan_b200.controllers.dcntrl_controller import DcntrlMAC
+    from iplan_b200.learners.ippo_learner import IPPOLearner
+    scheme, groups, pre = make_scheme(args)
+    B = data["history"].shape[0]
+    batch = EpisodeBatch(scheme, groups, B, args.episode_limit + 1, preprocess=pre, device="cuda")
+    mac = DcntrlMAC(batch.scheme, groups, args)
+    for i in range(args.n_agents):
+        mac.agents[i].load_state_dict(actors[i])
+        mac.critics[i].load_state_dict(critics[i])
+    log = Log()
+    learner = IPPOLearner(mac, batch.scheme, log, args)
+    batch.update(data, bs=slice(None), ts=slice(None))
+    return batch, mac, learner, log
+
+
+@pytest.mark.parametrize("case", ["mpe", "highway"])
+def test_train_matches_reference_golden(golden_dir, case):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    g = load(golden_dir, "learner.pt")[case]
+    args = args_from(g["args"])
+    A, T = args.n_agents, args.episode_limit
+    batch, mac, learner, log = build(args, g["data"], g["actors_before"], g["critics_before"])
+    # packed rows == the reference's _build_inputs_ippo output
+    F = mac.input_shape
+    for a in range(A):
+        assert maxdiff(batch.packed[a, :, :, :F], g["pre"][a]["obs_all"]) < 1e-6
+    learner.keep_pre = True
+    learner.insert_episode_batch(batch)
+    assert learner.can_sample()
+    learner.train(t_env=0)
+    torch.cuda.synchronize()
+    pre = learner.last_pre
+    worst = {}
+    for a in range(A):
+        ref = g["pre"][a]
+        for k in ("values_all", "returns", "advantages", "old_logp"):
+            worst[k] = max(worst.get(k, 0.0), maxdiff(pre[k][a], ref[k]))
+    print(f"[learner {case}] pre-update diffs {worst}")
+    assert worst["values_all"] < 1e-4 and worst["old_logp"] < 1e-4
+    assert worst["returns"] < 2e-4 and worst["advantages"] < 2e-4
+    dmax = {}
+    for a in range(A):
+        for kind, nets, after in (("actor", mac.agents, g["actors_after"]), ("critic", mac.critics, g["critics_after"])):
+            sd = nets[a].state_dict()
+            for k, v in after[a].items():
+                d = maxdiff(sd[k], v)
+                dmax[kind + ":" + k] = max(dmax.get(kind + ":" + k, 0.0), d)
+    top = sorted(dmax.items(), key=lambda kv: -kv[1])[:5]
+    print(f"[learner {case}] largest post-train weight diffs: {top}")
+    # 15 (4) Adam steps of lr 5e-4 move a weight by <= 7.5e-3 (2e-3); agreement to 5e-5 abs
+    assert top[0][1] < 5e-5, top
+    for key in ("value_loss", "policy_loss", "dist_entropy", "actor_grad_norm", "critic_grad_norm", "ratio"):
+        ref = [v for k, v in g["stats"].items() if k.endswith(key)][0]
+        mine = learner.train_info[key]
+        print(f"[learner {case}] {key}: cuda {mine:.6f} reference {ref:.6f}")
+        assert abs(mine - ref) < 2e-4 * max(1.0, abs(ref)), (key, mine, ref)
+    assert learner.count == 0 and not learner.can_sample()
+    # optimiser checkpoint has the reference's structure: 18 tensors with Adam state
+    sd = learner.actor_optimizers[0].state_dict()
+    assert len(sd["state"]) == g["actor_opt_steps"][0] and len(sd["param_groups"][0]["params"]) == 22
+
+
+def test_train_vs_oracle_highway_shape():
+    """Full Highway dims (A=5, N=55, F=2485), Bf=12 episodes x T=9, 3 epochs: CUDA vs oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from iplan_b200.config import make_args
+    from oracle import iplan_oracle as O
+    args = make_args("highway", episode_limit=9, buffer_size=12, batch_size=11, batch_size_run=12, ppo_epoch=3,
+                     use_cuda=True, device="cuda")
+    A, N, o, L, D, R, T, B = args.n_agents, args.max_vehicle_num, 5, 8, 32, 64, 9, 12
+    rng = np.random.default_rng(5)
+    hist = rng.uniform(-1, 1, size=(B, T + 1, A, N, o)).astype(np.float32)
+    hist[..., 0] = 1.0
+    hist[:, :, :, 25:] = 0.0
+    term = np.zeros((B, T + 1, A, 1), dtype=np.uint8)
+    term[2, 5:, 1] = 1
+    term[7, 3:, 4] = 1
+    data = dict(history=hist, attention_latent=rng.uniform(-1, 1, size=(B, T + 1, A, N, D)).astype(np.float32),
+                behavior_latent=rng.dirichlet(np.ones(L), size=(B, T + 1, A, N)).astype(np.float32),
+                rnn_states_actors=rng.uniform(-1, 1, size=(B, T + 1, A, R)).astype(np.float32),
+                rnn_states_critics=rng.uniform(-1, 1, size=(B, T + 1, A, R)).astype(np.float32),
+                actions=rng.integers(0, 5, size=(B, T + 1, A, 1)), avail_actions=np.ones((B, T + 1, A, 5), dtype=np.int64),
+                reward=(rng.normal(size=(B, T + 1, A, 1)) * 2).astype(np.float32), terminated=term)
+    torch.manual_seed(3)
+    from iplan_b200.modules.flat import ParamStack
+    F = N * 45 + 10
+    a0 = ParamStack("actor", A, (F, 5))
+    c0 = ParamStack("critic", A, (F,))
+    with torch.no_grad():
+        for n in a0.nets:
+            n.act.action_out.linear.weight.mul_(30.0)
+        a0.flat[:, :2 * F].uniform_(0.5, 1.5)
+        c0.flat[:, :2 * F].uniform_(0.5, 1.5)
+    actors = [{k: v.clone() for k, v in n.state_dict().items()} for n in a0.nets]
+    critics = [{k: v.clone() for k, v in n.state_dict().items()} for n in c0.nets]
+    batch, mac, learner, log = build(args, data, actors, critics)
+    learner.insert_episode_batch(batch)
+    learner.train(0)
+    torch.cuda.synchronize()
+    dt = {k: torch.as_tensor(v) for k, v in data.items()}
+    onehot = torch.nn.functional.one_hot(dt["actions"].squeeze(-1), 5).float()
+    oargs = SimpleNamespace(**vars(args))
+    worst = 0.0
+    for a in range(A):
+        ob = dict(history=dt["history"][:, :, a], attention_latent=dt["attention_latent"][:, :, a],
+                  behavior_latent=dt["behavior_latent"][:, :, a], actions=dt["actions"][:, :, a],
+                  actions_onehot=onehot[:, :, a], available_actions=dt["avail_actions"][:, :, a],
+                  reward=dt["reward"][:, :, a], terminated_masks=(1 - dt["terminated"][:, :, a].float()),
+                  rnn_states_actor=dt["rnn_states_actors"][:, :, a], rnn_states_critic=dt["rnn_states_critics"][:, :, a])
+        ap = {k: v.clone() for k, v in actors[a].items()}
+        cp = {k: v.clone() for k, v in critics[a].items()}
+        O.train_agent(ap, cp, ob, a, oargs)
+        for nets, ref in ((mac.agents, ap), (mac.critics, cp)):
+            sd = nets[a].state_dict()
+            for k, v in ref.items():
+                worst = max(worst, maxdiff(sd[k], v))
+    print(f"[learner highway-shape] worst post-train weight diff vs oracle {worst:.3e}")
+    assert worst < 5e-5
