@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the iPLAN rollout-and-learn hot path on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic input: a 90-timestep
+rollout of `envs_per_gpu` environments x 5 agents (K1 GAT + K1b behaviour encoder + K1c
+controller per timestep) followed by one IPPOLearner.train (GAE, 15 PPO epochs, all agents).
+Workload = BASELINE.json configs[2] "Hetero-Highway chaotic, 5 agents, 512 envs" per GPU
+(weak scaling: every rank owns 512 envs; at N GPUs the job is 512*N envs, one NCCL
+all-reduce of the actor+critic gradients per PPO epoch).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU port of the reference path, host cores
+
+Prints ONE JSON line (rank 0).  `value` = device-resident path, inputs already in HBM;
+`e2e` = the same work through the reference-facing numpy API (host buffers in/out every
+timestep); `roofline` = the dominant kernel (K1 GAT step) timed with CUDA events inside the
+timed region; `cpu_baseline` = the oracle port on the host cores (N=1 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec iPLAN Hetero-Highway chaotic (rollout + IPPO update)"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--envs-per-gpu", type=int, default=512)
+    p.add_argument("--e2e-steps", type=int, default=1)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return dict(hbm=pk["hbm_gbs"], tf_burst=pk["bf16_tflops"], tf_sus=pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+                    src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sus=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def gat_algorithmic(B, A, N, o, L, H=32):
+    """Algorithmic FLOPs and HBM bytes of ONE K1 launch."""
+    in_dim = o + L
+    per_node = (2 * H * in_dim                      # encode
+                + 2 * 2 * 2 * 3 * H * H             # factored input projections P,Q x 2 directions
+                + 2 * (N - 1) * 2 * 3 * H * H       # bidirectional GRU recurrence
+                + 2 * (N - 1) * 2 * 2 * H           # hard-attention logits
+                + 3 * 2 * H * H                     # q, k, v
+                + (N - 1) * 2 * H * 2               # scores + weighted sum
+                + 2 * 2 * 3 * H * H)                # GRUCell
+    nodes = B * A * N
+    return per_node * nodes, nodes * (in_dim + 2 * H) * 4
+
+
+def run_reference(args):
+    """--impl reference: the oracle port of the reference's CPU path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from iplan_b200.config import make_args
+    from oracle import cpu_baseline as cb
+    a = make_args("highway", use_cuda=False, device="cpu")
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    B, T = args.envs_per_gpu * args.gpus, a.episode_limit
+    params = cb.random_params(a)
+    train_eps = 16
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        t_step = cb.time_rollout_steps(a, params, args.envs_per_gpu, 1, warmup=0, seed=it)
+        t_train = cb.time_train(a, params, train_eps, seed=it) * (args.envs_per_gpu / train_eps)
+        if it >= args.warmup:
+            times.append((t_step, t_train, time.perf_counter() - t0))
+    t_step = sum(t[0] for t in times) / len(times)
+    t_train = sum(t[1] for t in times) / len(times)
+    # the CPU path does not shard: N x 512 envs cost N x the 512-env time
+    step_s = (T * t_step + t_train) * args.gpus
+    value = B * T / step_s
+    sample = (f"each step: 1 rollout timestep at B={args.envs_per_gpu} (x{T}) + one update at Bf={train_eps} episodes "
+              f"scaled x{args.envs_per_gpu / train_eps:g} in rows; x{args.gpus} for the {B}-env job (no sharding on CPU)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Hetero-Highway chaotic, 5 agents, 512 envs/GPU, T=90, 15 PPO epochs",
+                   "envs": B, "agents": a.n_agents, "slots": a.max_vehicle_num, "feat_dim": 2485},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from iplan_b200 import _lib
+    from iplan_b200.runners.synthetic_runner import build_system
+    Bl = args.envs_per_gpu
+    sysm = build_system(n_envs=Bl, env="highway", hazard=0.01, seed=112358 + rank,
+                        batch_size=Bl * world - 1)          # global "first batch_size episodes" rule
+    if world > 1:   # replicas start from identical weights (rank 0's)
+        for t in (sysm.mac.actor_stack.flat, sysm.mac.critic_stack.flat, sysm.prediction.stack.flat, sysm.behavior.stack.flat):
+            dist.broadcast(t, 0)
+    a = sysm.args
+    T = a.episode_limit
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sysm.run_and_train()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    gat_events = []
+    sysm.runner.gat_events = gat_events
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    em = torch.cuda.Event(enable_timing=True)
+    roll_ms = 0.0
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        batch, *_ = sysm.runner.run()
+        s1.record()
+        sysm.learner.insert_episode_batch(batch)
+        sysm.learner.train(sysm.runner.t_env)
+        gat_events.append(("roll", s0, s1))
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = (_lib.launch_count() - l0) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    sysm.runner.gat_events = None
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    ms_per_step = ms / args.steps
+    value = Bl * world * T / (ms_per_step / 1e3)
+    gat_ms = [s.elapsed_time(e) for tag, s, e in gat_events if tag == "gat"]
+    roll_ms = [s.elapsed_time(e) for tag, s, e in gat_events if tag == "roll"]
+    gat_mean = sum(gat_ms) / max(1, len(gat_ms))
+
+    # ---- e2e: same work through the reference-facing numpy API -----------------------------
+    e2e = None
+    if not args.no_e2e:
+        sysm.run_and_train(api=True)                        # warm-up of the API path
+        _lib.io_bytes["h2d"] = _lib.io_bytes["d2h"] = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            sysm.run_and_train(api=True)
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / args.e2e_steps], device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": Bl * world * T / float(dt), "unit": "env-steps/s",
+               "h2d_bytes_per_step": _lib.io_bytes["h2d"] // args.e2e_steps,
+               "d2h_bytes_per_step": _lib.io_bytes["d2h"] // args.e2e_steps,
+               "ms_per_step": float(dt) * 1e3, "steps": args.e2e_steps,
+               "path": "GAT_latent_update/latent_update/EpisodeBatch.update/select_actions_ippo with numpy buffers every timestep"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    flops, hbm_bytes = gat_algorithmic(Bl, a.n_agents, a.max_vehicle_num, a.obs_shape_single, a.latent_dim)
+    ach_tf = flops / (gat_mean * 1e-3) / 1e12 if gat_mean > 0 else 0.0
+    roofline = {"kernel": "gat_step_kernel (K1)", "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sus"],
+                "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sus"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "launch_ms": gat_mean, "launches_timed": len(gat_ms),
+                "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": hbm_bytes,
+                "hbm_achieved_gbs": hbm_bytes / (gat_mean * 1e-3) / 1e9 if gat_mean > 0 else 0.0,
+                "hbm_frac": (hbm_bytes / (gat_mean * 1e-3) / 1e9) / pk["hbm"] if gat_mean > 0 else 0.0,
+                "share_of_step": sum(gat_ms) / ms if ms > 0 else None,
+                "note": "fp32 FMA + MUFU bound recurrence (54-step bi-GRU per ego); see DESIGN.md"}
+    out = {
+        "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "Hetero-Highway chaotic, 5 agents, 512 envs/GPU, T=90, 15 PPO epochs (BASELINE configs[2])",
+                   "envs": Bl * world, "envs_per_gpu": Bl, "agents": a.n_agents, "slots": a.max_vehicle_num,
+                   "feat_dim": sysm.mac.input_shape, "episode_limit": T, "ppo_epoch": a.ppo_epoch,
+                   "parallelism": f"env-sharded x{world}", "l2": "inputs (2.3 GB episode store) exceed L2"},
+        "ms_rollout": sum(roll_ms) / max(1, len(roll_ms)), "ms_update": ms_per_step - sum(roll_ms) / max(1, len(roll_ms)),
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline as cb
+        from iplan_b200.config import make_args
+        cpu = cb.measure(make_args("highway", use_cuda=False, device="cpu"), B=Bl, rollout_steps=2, train_eps=32)
+        out["cpu_baseline"] = {"value": cpu["value"], "unit": "env-steps/s", "cores": cpu["cores"], "kind": "port",
+                               "sample": cpu["sample"], "t_rollout_step_s": cpu["t_step"], "t_update_s": cpu["t_train"]}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

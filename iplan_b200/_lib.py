@@ -103,6 +103,29 @@ def view(t):
     return View(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
 
 
+io_bytes = {"h2d": 0, "d2h": 0}      # host<->device traffic of the reference-facing (numpy) API
+
+
+def to_device(x, dtype=torch.float32, device="cuda"):
+    """numpy / CPU tensor -> CUDA tensor of `dtype`, counting the bytes that cross PCIe."""
+    import numpy as np
+    if torch.is_tensor(x):
+        if x.is_cuda:
+            return x.to(dtype)
+        t = x
+    else:
+        t = torch.as_tensor(np.asarray(x))
+    t = t.to(dtype)
+    io_bytes["h2d"] += t.numel() * t.element_size()
+    return t.to(device, non_blocking=True)
+
+
+def to_host(t):
+    """CUDA tensor -> numpy, counting the bytes."""
+    io_bytes["d2h"] += t.numel() * t.element_size()
+    return t.cpu().numpy()
+
+
 def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -115,7 +115,7 @@ class EpisodeBatch:
             if k in self.data.transition_data:
                 target = self.data.transition_data
                 if mark_filled:
-                    target["filled"][slices] = 1
+                    target["filled"][tuple(slices)] = 1
                     mark_filled = False
                 _slices = tuple(slices)
             elif k in self.data.episode_data:
@@ -124,7 +124,10 @@ class EpisodeBatch:
             else:
                 raise KeyError("{} not found in transition or episode data".format(k))
             dtype = self.scheme[k].get("dtype", th.float32)
-            if th.is_tensor(v):
+            if str(self.device).startswith("cuda"):
+                from .. import _lib
+                v = _lib.to_device(v, dtype=dtype, device=self.device)      # counts PCIe bytes
+            elif th.is_tensor(v):
                 v = v.to(device=self.device, dtype=dtype)
             else:
                 v = th.as_tensor(np.asarray(v)).to(device=self.device, dtype=dtype)

@@ -89,11 +89,11 @@ class DcntrlMAC:
         actions, logp, values = self.controller_step(feat, rnn_a, rnn_c, new_a, new_c, avail_u8,
                                                      test_mode=test_mode, uniforms=uni, logits=logits)
         self.last_logits = logits
-        values_np = values.t().cpu().numpy()                                        # [B,A]
-        actions_np = actions.t().to(th.int64).cpu().numpy()
+        values_np = _lib.to_host(values.t())                                        # [B,A]
+        actions_np = _lib.to_host(actions.t().to(th.int64))
         action_log_probs = [logp[a].view(B, 1) for a in range(A)]                   # list[A] of [B,1]
-        rnn_a_np = new_a.permute(1, 0, 2).unsqueeze(0).cpu().numpy()                # [1,B,A,R]
-        rnn_c_np = new_c.permute(1, 0, 2).unsqueeze(0).cpu().numpy()
+        rnn_a_np = _lib.to_host(new_a.permute(1, 0, 2).unsqueeze(0))                # [1,B,A,R]
+        rnn_c_np = _lib.to_host(new_c.permute(1, 0, 2).unsqueeze(0))
         return values_np, actions_np, action_log_probs, rnn_a_np, rnn_c_np
 
     # ---- learner-facing evaluation helpers (reference :61-85); bound by the learner ----

@@ -516,9 +516,13 @@ __global__ void __launch_bounds__(256) gru_head_kernel(HeadArgs h) {
                 const float eo = ret - v, ec = ret - vc;
                 const float lo = huber_os(eo, h.huber_delta), lc = huber_os(ec, h.huber_delta);
                 const bool inside = diff >= -h.clip && diff <= h.clip;
-                float g = 0.0f;                                   // d max(lo, lc) / d v
-                if (lo > lc) g = -huber_os_grad(eo, h.huber_delta);
-                else if (lo == lc) g = inside ? -huber_os_grad(eo, h.huber_delta) : -0.5f * huber_os_grad(eo, h.huber_delta);
+                // d max(lo, lc) / d v.  d lo/dv = -h'(eo);  d lc/dv = -h'(ec) where the clamp passes
+                // (inside the range), else 0.  Inside the range vc = vo + (v - vo) can differ from v
+                // by an ulp, so which of lo / lc is larger is rounding noise there: both branches
+                // must carry the same gradient (torch.max splits it evenly on an exact tie).
+                const float go = -huber_os_grad(eo, h.huber_delta);
+                const float gc = inside ? -huber_os_grad(ec, h.huber_delta) : 0.0f;
+                const float g = lo > lc ? go : (lc > lo ? gc : 0.5f * (go + gc));
                 dv = h.v_coef * m * inv_msum * g;
                 st_loss += fmaxf(lo, lc) * m * inv_msum;
             }

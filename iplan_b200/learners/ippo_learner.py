@@ -280,6 +280,8 @@ class IPPOLearner:
                 _lib.ptr(w["Z1"]), _lib.ptr(w["SM"]), _lib.ptr(w["G"]), st), "fc1_backward")
             if dist:
                 self._allreduce_grads(dist, ga, gc)
+            if self.keep_pre and _ == 0:
+                self.first_grads = {"actor": ga.clone(), "critic": gc.clone()}
             for kind, g, col in (("actor", ga, 4), ("critic", gc, 5)):
                 self.steps[kind] += 1
                 stack = self.stacks[kind]

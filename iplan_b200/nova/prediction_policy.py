@@ -59,9 +59,9 @@ class Prediction_policy:
     # ---- reference-compatible numpy entry point (reference :92-118) -----------------
     def GAT_latent_update(self, history_single, encoder_hidden, behavior_latent=None):
         dev = self.device
-        hs = torch.as_tensor(np.asarray(history_single), dtype=torch.float32).to(dev, non_blocking=True)
-        eh = torch.as_tensor(np.asarray(encoder_hidden), dtype=torch.float32).to(dev, non_blocking=True)
-        bl = torch.as_tensor(np.asarray(behavior_latent), dtype=torch.float32).to(dev, non_blocking=True)
+        hs = _lib.to_device(history_single)
+        eh = _lib.to_device(encoder_hidden)
+        bl = _lib.to_device(behavior_latent)
         out = torch.empty_like(eh)
         perm = (1, 0, 2, 3)       # [B,A,N,*] -> [A,B,N,*] views, no copy
         gum = self.debug_gumbel
@@ -72,7 +72,7 @@ class Prediction_policy:
             dbg = torch.zeros(A, B, N, N - 1, device=dev)
             self.last_hard = dbg
         self.gat_step(hs.permute(perm), bl.permute(perm), eh.permute(perm), out.permute(perm), gum, dbg)
-        return out.cpu().numpy()
+        return _lib.to_host(out)
 
     def learn(self, batch, t_env):
         raise NotImplementedError("Prediction_policy.learn (aux trajectory-prediction loss, reference "

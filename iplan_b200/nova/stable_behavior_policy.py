@@ -51,18 +51,18 @@ class Behavior_policy:
     # ---- reference-compatible entry point (reference :83-123) -------------------------
     def latent_update(self, history, encoder_hidden, prev_latent):
         dev = self.device
-        hist = torch.as_tensor(np.asarray(history), dtype=torch.float32).to(dev, non_blocking=True)
+        hist = _lib.to_device(history)
         B, A, N, W, o = hist.shape
-        if torch.is_tensor(encoder_hidden):
-            hid = encoder_hidden.detach().to(dev, torch.float32).clone()
+        if torch.is_tensor(encoder_hidden) and encoder_hidden.is_cuda:
+            hid = encoder_hidden.detach().to(torch.float32).clone()
         else:
-            hid = torch.as_tensor(np.asarray(encoder_hidden), dtype=torch.float32).to(dev)
-        prev = torch.as_tensor(np.asarray(prev_latent), dtype=torch.float32).to(dev, non_blocking=True)
+            hid = _lib.to_device(encoder_hidden)
+        prev = _lib.to_device(prev_latent)
         new = torch.empty_like(prev)
         hid_v = hid[:, 0].permute(1, 0, 2, 3)                    # [B,1,A,N,E] -> [A,B,N,E] view
         self.behavior_step(hist.reshape(B, A, N, W * o).permute(1, 0, 2, 3), hid_v,
                            prev.permute(1, 0, 2, 3), new.permute(1, 0, 2, 3))
-        return new.cpu().numpy(), hid
+        return _lib.to_host(new), hid
 
     def learn(self, batch, t_env):
         raise NotImplementedError("Behavior_policy.learn (aux reconstruction loss, reference "

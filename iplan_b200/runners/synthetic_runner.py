@@ -164,8 +164,20 @@ class ParallelRunner:
                 window[..., :(W - 1) * o] = window[..., o:].clone()
             window[..., (W - 1) * o:] = h
 
+        events = getattr(self, "gat_events", None)
+
+        def gat(*a):
+            """K1 launch, optionally bracketed by CUDA events on the launching stream (bench.py)."""
+            if events is None:
+                return self.prediction_learner.gat_step(*a)
+            e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+            e0.record()
+            self.prediction_learner.gat_step(*a)
+            e1.record()
+            events.append(("gat", e0, e1))
+
         push_history(0)
-        self.prediction_learner.gat_step(hist_v[:, :, 0], zeros_beh, zeros_att, att_v[:, :, 0])
+        gat(hist_v[:, :, 0], zeros_beh, zeros_att, att_v[:, :, 0])
         for t in range(T):
             acts, _, _ = self.mac.controller_step(
                 packed[:, :, t], rnn_a[:, :, t], rnn_c[:, :, t], rnn_a[:, :, t + 1], rnn_c[:, :, t + 1],
@@ -173,7 +185,7 @@ class ParallelRunner:
                 this_onehot=onehot_cols[:, :, 0] if t == 0 else None)
             actions_all[:, :, t] = acts
             push_history(t + 1)
-            self.prediction_learner.gat_step(hist_v[:, :, t + 1], beh_v[:, :, t], att_v[:, :, t], att_v[:, :, t + 1])
+            gat(hist_v[:, :, t + 1], beh_v[:, :, t], att_v[:, :, t], att_v[:, :, t + 1])
             self.behavior_learner.behavior_step(window, enc_hid, beh_v[:, :, t], beh_v[:, :, t + 1])
         # episode-level stores in the reference's layout [B,T+1,A,*]
         batch["actions"][..., 0] = actions_all.permute(1, 2, 0).long()

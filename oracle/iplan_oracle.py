@@ -460,17 +460,21 @@ def train_agent(actor_p, critic_p, batch, agent_id, args, opt_a=None, opt_c=None
         values, _ = critic_value(critic_p, mb["obs"], mb["rnn_c"])
         pol_loss, ratio = policy_loss_terms(lp, mb["old_lp"], mb["adv"], mb["alive"], args.clip_param)
         g_a = torch.autograd.grad(pol_loss - ent_mean * args.entropy_coef, a_tr)
+        raw_a = [g.clone() for g in g_a]
         g_a, n_a = clip_grads(g_a, args.max_grad_norm)
         v_loss = value_loss_terms(values, mb["old_v"], mb["ret"], mb["alive"],
                                   args.clip_param, args.huber_delta)
         g_c = torch.autograd.grad(v_loss * args.value_loss_coef, c_tr)
+        raw_c = [g.clone() for g in g_c]
         g_c, n_c = clip_grads(g_c, args.max_grad_norm)
         with torch.no_grad():
             opt_a.step(g_a)
             opt_c.step(g_c)
         stats.append(dict(value_loss=v_loss.item(), policy_loss=pol_loss.item(),
                           dist_entropy=ent_mean.item(), actor_grad_norm=n_a.item(),
-                          critic_grad_norm=n_c.item(), ratio=ratio.mean().item()))
+                          critic_grad_norm=n_c.item(), ratio=ratio.mean().item(),
+                          grads_actor=dict(zip(ACTOR_TRAINABLE, raw_a)) if ep == 0 else None,
+                          grads_critic=dict(zip(CRITIC_TRAINABLE, raw_c)) if ep == 0 else None))
     for t in a_tr + c_tr:
         t.requires_grad_(False)
     pre = dict(values_all=v_all, returns=returns, advantages=adv, old_logp=old_lp.view(Bf, T))

@@ -123,6 +123,7 @@ def test_train_vs_oracle_highway_shape():
     actors = [{k: v.clone() for k, v in n.state_dict().items()} for n in a0.nets]
     critics = [{k: v.clone() for k, v in n.state_dict().items()} for n in c0.nets]
     batch, mac, learner, log = build(args, data, actors, critics)
+    learner.keep_pre = True
     learner.insert_episode_batch(batch)
     learner.train(0)
     torch.cuda.synchronize()
@@ -130,6 +131,7 @@ def test_train_vs_oracle_highway_shape():
     onehot = torch.nn.functional.one_hot(dt["actions"].squeeze(-1), 5).float()
     oargs = SimpleNamespace(**vars(args))
     worst = 0.0
+    offs = {"actor": mac.actor_stack.named_offsets(), "critic": mac.critic_stack.named_offsets()}
     for a in range(A):
         ob = dict(history=dt["history"][:, :, a], attention_latent=dt["attention_latent"][:, :, a],
                   behavior_latent=dt["behavior_latent"][:, :, a], actions=dt["actions"][:, :, a],
@@ -138,7 +140,18 @@ def test_train_vs_oracle_highway_shape():
                   rnn_states_actor=dt["rnn_states_actors"][:, :, a], rnn_states_critic=dt["rnn_states_critics"][:, :, a])
         ap = {k: v.clone() for k, v in actors[a].items()}
         cp = {k: v.clone() for k, v in critics[a].items()}
-        O.train_agent(ap, cp, ob, a, oargs)
+        stats, pre, _, _ = O.train_agent(ap, cp, ob, a, oargs)
+        mine = learner.last_pre
+        dpre = {k: maxdiff(mine[k][a], pre[k]) for k in ("values_all", "returns", "advantages", "old_logp")}
+        gbad = []
+        for kind, key in (("actor", "grads_actor"), ("critic", "grads_critic")):
+            for name, gref in stats[0][key].items():
+                off, shape = offs[kind][name]
+                gm = learner.first_grads[kind][a, off:off + gref.numel()].view(gref.shape).cpu()
+                rel = float((gm - gref).abs().max() / (gref.abs().max() + 1e-12))
+                gbad.append((rel, kind + ":" + name, float(gref.abs().max())))
+        gbad.sort(reverse=True)
+        print(f"[learner highway-shape a={a}] pre {dpre}\n   worst first-epoch grads (rel, name, |ref|max): {gbad[:4]}")
         for nets, ref in ((mac.agents, ap), (mac.critics, cp)):
             sd = nets[a].state_dict()
             for k, v in ref.items():
