@@ -15,8 +15,17 @@
 //   x_i = sum_s soft * hard * v_j (no renormalisation)                      (:132)
 //   out = GRUCell(x_i, h_prev_i)                                            (:140)
 //
-// HBM traffic per (b,a): read N*(o+L+32) floats, write N*32 floats; weights (28.8k
-// floats) come from L2.  The work is the 2*N sequential GRU chains of length N-1.
+// The work is the 2N GRU chains of length N-1 (91 % of the FLOPs).  They run on the tensor
+// cores: a warp advances 16 chains (egos) of one direction per step as ONE 16x96x32 product
+// h . W_hh^T with mma.sync.m16n8k16 (f16 inputs, f32 accumulate).  fp32 accuracy is kept by
+// splitting both operands into f16 hi + lo parts and issuing hi*hi + lo*hi + hi*lo (the
+// dropped lo*lo term is < 2^-22 relative).  The accumulator fragment of step s is, element
+// for element, the A fragment of step s+1, so the hidden state never leaves registers.
+//
+// HBM traffic per (b,a): read N*(o+L+32) floats, write N*32 floats; weights (28.8k floats)
+// come from L2.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace iplan {
@@ -25,9 +34,9 @@ constexpr int H = IPLAN_HID;   // 32 == GAT_hidden_dim == attention_dim
 constexpr int G3 = 3 * H;      // gate rows r|z|n
 constexpr int GAT_THREADS = 256;
 constexpr int GAT_WARPS = GAT_THREADS / 32;
-constexpr int SEQ_G = 7;       // GRU chains a warp advances together (register blocking)
 constexpr int IN_MAX = 16;     // obs_dim + latent_dim upper bound
-constexpr int WT_LD = 97;      // padded leading dim of the transposed GRUCell weights
+constexpr int NT_G = G3 / 8;   // 12 n-tiles of 8 gate columns
+constexpr int KB_H = H / 16;   // 2 k-blocks of 16 hidden units
 
 struct GatArgs {
     const float* params; int64_t param_stride;
@@ -40,7 +49,83 @@ struct GatArgs {
 
 __host__ __device__ inline size_t gat_smem_floats(int N) {
     return (size_t)N * IN_MAX + (size_t)N * H + 4 * (size_t)N * G3 + 2 * (size_t)N * (N - 1) +
-           GAT_WARPS * SEQ_G * H + 2 * H * WT_LD + GAT_WARPS * 64;
+           2 * NT_G * KB_H * 32 * 2 + GAT_WARPS * 64;
+}
+
+// fast, fp32-accurate-enough gates (abs error ~1e-7): ex2.approx + rcp.approx
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+
+// (x, y) -> packed f16 hi pair and f16 lo (residual) pair
+__device__ __forceinline__ void split_f16(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// D = A(16x16, row) * B(16x8, col) + C, f16 x f16 -> f32
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const float (&c)[4]) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
+}
+
+// out[n][c] = act( sum_{k<32} in[n][k] * Wg[c*ldw + k] + bias[c] )  for n < N, c < cols (cols % 8 == 0)
+// `in` / `out` in shared memory (row pitch ldin / ldout floats), W and bias in global memory.
+// All warps of the CTA cooperate: one task = one 16-node x 8-column tile = 6 MMAs (f16 hi/lo
+// split, see header).  W is read as B fragments straight from global memory: a quad reads 32
+// contiguous bytes of one weight row, so every sector fetched is fully used.
+__device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, const float* __restrict__ Wg, int ldw,
+                                            const float* __restrict__ bias, int cols, float* out, int ldout, bool relu,
+                                            int warp, int lane) {
+    const int gq = lane >> 2, tq = lane & 3;
+    const int mtiles = (N + 15) >> 4, ntiles = cols >> 3;
+    int cur_mt = -1;
+    uint32_t ahi[KB_H][4], alo[KB_H][4];
+    for (int task = warp; task < mtiles * ntiles; task += GAT_WARPS) {
+        const int mt = task / ntiles, nt = task - mt * ntiles;      // consecutive tasks share the m-tile
+        const int r0 = mt * 16 + gq, r1 = r0 + 8;
+        if (mt != cur_mt) {
+            cur_mt = mt;
+            const float* x0 = in + min(r0, N - 1) * ldin + 2 * tq;
+            const float* x1 = in + min(r1, N - 1) * ldin + 2 * tq;
+#pragma unroll
+            for (int kb = 0; kb < KB_H; ++kb) {
+                const float2 v00 = *reinterpret_cast<const float2*>(x0 + 16 * kb);
+                const float2 v10 = *reinterpret_cast<const float2*>(x1 + 16 * kb);
+                const float2 v01 = *reinterpret_cast<const float2*>(x0 + 16 * kb + 8);
+                const float2 v11 = *reinterpret_cast<const float2*>(x1 + 16 * kb + 8);
+                split_f16(v00.x, v00.y, ahi[kb][0], alo[kb][0]);
+                split_f16(v10.x, v10.y, ahi[kb][1], alo[kb][1]);
+                split_f16(v01.x, v01.y, ahi[kb][2], alo[kb][2]);
+                split_f16(v11.x, v11.y, ahi[kb][3], alo[kb][3]);
+            }
+        }
+        const int c0 = 8 * nt + 2 * tq;
+        float acc[4];
+        const float b0 = bias ? bias[c0] : 0.0f, b1 = bias ? bias[c0 + 1] : 0.0f;
+        const float cinit[4] = {b0, b1, b0, b1};
+        const float* wr = Wg + (size_t)(8 * nt + gq) * ldw + 2 * tq;
+        uint32_t bh[KB_H][2], bl[KB_H][2];
+#pragma unroll
+        for (int kb = 0; kb < KB_H; ++kb) {
+            const float2 w0 = *reinterpret_cast<const float2*>(wr + 16 * kb);
+            const float2 w1 = *reinterpret_cast<const float2*>(wr + 16 * kb + 8);
+            split_f16(w0.x, w0.y, bh[kb][0], bl[kb][0]);
+            split_f16(w1.x, w1.y, bh[kb][1], bl[kb][1]);
+        }
+        mma16816(acc, ahi[0], bh[0][0], bh[0][1], cinit);
+        mma16816(acc, ahi[1], bh[1][0], bh[1][1], acc);
+        mma16816(acc, alo[0], bh[0][0], bh[0][1], acc);
+        mma16816(acc, alo[1], bh[1][0], bh[1][1], acc);
+        mma16816(acc, ahi[0], bl[0][0], bl[0][1], acc);
+        mma16816(acc, ahi[1], bl[1][0], bl[1][1], acc);
+        if (relu) { acc[0] = fmaxf(acc[0], 0.f); acc[1] = fmaxf(acc[1], 0.f); acc[2] = fmaxf(acc[2], 0.f); acc[3] = fmaxf(acc[3], 0.f); }
+        if (r0 < N) { out[r0 * ldout + c0] = acc[0]; out[r0 * ldout + c0 + 1] = acc[1]; }
+        if (r1 < N) { out[r1 * ldout + c0] = acc[2]; out[r1 * ldout + c0 + 1] = acc[3]; }
+    }
 }
 
 __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
@@ -57,14 +142,16 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
     float* s_P = s_enc + N * H;                         // [2][N][96]  ego part + b_ih
     float* s_Q = s_P + 2 * N * G3;                      // [2][N][96]  neighbour part
     float* s_dl = s_Q + 2 * N * G3;                     // [2][N][N-1] per-direction logit diff
-    float* s_hb = s_dl + 2 * N * NM1;                   // [warps][SEQ_G][H] chain states
-    float* s_wt = s_hb + GAT_WARPS * SEQ_G * H;         // [2][H][WT_LD] GRUCell W^T
-    float* s_w = s_wt + 2 * H * WT_LD;                  // [warps][64] attention weights
-    // after the recurrence the P/Q region is reused:
+    uint2* s_wlo = reinterpret_cast<uint2*>(s_dl + 2 * N * NM1);   // [2][12][2][32] f16 lo parts of W_hh (B fragments)
+    float* s_w = reinterpret_cast<float*>(s_wlo + 2 * NT_G * KB_H * 32);   // [warps][64] attention weights
+    // after the recurrence the P/Q region (4*N*96 floats) is reused:
     float* s_q = s_P;                                   // [N][33]
     float* s_k = s_q + N * 33;                          // [N][33]
     float* s_v = s_k + N * 33;                          // [N][H]
     float* s_xa = s_v + N * H;                          // [N][H] aggregated messages
+    float* s_hp = s_xa + N * H;                         // [N][H] h_prev
+    float* s_gi = s_hp + N * H;                         // [N][96] GRUCell input pre-activations
+    float* s_gh = s_gi + N * G3;                        // [N][96] GRUCell hidden pre-activations (354 N <= 384 N)
 
     const float* hist = a.hist.ptr + ag * a.hist.stride_agent + b * a.hist.stride_env;
     const float* beh = a.beh.ptr + ag * a.beh.stride_agent + b * a.beh.stride_env;
@@ -91,155 +178,165 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
     __syncthreads();
 
     // ---- phase 2: factored input projections P (ego, + b_ih) and Q (neighbour) ------
-    for (int col = tid; col < 4 * G3; col += GAT_THREADS) {
-        const int d = col / (2 * G3);
-        const int part = (col - d * 2 * G3) / G3;
-        const int g = col % G3;
-        const float* wih = W + (d ? L.wih_r : L.wih_f) + g * (2 * H) + part * H;
-        float w[H];
+#pragma unroll 1
+    for (int d = 0; d < 2; ++d) {
+        const float* wih = W + (d ? L.wih_r : L.wih_f);
+        dense32_mma(s_enc, H, N, wih, 2 * H, W + (d ? L.bih_r : L.bih_f), G3, s_P + (size_t)d * N * G3, G3, false, warp, lane);
+        dense32_mma(s_enc, H, N, wih + H, 2 * H, nullptr, G3, s_Q + (size_t)d * N * G3, G3, false, warp, lane);
+    }
+    // W_hh B fragments (mma.m16n8k16 "col" operand: b0 = (k=2t,2t+1 ; n=g), b1 = (k=2t+8,2t+9 ; n=g)),
+    // B[k][n] = W_hh[gate n][hidden k]; f16 hi parts stay in registers, lo parts go to shared memory.
+    const int gq = lane >> 2, tq = lane & 3;
+    const int dir = warp >> 2, mt = warp & 3;            // warps 0-3 forward, 4-7 reverse; m-tile of 16 egos
+    uint32_t whi[NT_G][KB_H][2];
+    {
+        const float* whh = W + (dir ? L.whh_r : L.whh_f);
 #pragma unroll
-        for (int k = 0; k < H; ++k) w[k] = wih[k];
-        const float bias = part == 0 ? W[(d ? L.bih_r : L.bih_f) + g] : 0.0f;
-        float* dst = (part == 0 ? s_P : s_Q) + (size_t)d * N * G3 + g;
-        for (int n = 0; n < N; ++n) {
-            float acc = bias;
-            const float4* e4 = reinterpret_cast<const float4*>(s_enc + n * H);
+        for (int nt = 0; nt < NT_G; ++nt)
 #pragma unroll
-            for (int kk = 0; kk < H / 4; ++kk) {
-                const float4 e = e4[kk];
-                acc = fmaf(w[4 * kk + 0], e.x, acc);
-                acc = fmaf(w[4 * kk + 1], e.y, acc);
-                acc = fmaf(w[4 * kk + 2], e.z, acc);
-                acc = fmaf(w[4 * kk + 3], e.w, acc);
+            for (int kb = 0; kb < KB_H; ++kb) {
+                const float* wr = whh + (8 * nt + gq) * H + 16 * kb + 2 * tq;
+                const float2 w0 = *reinterpret_cast<const float2*>(wr);
+                const float2 w1 = *reinterpret_cast<const float2*>(wr + 8);
+                uint32_t lo0, lo1;
+                split_f16(w0.x, w0.y, whi[nt][kb][0], lo0);
+                split_f16(w1.x, w1.y, whi[nt][kb][1], lo1);
+                if (mt == 0) s_wlo[((dir * NT_G + nt) * KB_H + kb) * 32 + lane] = make_uint2(lo0, lo1);
             }
-            dst[n * G3] = acc;
-        }
     }
     __syncthreads();
 
-    // ---- phase 3: the 2N GRU chains -------------------------------------------------
+    // ---- phase 3: the 2N GRU chains on the tensor cores ------------------------------
     {
-        const int d = warp >> 2;          // warps 0-3 forward, 4-7 reverse
-        const int wi = warp & 3;
-        const int count = (N - wi + 3) >> 2;      // egos wi, wi+4, ...
-        const float* whh = W + (d ? L.whh_r : L.whh_f);
-        const float* bhh = W + (d ? L.bhh_r : L.bhh_f);
-        float w_r[H], w_z[H], w_n[H];
+        const int row0 = mt * 16 + gq, row1 = row0 + 8;                 // ego indices of this thread's two rows
+        const bool ok0 = row0 < N, ok1 = row1 < N;
+        const int i0 = ok0 ? row0 : N - 1, i1 = ok1 ? row1 : N - 1;
+        if (mt * 16 < N) {                                              // warp-uniform: tile has live egos
+            const float* bhh = W + (dir ? L.bhh_r : L.bhh_f);
+            const float* Pd = s_P + (size_t)dir * N * G3;
+            const float* Qd = s_Q + (size_t)dir * N * G3;
+            float* dl = s_dl + (size_t)dir * N * NM1;
+            const uint2* wlo = s_wlo + (size_t)dir * NT_G * KB_H * 32 + lane;
+            // per-chain constants in accumulator-fragment layout: element e of tile nt is
+            // (row e<2 ? row0 : row1, col 8*nt + 2*tq + (e&1))
+            float cst[8][4], pn[4][4], bn[4][2], wd[4][2];
 #pragma unroll
-        for (int k = 0; k < H; ++k) {
-            w_r[k] = whh[(lane) * H + k];
-            w_z[k] = whh[(H + lane) * H + k];
-            w_n[k] = whh[(2 * H + lane) * H + k];
-        }
-        const float b_r = bhh[lane], b_z = bhh[H + lane], b_n = bhh[2 * H + lane];
-        const float wd = W[L.he_w + 2 * H + d * H + lane] - W[L.he_w + d * H + lane];
-        const float* Pd = s_P + (size_t)d * N * G3;
-        const float* Qd = s_Q + (size_t)d * N * G3;
-        float* dl = s_dl + (size_t)d * N * NM1;
-        float* hb = s_hb + warp * SEQ_G * H;
-
-        for (int base = 0; base < count; base += SEQ_G) {
-            int ego[SEQ_G];
-            float pr[SEQ_G], pz[SEQ_G], pn[SEQ_G], h[SEQ_G];
+            for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-            for (int g = 0; g < SEQ_G; ++g) {
-                const bool valid = base + g < count;
-                ego[g] = valid ? wi + 4 * (base + g) : -1;
-                const int i = valid ? ego[g] : 0;
-                pr[g] = Pd[i * G3 + lane];
-                pz[g] = Pd[i * G3 + H + lane];
-                pn[g] = Pd[i * G3 + 2 * H + lane];
-                h[g] = 0.0f;
-                hb[g * H + lane] = 0.0f;
+                for (int e = 0; e < 4; ++e) {
+                    const int col = 8 * nt + 2 * tq + (e & 1);
+                    cst[nt][e] = Pd[(e < 2 ? i0 : i1) * G3 + col] + bhh[col];          // r | z : P + b_hh
+                }
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) pn[t4][e] = Pd[(e < 2 ? i0 : i1) * G3 + 2 * H + 8 * t4 + 2 * tq + (e & 1)];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c = 8 * t4 + 2 * tq + u;
+                    bn[t4][u] = bhh[2 * H + c];
+                    wd[t4][u] = W[L.he_w + 2 * H + dir * H + c] - W[L.he_w + dir * H + c];
+                }
             }
-            __syncwarp();
+            float h[4][4];
+#pragma unroll
+            for (int t4 = 0; t4 < 4; ++t4)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[t4][e] = 0.0f;
+
             for (int step = 0; step < NM1; ++step) {
-                const int s = d ? NM1 - 1 - step : step;
-                float ar[SEQ_G], az[SEQ_G], an[SEQ_G];
+                const int s = dir ? NM1 - 1 - step : step;
+                // A fragments from the hidden state (accumulator layout == A layout, see header)
+                uint32_t ahi[KB_H][4], alo[KB_H][4];
 #pragma unroll
-                for (int g = 0; g < SEQ_G; ++g) { ar[g] = b_r; az[g] = b_z; an[g] = b_n; }
-#pragma unroll
-                for (int kk = 0; kk < H / 4; ++kk) {
-#pragma unroll
-                    for (int g = 0; g < SEQ_G; ++g) {
-                        const float4 hv = *reinterpret_cast<const float4*>(hb + g * H + 4 * kk);
-                        ar[g] = fmaf(w_r[4 * kk + 0], hv.x, ar[g]);
-                        az[g] = fmaf(w_z[4 * kk + 0], hv.x, az[g]);
-                        an[g] = fmaf(w_n[4 * kk + 0], hv.x, an[g]);
-                        ar[g] = fmaf(w_r[4 * kk + 1], hv.y, ar[g]);
-                        az[g] = fmaf(w_z[4 * kk + 1], hv.y, az[g]);
-                        an[g] = fmaf(w_n[4 * kk + 1], hv.y, an[g]);
-                        ar[g] = fmaf(w_r[4 * kk + 2], hv.z, ar[g]);
-                        az[g] = fmaf(w_z[4 * kk + 2], hv.z, az[g]);
-                        an[g] = fmaf(w_n[4 * kk + 2], hv.z, an[g]);
-                        ar[g] = fmaf(w_r[4 * kk + 3], hv.w, ar[g]);
-                        az[g] = fmaf(w_z[4 * kk + 3], hv.w, az[g]);
-                        an[g] = fmaf(w_n[4 * kk + 3], hv.w, an[g]);
-                    }
+                for (int kb = 0; kb < KB_H; ++kb) {
+                    split_f16(h[2 * kb][0], h[2 * kb][1], ahi[kb][0], alo[kb][0]);          // row g,   k low
+                    split_f16(h[2 * kb][2], h[2 * kb][3], ahi[kb][1], alo[kb][1]);          // row g+8, k low
+                    split_f16(h[2 * kb + 1][0], h[2 * kb + 1][1], ahi[kb][2], alo[kb][2]);  // row g,   k high
+                    split_f16(h[2 * kb + 1][2], h[2 * kb + 1][3], ahi[kb][3], alo[kb][3]);  // row g+8, k high
                 }
-                __syncwarp();   // every lane has consumed the old states
+                // six passes over the 12 independent n-tiles: consecutive MMAs never depend on
+                // each other, so the tensor pipe stays busy (each pass is one operand pair)
+                float acc[NT_G][4];
 #pragma unroll
-                for (int g = 0; g < SEQ_G; ++g) {
-                    if (ego[g] >= 0) {       // warp-uniform
-                        const int i = ego[g];
-                        const int j = s < i ? s : s + 1;
-                        const float* qj = Qd + j * G3;
-                        const float r = sigmoidf_acc(pr[g] + qj[lane] + ar[g]);
-                        const float z = sigmoidf_acc(pz[g] + qj[H + lane] + az[g]);
-                        const float n = tanhf_acc(pn[g] + qj[2 * H + lane] + r * an[g]);
-                        h[g] = (1.0f - z) * n + z * h[g];
-                        hb[g * H + lane] = h[g];
-                        const float part = warp_sum(wd * h[g]);
-                        if (lane == 0) dl[i * NM1 + s] = part;
-                    }
+                for (int nt = 0; nt < NT_G; ++nt) {
+                    float c0[4];
+                    if (nt < 8) { c0[0] = cst[nt][0]; c0[1] = cst[nt][1]; c0[2] = cst[nt][2]; c0[3] = cst[nt][3]; }
+                    else { c0[0] = bn[nt - 8][0]; c0[1] = bn[nt - 8][1]; c0[2] = bn[nt - 8][0]; c0[3] = bn[nt - 8][1]; }
+                    mma16816(acc[nt], ahi[0], whi[nt][0][0], whi[nt][0][1], c0);
                 }
-                __syncwarp();
+#pragma unroll
+                for (int nt = 0; nt < NT_G; ++nt) mma16816(acc[nt], ahi[1], whi[nt][1][0], whi[nt][1][1], acc[nt]);
+#pragma unroll
+                for (int nt = 0; nt < NT_G; ++nt) mma16816(acc[nt], alo[0], whi[nt][0][0], whi[nt][0][1], acc[nt]);
+#pragma unroll
+                for (int nt = 0; nt < NT_G; ++nt) mma16816(acc[nt], alo[1], whi[nt][1][0], whi[nt][1][1], acc[nt]);
+#pragma unroll
+                for (int nt = 0; nt < NT_G; ++nt) {
+                    const uint2 l0 = wlo[(nt * KB_H + 0) * 32];
+                    mma16816(acc[nt], ahi[0], l0.x, l0.y, acc[nt]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < NT_G; ++nt) {
+                    const uint2 l1 = wlo[(nt * KB_H + 1) * 32];
+                    mma16816(acc[nt], ahi[1], l1.x, l1.y, acc[nt]);
+                }
+                // gates; neighbour of ego i at position s is j = s < i ? s : s + 1
+                const float* q0 = Qd + (s < i0 ? s : s + 1) * G3 + 2 * tq;
+                const float* q1 = Qd + (s < i1 ? s : s + 1) * G3 + 2 * tq;
+                float pl0 = 0.0f, pl1 = 0.0f;
+#pragma unroll
+                for (int t4 = 0; t4 < 4; ++t4) {
+                    const float2 qr0 = *reinterpret_cast<const float2*>(q0 + 8 * t4);
+                    const float2 qz0 = *reinterpret_cast<const float2*>(q0 + H + 8 * t4);
+                    const float2 qn0 = *reinterpret_cast<const float2*>(q0 + 2 * H + 8 * t4);
+                    const float2 qr1 = *reinterpret_cast<const float2*>(q1 + 8 * t4);
+                    const float2 qz1 = *reinterpret_cast<const float2*>(q1 + H + 8 * t4);
+                    const float2 qn1 = *reinterpret_cast<const float2*>(q1 + 2 * H + 8 * t4);
+                    const float qr[4] = {qr0.x, qr0.y, qr1.x, qr1.y};
+                    const float qz[4] = {qz0.x, qz0.y, qz1.x, qz1.y};
+                    const float qn[4] = {qn0.x, qn0.y, qn1.x, qn1.y};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float r = sigmoid_fast(acc[t4][e] + qr[e]);
+                        const float z = sigmoid_fast(acc[4 + t4][e] + qz[e]);
+                        const float n = tanh_fast(pn[t4][e] + qn[e] + r * acc[8 + t4][e]);
+                        h[t4][e] = n + z * (h[t4][e] - n);                  // (1 - z) n + z h
+                    }
+                    pl0 = fmaf(wd[t4][0], h[t4][0], fmaf(wd[t4][1], h[t4][1], pl0));
+                    pl1 = fmaf(wd[t4][0], h[t4][2], fmaf(wd[t4][1], h[t4][3], pl1));
+                }
+                // the 32 hidden units of a row live in the 4 lanes of a quad
+                pl0 += __shfl_xor_sync(0xffffffffu, pl0, 1); pl0 += __shfl_xor_sync(0xffffffffu, pl0, 2);
+                pl1 += __shfl_xor_sync(0xffffffffu, pl1, 1); pl1 += __shfl_xor_sync(0xffffffffu, pl1, 2);
+                if (tq == 0) {
+                    if (ok0) dl[i0 * NM1 + s] = pl0;
+                    if (ok1) dl[i1 * NM1 + s] = pl1;
+                }
             }
         }
     }
     __syncthreads();
 
     // ---- phase 4: q, k, v and the transposed GRUCell weights -------------------------
-    for (int idx = tid; idx < N * H; idx += GAT_THREADS) {
-        const int n = idx >> 5, c = idx & 31;
-        const float* e = s_enc + n * H;
-        const float* wq = W + L.q_w + c * H;
-        const float* wk = W + L.k_w + c * H;
-        const float* wv = W + L.v_w + c * H;
-        float aq = 0.0f, ak = 0.0f, av = W[L.v_b + c];
-#pragma unroll 8
-        for (int k = 0; k < H; ++k) {
-            const float ek = e[k];
-            aq = fmaf(wq[k], ek, aq);
-            ak = fmaf(wk[k], ek, ak);
-            av = fmaf(wv[k], ek, av);
-        }
-        s_q[n * 33 + c] = aq;
-        s_k[n * 33 + c] = ak;
-        s_v[n * H + c] = fmaxf(av, 0.0f);
-    }
-    for (int idx = tid; idx < 2 * G3 * H; idx += GAT_THREADS) {
-        const int m = idx / (G3 * H);
-        const int r = idx - m * G3 * H;
-        const int g = r >> 5, k = r & 31;
-        s_wt[(m * H + k) * WT_LD + g] = W[(m ? L.c_whh : L.c_wih) + g * H + k];
-    }
+    dense32_mma(s_enc, H, N, W + L.q_w, H, nullptr, H, s_q, 33, false, warp, lane);
+    dense32_mma(s_enc, H, N, W + L.k_w, H, nullptr, H, s_k, 33, false, warp, lane);
+    dense32_mma(s_enc, H, N, W + L.v_w, H, W + L.v_b, H, s_v, H, true, warp, lane);
+    for (int idx = tid; idx < N * H; idx += GAT_THREADS)          // stage h_prev for the GRUCell product
+        s_hp[idx] = hprev[(idx >> 5) * a.hprev.stride_slot + (idx & 31)];
     __syncthreads();
 
     // ---- phase 5: soft x hard attention + GRUCell, one warp per ego ------------------
     const float db = W[L.he_b + 1] - W[L.he_b + 0];
     float* wbuf = s_w + warp * 64;
-    float* hpb = s_hb + warp * SEQ_G * H;     // reuse: broadcast buffer for h_prev
     for (int i = warp; i < N; i += GAT_WARPS) {
         float sc[2], hd[2];
-        int jj[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int s = lane + 32 * u;
-            sc[u] = -INFINITY; hd[u] = 0.0f; jj[u] = 0;
+            sc[u] = -INFINITY; hd[u] = 0.0f;
             if (s < NM1) {
                 const int j = s < i ? s : s + 1;
-                jj[u] = j;
                 float acc = 0.0f;
 #pragma unroll 8
                 for (int k = 0; k < H; ++k) acc = fmaf(s_q[i * 33 + k], s_k[j * 33 + k], acc);
@@ -267,36 +364,34 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
         const float den = warp_sum(e0 + e1);
         wbuf[lane] = (e0 / den) * hd[0];
         wbuf[lane + 32] = (e1 / den) * hd[1];
-        hpb[lane] = hprev[i * a.hprev.stride_slot + lane];
         __syncwarp();
-        float xa = 0.0f;
-        for (int s = 0; s < NM1; ++s) {
-            const int j = s < i ? s : s + 1;
-            xa = fmaf(wbuf[s], s_v[j * H + lane], xa);
+        // x_i = sum_s w[s] * v[j(s)]: four independent partial sums per lane
+        float xa0 = 0.0f, xa1 = 0.0f, xa2 = 0.0f, xa3 = 0.0f;
+        int s = 0;
+        for (; s + 3 < NM1; s += 4) {
+            xa0 = fmaf(wbuf[s], s_v[(s < i ? s : s + 1) * H + lane], xa0);
+            xa1 = fmaf(wbuf[s + 1], s_v[(s + 1 < i ? s + 1 : s + 2) * H + lane], xa1);
+            xa2 = fmaf(wbuf[s + 2], s_v[(s + 2 < i ? s + 2 : s + 3) * H + lane], xa2);
+            xa3 = fmaf(wbuf[s + 3], s_v[(s + 3 < i ? s + 3 : s + 4) * H + lane], xa3);
         }
-        s_xa[i * H + lane] = xa;
+        for (; s < NM1; ++s) xa0 = fmaf(wbuf[s], s_v[(s < i ? s : s + 1) * H + lane], xa0);
+        s_xa[i * H + lane] = (xa0 + xa1) + (xa2 + xa3);
         __syncwarp();
-        // GRUCell(x_i, h_prev_i): lane c owns gate rows c, H+c, 2H+c
-        float gi0 = W[L.c_bih + lane], gi1 = W[L.c_bih + H + lane], gi2 = W[L.c_bih + 2 * H + lane];
-        float gh0 = W[L.c_bhh + lane], gh1 = W[L.c_bhh + H + lane], gh2 = W[L.c_bhh + 2 * H + lane];
-#pragma unroll 8
-        for (int k = 0; k < H; ++k) {
-            const float xk = s_xa[i * H + k];
-            const float hk = hpb[k];
-            const float* wi = s_wt + k * WT_LD;
-            const float* wh = s_wt + (H + k) * WT_LD;
-            gi0 = fmaf(wi[lane], xk, gi0);
-            gi1 = fmaf(wi[H + lane], xk, gi1);
-            gi2 = fmaf(wi[2 * H + lane], xk, gi2);
-            gh0 = fmaf(wh[lane], hk, gh0);
-            gh1 = fmaf(wh[H + lane], hk, gh1);
-            gh2 = fmaf(wh[2 * H + lane], hk, gh2);
-        }
-        const float r = sigmoidf_acc(gi0 + gh0);
-        const float z = sigmoidf_acc(gi1 + gh1);
-        const float n = tanhf_acc(gi2 + r * gh2);
-        outp[i * a.out.stride_slot + lane] = (1.0f - z) * n + z * hpb[lane];
-        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- phase 6: GRUCell(x_i, h_prev_i) (:140): two N x 96 x 32 products + gates -----
+    dense32_mma(s_xa, H, N, W + L.c_wih, H, W + L.c_bih, G3, s_gi, G3, false, warp, lane);
+    dense32_mma(s_hp, H, N, W + L.c_whh, H, W + L.c_bhh, G3, s_gh, G3, false, warp, lane);
+    __syncthreads();
+    for (int idx = tid; idx < N * H; idx += GAT_THREADS) {
+        const int n = idx >> 5, c = idx & 31;
+        const float* gi = s_gi + n * G3;
+        const float* gh = s_gh + n * G3;
+        const float r = sigmoidf_acc(gi[c] + gh[c]);
+        const float z = sigmoidf_acc(gi[H + c] + gh[H + c]);
+        const float nn = tanhf_acc(gi[2 * H + c] + r * gh[2 * H + c]);
+        outp[n * a.out.stride_slot + c] = (1.0f - z) * nn + z * s_hp[idx];
     }
 }
 

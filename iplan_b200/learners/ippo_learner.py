@@ -20,13 +20,8 @@ import math
 
 import torch as th
 
-from .. import _lib
+from .. import _lib, parallel
 from ..modules.flat import DEAD, FROZEN
-
-
-def _dist():
-    import torch.distributed as dist
-    return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
 
 
 class _AdamSlot:
@@ -118,7 +113,7 @@ class IPPOLearner:
         self.work = None
         self.last_pre = None        # pre-update tensors of the last train() (parity tests)
         self.keep_pre = False
-        self.fixed_store = None
+        self.bucket = parallel.GradBucket()
 
     # ------------------------------------------------------------------------------
     def lr_decay(self, episode, episodes):
@@ -235,12 +230,12 @@ class IPPOLearner:
         Fp = s["X"].shape[-1]
         rows = Bf * T1
         T = T1 - 1
-        dist = _dist()
+        dist = parallel.dist_or_none()
         world = dist.get_world_size() if dist else 1
         rank = dist.get_rank() if dist else 0
         # first batch_size (global) episodes are trained on (generate_data :371-394)
-        n_train_global = self.batch_size if not dist else self.batch_size
-        n_train = max(0, min(Bf, n_train_global - rank * Bf))
+        n_train_global = self.batch_size
+        n_train = parallel.shard_train_episodes(rank, world, Bf, n_train_global)
         w = self._work_buffers(A, rows, Fp)
         actor, critic = self.stacks["actor"].flat, self.stacks["critic"].flat
         X = s["X"]
@@ -256,8 +251,7 @@ class IPPOLearner:
         _lib.check(lib.iplan_learner_gae(_lib.ptr(w["old_value"]), _lib.ptr(s["reward"]), _lib.ptr(s["alive"]),
                                          self.gamma, self.gae_lambda, T1, Bf, n_train, A,
                                          _lib.ptr(w["returns"]), _lib.ptr(w["adv"]), _lib.ptr(w["moments"]), st), "gae")
-        if dist:
-            dist.all_reduce(w["moments"])
+        parallel.allreduce_sum_(w["moments"])
         _lib.check(lib.iplan_learner_adv_finalize(_lib.ptr(w["moments"]), float(n_train_global * T), _lib.ptr(w["norm"]), A, st),
                    "adv_finalize")
         ctx = self._ctx(w, s, A, Bf, T1, n_train, actor, critic, s["rnn_a"], s["rnn_c"], s["rnn_a"].stride(0), R,
@@ -278,8 +272,7 @@ class IPPOLearner:
                 _lib.ptr(actor), self.stacks["actor"].stride(), _lib.ptr(critic), self.stacks["critic"].stride(),
                 _lib.ptr(ga), _lib.ptr(gc), _lib.ptr(X), X.stride(0), Fp, F, rows, A,
                 _lib.ptr(w["Z1"]), _lib.ptr(w["SM"]), _lib.ptr(w["G"]), st), "fc1_backward")
-            if dist:
-                self._allreduce_grads(dist, ga, gc)
+            self.bucket.allreduce([ga, gc])          # ONE NCCL all-reduce per PPO epoch (no-op at world 1)
             if self.keep_pre and _ == 0:
                 self.first_grads = {"actor": ga.clone(), "critic": gc.clone()}
             for kind, g, col in (("actor", ga, 4), ("critic", gc, 5)):
@@ -306,15 +299,6 @@ class IPPOLearner:
                 self.logger.log_stat(self.log_prefix + k, self.train_info[k], t_env)
 
     num_mini_batch_ = 1
-
-    def _allreduce_grads(self, dist, ga, gc):
-        """ONE NCCL all-reduce (SUM) of actor+critic gradients of all agents per PPO epoch."""
-        if not hasattr(self, "_bucket") or self._bucket.numel() != ga.numel() + gc.numel():
-            self._bucket = th.empty(ga.numel() + gc.numel(), device=self.device)
-        na = ga.numel()
-        self._bucket[:na].copy_(ga.view(-1)); self._bucket[na:].copy_(gc.view(-1))
-        dist.all_reduce(self._bucket)
-        ga.view(-1).copy_(self._bucket[:na]); gc.view(-1).copy_(self._bucket[na:])
 
     # ---- reference-named helper (reference :344-365) ------------------------------------
     def compute_returns(self, agent_id, obs_all, rewards, terminated, rnn_state_critic_all):

@@ -117,9 +117,12 @@ class ParamStack:
         self.spec = {"gat": gat_spec, "beh": beh_spec, "actor": actor_spec, "critic": critic_spec}[kind](*dims)
         self.total, self.offsets = _lib.layout(kind, *dims)
         assert len(self.offsets) == len(self.spec)
-        self.flat = torch.zeros(n_agents, self.total, dtype=torch.float32, device=device)
+        # initialise on the host (orthogonal init = QR: dozens of tiny launches on a GPU), then move
+        self.flat = torch.zeros(n_agents, self.total, dtype=torch.float32)
         self.nets = [AgentNet(self, i) for i in range(n_agents)]
         self.reset_parameters()
+        if str(device) != "cpu":
+            self.to(device)
 
     # -- placement ----------------------------------------------------------------
     def _move(self, fn):
