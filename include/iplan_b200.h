@@ -127,11 +127,17 @@ int iplan_controller_step(const float* actor_params, int64_t actor_stride,
 int iplan_learner_row_stats(const float* X, int64_t x_stride_agent, int ldx, int feat_dim, int64_t rows,
                             int n_agents, float* stat, void* stream);
 
-/* feature LayerNorm + fc1 of actor and critic as ONE product over X (mlp.py:50-56):
- * Z1 [A][rows][128] (actor 0..63 | critic 64..127).  Wp [A][128][ldx], ws/cc [A][128] scratch. */
+/* f16 hi / lo split of the (constant) input rows, once per train(): X = Xh + Xl to ~2^-22.
+ * Xh, Xl: __half arrays with X's shape.  The two big products below stream these copies. */
+int iplan_learner_x_split(const float* X, int64_t n_elems, void* Xh, void* Xl, void* stream);
+
+/* feature LayerNorm + fc1 of actor and critic as ONE tensor-core product over X (mlp.py:50-56):
+ * Z1 [A][rows][128] (actor 0..63 | critic 64..127).  Wh/Wl [A][128][ldx] __half and ws/cc [A][128]
+ * are scratch (the LayerNorm-folded weights, rebuilt each call).  ldx % 32 == 0. */
 int iplan_learner_fc1_forward(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
-                              const float* X, int64_t x_stride_agent, int ldx, int feat_dim, int64_t rows, int n_agents,
-                              const float* stat, float* Wp, float* ws, float* cc, float* Z1, void* stream);
+                              const void* Xh, const void* Xl, int64_t x_stride_agent, int ldx, int feat_dim,
+                              int64_t rows, int n_agents, const float* stat, void* Wh, void* Wl,
+                              float* ws, float* cc, float* Z1, void* stream);
 
 typedef struct {
     const float* actor; const float* critic; int64_t actor_stride, critic_stride;   /* parameters */
@@ -157,11 +163,15 @@ typedef struct {
  *   fc1.weight / feature_norm in g_actor / g_critic. */
 int iplan_learner_tail(const iplan_learner_ctx* ctx, int train, void* stream);
 
-/* fc1.weight and feature_norm gradients from dZ1 (left in Z1 by the train tail). G [A][128][ldx] scratch. */
+/* fc1.weight and feature_norm gradients from dZ1 (left in Z1 by the train tail): tensor-core
+ * product G = dZ1^T X over the f16 copies.  Scratch: Dh/Dl [A][rows][128] __half (scaled split of
+ * dZ1), gscale [2A] floats, G [A][128][ldx] floats. */
 int iplan_learner_fc1_backward(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
                                float* g_actor, float* g_critic,
-                               const float* X, int64_t x_stride_agent, int ldx, int feat_dim, int64_t rows, int n_agents,
-                               const float* dZ1, const float* SM, float* G, void* stream);
+                               const void* Xh, const void* Xl, int64_t x_stride_agent, int ldx, int feat_dim,
+                               int64_t rows, int n_agents,
+                               const float* dZ1, void* Dh, void* Dl, float* gscale,
+                               const float* SM, float* G, void* stream);
 
 /* K2a: GAE backward scan (compute_returns :344-365), raw advantages zeroed where the agent is
  * dead (:273-277) and their moments: moments [A][4] = (sum, sum of squares, count, sum of

@@ -43,9 +43,11 @@ _SIGNATURES = {
                                    _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p,
                                    _i, _i, _i, _i, _p]),
     "iplan_learner_row_stats": (_i, [_p, _i64, _i, _i, _i64, _i, _p, _p]),
-    "iplan_learner_fc1_forward": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p]),
+    "iplan_learner_x_split": (_i, [_p, _i64, _p, _p, _p]),
+    "iplan_learner_fc1_forward": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p, _p]),
     "iplan_learner_tail": (_i, [_p, _i, _p]),
-    "iplan_learner_fc1_backward": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p]),
+    "iplan_learner_fc1_backward": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i, _i, _i64, _i,
+                                        _p, _p, _p, _p, _p, _p, _p]),
     "iplan_learner_gae": (_i, [_p, _p, _p, _f, _f, _i, _i, _i, _i, _p, _p, _p, _p]),
     "iplan_learner_adv_finalize": (_i, [_p, C.c_double, _p, _i, _p]),
     "iplan_learner_adam": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _f, _f, _i, _f, _p, _i, _p]),

@@ -72,100 +72,6 @@ __global__ void row_stats_kernel(const float* __restrict__ X, int64_t x_sa, int 
     }
 }
 
-// ---------------------------------------------------------------------------------------
-// fc1_prep: W'[a][type*64+k][f] = gamma[f] * W1[k][f] (0 for f >= F), ws = sum_f W', c = W1.beta + b1
-// ---------------------------------------------------------------------------------------
-__global__ void fc1_prep_kernel(NetParams P, int F, int ldw, float* __restrict__ Wp /* [A][128][ldw] */,
-                                float* __restrict__ ws /* [A][128] */, float* __restrict__ cc /* [A][128] */) {
-    const int a = blockIdx.y, kk = blockIdx.x;        // kk in [0,128)
-    const int type = kk >> 6, k = kk & 63;
-    const float* p = P.net(a, type);
-    const TrunkLayout L = trunk_layout(F, 1, false);  // trunk offsets do not depend on the head
-    const float* w1 = p + L.fc1_w + (int64_t)k * F;
-    float* out = Wp + ((int64_t)a * 128 + kk) * ldw;
-    float s = 0.0f, c = 0.0f;
-    for (int f = threadIdx.x; f < ldw; f += blockDim.x) {
-        float v = 0.0f;
-        if (f < F) {
-            const float w = w1[f];
-            v = p[L.ln0_w + f] * w;
-            c = fmaf(p[L.ln0_b + f], w, c);
-        }
-        out[f] = v;
-        s += v;
-    }
-    __shared__ float red[2][32];
-    s = warp_sum(s); c = warp_sum(c);
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = c; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int nw = blockDim.x >> 5;
-        s = threadIdx.x < nw ? red[0][threadIdx.x] : 0.0f;
-        c = threadIdx.x < nw ? red[1][threadIdx.x] : 0.0f;
-        s = warp_sum(s); c = warp_sum(c);
-        if (threadIdx.x == 0) { ws[a * 128 + kk] = s; cc[a * 128 + kk] = c + p[L.fc1_b + k]; }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// fc1_fwd: Z1[a][r][0..128) = rstd_r * (X_a[r] . W'[a][n] - mean_r * ws[n]) + c[n]
-// ---------------------------------------------------------------------------------------
-using Fc1Tile = GemmTile<128, 128, 16, 8, 8>;
-__global__ void __launch_bounds__(Fc1Tile::THREADS) fc1_fwd_kernel(
-    const float* __restrict__ X, int64_t x_sa, int ldx, int64_t rows, const float* __restrict__ Wp, int ldw,
-    const float* __restrict__ ws, const float* __restrict__ cc, const float* __restrict__ stat,
-    float* __restrict__ Z1 /* [A][rows][128] */) {
-    __shared__ __align__(16) float smem[Fc1Tile::SMEM_FLOATS];
-    const int a = blockIdx.y;
-    const int m0 = blockIdx.x * 128;
-    const float* xa = X + a * x_sa;
-    const float* wa = Wp + (int64_t)a * 128 * ldw;
-    float acc[8][8];
-    Fc1Tile::run<true, true>(smem, (int)rows, 128, m0, 0, 0, ldw,
-                             [&](int m, int k) { return xa[(int64_t)m * ldx + k]; },
-                             [&](int k, int n) { return wa[(int64_t)n * ldw + k]; }, acc);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = m0 + Fc1Tile::row_of(i);
-        if (r >= rows) continue;
-        const float mean = stat[(a * rows + r) * 2], rstd = stat[(a * rows + r) * 2 + 1];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int n = Fc1Tile::col_of(j);
-            Z1[(a * rows + r) * 128 + n] = rstd * (acc[i][j] - mean * ws[a * 128 + n]) + cc[a * 128 + n];
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// fc1_bwd: G[a][kk][f] += sum_r dZ1s[a][r][kk] * X_a[r][f]   (dZ1s already scaled by rstd_r)
-// split over row chunks, accumulated with atomics
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(Fc1Tile::THREADS) fc1_bwd_kernel(
-    const float* __restrict__ X, int64_t x_sa, int ldx, int64_t rows, int rows_per_chunk,
-    const float* __restrict__ dZ1 /* [A][rows][128] */, float* __restrict__ G /* [A][128][ldg] */, int ldg) {
-    __shared__ __align__(16) float smem[Fc1Tile::SMEM_FLOATS];
-    const int a = blockIdx.z;
-    const int n0 = blockIdx.x * 128;                      // feature tile
-    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
-    const int64_t r1 = min(rows, r0 + rows_per_chunk);
-    const float* xa = X + a * x_sa;
-    const float* dz = dZ1 + (int64_t)a * rows * 128;
-    float acc[8][8];
-    Fc1Tile::run<false, false>(smem, 128, ldg, 0, n0, (int)r0, (int)r1,
-                               [&](int m, int k) { return dz[(int64_t)k * 128 + m]; },
-                               [&](int k, int n) { return xa[(int64_t)k * ldx + n]; }, acc);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int kk = Fc1Tile::row_of(i);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int f = n0 + Fc1Tile::col_of(j);
-            if (f < ldg) atomicAdd(&G[((int64_t)a * 128 + kk) * ldg + f], acc[i][j]);
-        }
-    }
-}
-
 // fc1_grad_finish: from G, S = colsum(dZ1), M = sum_r dZ1s*mu  ->  grads of fc1.W, LN0 gamma/beta
 //   dW1[k][f] = gamma[f]*(G[k][f] - M[k]) + beta[f]*S[k];  dgamma[f] = sum_k W1[k][f]*(G[k][f]-M[k]);
 //   dbeta[f] = sum_k W1[k][f]*S[k]          (fc1.bias grad = S is written by ln_relu_bwd)
@@ -709,19 +615,6 @@ extern "C" int iplan_learner_row_stats(const float* X, int64_t x_stride_agent, i
     return check_launch("row_stats");
 }
 
-extern "C" int iplan_learner_fc1_forward(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
-                                         const float* X, int64_t x_stride_agent, int ldx, int feat_dim, int64_t rows, int n_agents,
-                                         const float* stat, float* Wp, float* ws, float* cc, float* Z1, void* stream) {
-    IPLAN_REQUIRE(actor && critic && X && stat && Wp && ws && cc && Z1, "fc1_forward: null pointer");
-    IPLAN_REQUIRE(ldx % 4 == 0 && ldx >= feat_dim, "fc1_forward: ldx must be a multiple of 4 and >= feat_dim");
-    NetParams P{actor, critic, actor_stride, critic_stride};
-    fc1_prep_kernel<<<dim3(128, n_agents), 256, 0, (cudaStream_t)stream>>>(P, feat_dim, ldx, Wp, ws, cc);
-    dim3 grid((unsigned)((rows + 127) / 128), n_agents);
-    fc1_fwd_kernel<<<grid, Fc1Tile::THREADS, 0, (cudaStream_t)stream>>>(X, x_stride_agent, ldx, rows, Wp, ldx, ws, cc, stat, Z1);
-    count_launch(2);
-    return check_launch("fc1_forward");
-}
-
 // everything between Z1 and the heads; train != 0 also runs the loss + backward down to dZ1
 // (scaled by rstd) and all gradients except fc1.W / LN0, which iplan_learner_fc1_backward adds.
 
@@ -788,23 +681,18 @@ extern "C" int iplan_learner_tail(const iplan_learner_ctx* c, int train, void* s
     return check_launch("learner_tail");
 }
 
-extern "C" int iplan_learner_fc1_backward(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
-                                          float* g_actor, float* g_critic,
-                                          const float* X, int64_t x_stride_agent, int ldx, int feat_dim, int64_t rows, int n_agents,
-                                          const float* dZ1, const float* SM, float* G, void* stream) {
-    IPLAN_REQUIRE(actor && critic && g_actor && g_critic && X && dZ1 && SM && G, "fc1_backward: null pointer");
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(G, 0, sizeof(float) * (size_t)n_agents * 128 * ldx, st);
-    if (e != cudaSuccess) { set_error("fc1_backward: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    const int chunk = 2048;
-    dim3 grid((unsigned)((ldx + 127) / 128), (unsigned)((rows + chunk - 1) / chunk), n_agents);
-    fc1_bwd_kernel<<<grid, Fc1Tile::THREADS, 0, st>>>(X, x_stride_agent, ldx, rows, chunk, dZ1, G, ldx);
+namespace iplan {
+// fc1.weight / feature_norm gradients from the product G (fc1_mma.cu) and the column sums S | M
+int launch_fc1_grad_finish(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
+                           float* g_actor, float* g_critic, int feat_dim, const float* G, int ldg, const float* SM,
+                           int n_agents, cudaStream_t st) {
     NetParams P{actor, critic, actor_stride, critic_stride};
     NetGrads Gr{g_actor, g_critic, actor_stride, critic_stride};
-    fc1_grad_finish_kernel<<<dim3((feat_dim + 127) / 128, n_agents, 2), 128, 0, st>>>(P, Gr, feat_dim, G, ldx, SM);
-    count_launch(2);
-    return check_launch("fc1_backward");
+    fc1_grad_finish_kernel<<<dim3((feat_dim + 127) / 128, n_agents, 2), 128, 0, st>>>(P, Gr, feat_dim, G, ldg, SM);
+    count_launch();
+    return check_launch("fc1_grad_finish");
 }
+}  // namespace iplan
 
 extern "C" int iplan_learner_gae(const float* values, const float* reward, const float* alive, float gamma, float lam,
                                  int T1, int n_eps, int n_train_eps, int n_agents,

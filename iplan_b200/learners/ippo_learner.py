@@ -178,8 +178,10 @@ class IPPOLearner:
         if self.work is None or self.work["key"] != key:
             dev = self.device
             z = lambda *s, **k: th.zeros(*s, device=dev, **k)
+            hz = lambda *s: th.zeros(*s, device=dev, dtype=th.float16)
             self.work = dict(
-                key=key, stat=z(A, rows, 2), Wp=z(A, 128, Fp), ws=z(A, 128), cc=z(A, 128), Z1=z(A, rows, 128),
+                key=key, stat=z(A, rows, 2), Wh=hz(A, 128, Fp), Wl=hz(A, 128, Fp), ws=z(A, 128), cc=z(A, 128), Z1=z(A, rows, 128),
+                Xh=hz(A, rows, Fp), Xl=hz(A, rows, Fp), Dh=hz(A, rows, 128), Dl=hz(A, rows, 128), gscale=z(2 * A),
                 A1=z(A, 2, rows, 64), Z2=z(A, 2, rows, 64), A2=z(A, 2, rows, 64), GI=z(A, 2, rows, 192), GH=z(A, 2, rows, 192),
                 SM=z(A, 2, 128), G=z(A, 128, Fp), logp=z(A, rows), ent=z(A, rows), value=z(A, rows),
                 returns=z(A, rows), adv=z(A, rows), moments=z(A, 4, dtype=th.float64), norm=z(A, 4),
@@ -211,8 +213,8 @@ class IPPOLearner:
         lib, st = _lib.lib, _lib.stream()
         _lib.check(lib.iplan_learner_fc1_forward(
             _lib.ptr(actor), self.stacks["actor"].stride(), _lib.ptr(critic), self.stacks["critic"].stride(),
-            _lib.ptr(X), X.stride(0), Fp, F, rows, A, _lib.ptr(w["stat"]), _lib.ptr(w["Wp"]), _lib.ptr(w["ws"]),
-            _lib.ptr(w["cc"]), _lib.ptr(w["Z1"]), st), "fc1_forward")
+            _lib.ptr(w["Xh"]), _lib.ptr(w["Xl"]), w["Xh"].stride(0), Fp, F, rows, A, _lib.ptr(w["stat"]),
+            _lib.ptr(w["Wh"]), _lib.ptr(w["Wl"]), _lib.ptr(w["ws"]), _lib.ptr(w["cc"]), _lib.ptr(w["Z1"]), st), "fc1_forward")
         import ctypes
         _lib.check(lib.iplan_learner_tail(ctypes.byref(ctx), 1 if train else 0, st), "learner_tail")
 
@@ -245,6 +247,8 @@ class IPPOLearner:
 
         # ---- once per train(): input LayerNorm statistics, pre-update values / log-probs, GAE
         _lib.check(lib.iplan_learner_row_stats(_lib.ptr(X), X.stride(0), Fp, F, rows, A, _lib.ptr(w["stat"]), st), "row_stats")
+        assert X.is_contiguous()
+        _lib.check(lib.iplan_learner_x_split(_lib.ptr(X), X.numel(), _lib.ptr(w["Xh"]), _lib.ptr(w["Xl"]), st), "x_split")
         self._forward(w, ctx, X, A, rows, Fp, F, actor, critic, train=False)
         w["old_logp"] = w["logp"].clone()
         w["old_value"] = w["value"].clone()
@@ -270,8 +274,9 @@ class IPPOLearner:
             self._forward(w, ctx, X, A, rows, Fp, F, actor, critic, train=True)
             _lib.check(lib.iplan_learner_fc1_backward(
                 _lib.ptr(actor), self.stacks["actor"].stride(), _lib.ptr(critic), self.stacks["critic"].stride(),
-                _lib.ptr(ga), _lib.ptr(gc), _lib.ptr(X), X.stride(0), Fp, F, rows, A,
-                _lib.ptr(w["Z1"]), _lib.ptr(w["SM"]), _lib.ptr(w["G"]), st), "fc1_backward")
+                _lib.ptr(ga), _lib.ptr(gc), _lib.ptr(w["Xh"]), _lib.ptr(w["Xl"]), w["Xh"].stride(0), Fp, F, rows, A,
+                _lib.ptr(w["Z1"]), _lib.ptr(w["Dh"]), _lib.ptr(w["Dl"]), _lib.ptr(w["gscale"]),
+                _lib.ptr(w["SM"]), _lib.ptr(w["G"]), st), "fc1_backward")
             self.bucket.allreduce([ga, gc])          # ONE NCCL all-reduce per PPO epoch (no-op at world 1)
             if self.keep_pre and _ == 0:
                 self.first_grads = {"actor": ga.clone(), "critic": gc.clone()}
@@ -344,7 +349,9 @@ def eval_rows(mac, agent_id, obs, rnn_states, net, action=None, avail=None):
     X[0, :, :F] = x
     h = rnn_states.reshape(-1, 64).to(dev, th.float32).contiguous()
     z = lambda *s, **k: th.zeros(*s, device=dev, **k)
-    w = dict(stat=z(1, rows, 2), Wp=z(1, 128, Fp), ws=z(1, 128), cc=z(1, 128), Z1=z(1, rows, 128),
+    hz = lambda *s: th.zeros(*s, device=dev, dtype=th.float16)
+    w = dict(stat=z(1, rows, 2), Wh=hz(1, 128, Fp), Wl=hz(1, 128, Fp), Xh=hz(1, rows, Fp), Xl=hz(1, rows, Fp),
+             ws=z(1, 128), cc=z(1, 128), Z1=z(1, rows, 128),
              A1=z(1, 2, rows, 64), Z2=z(1, 2, rows, 64), A2=z(1, 2, rows, 64), GI=z(1, 2, rows, 192), GH=z(1, 2, rows, 192),
              logp=z(1, rows), ent=z(1, rows), value=z(1, rows))
     actor = mac.actor_stack.flat[agent_id:agent_id + 1]
@@ -353,9 +360,10 @@ def eval_rows(mac, agent_id, obs, rnn_states, net, action=None, avail=None):
     av = (avail.reshape(rows, -1).to(dev) != 0).to(th.uint8).contiguous() if avail is not None else None
     lib, st, P = _lib.lib, _lib.stream(), _lib.ptr
     _lib.check(lib.iplan_learner_row_stats(P(X), X.stride(0), Fp, F, rows, 1, P(w["stat"]), st), "row_stats")
+    _lib.check(lib.iplan_learner_x_split(P(X), X.numel(), P(w["Xh"]), P(w["Xl"]), st), "x_split")
     _lib.check(lib.iplan_learner_fc1_forward(P(actor), mac.actor_stack.stride(), P(critic), mac.critic_stack.stride(),
-                                             P(X), X.stride(0), Fp, F, rows, 1, P(w["stat"]), P(w["Wp"]), P(w["ws"]),
-                                             P(w["cc"]), P(w["Z1"]), st), "fc1_forward")
+                                             P(w["Xh"]), P(w["Xl"]), w["Xh"].stride(0), Fp, F, rows, 1, P(w["stat"]),
+                                             P(w["Wh"]), P(w["Wl"]), P(w["ws"]), P(w["cc"]), P(w["Z1"]), st), "fc1_forward")
     c = _lib.LearnerCtx()
     c.actor, c.critic = P(actor), P(critic)
     c.actor_stride, c.critic_stride = mac.actor_stack.stride(), mac.critic_stack.stride()
