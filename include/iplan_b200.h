@@ -153,6 +153,9 @@ typedef struct {
     const float* norm;             /* [A][4] from iplan_learner_adv_finalize */
     float* stats;                  /* [A][8] += policy loss, value loss, entropy, ratio, actor |g|, critic |g| */
     float clip, ent_coef, v_coef, huber_delta;
+    float grad_scale;              /* power-of-two loss scale: every gradient buffer holds grad_scale * g
+                                      (keeps the backward operands inside f16's normal range for the
+                                      split-f16 tensor-core products); pass the same value to iplan_learner_adam */
 } iplan_learner_ctx;
 
 /* Z1 -> LN/ReLU -> fc2 -> LN/ReLU -> GRU step -> LN -> heads (R_Actor.evaluate_actions,
@@ -188,7 +191,7 @@ int iplan_learner_adv_finalize(const double* moments, double n_train_rows_global
 int iplan_learner_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* mask,
                        float* sqnorm_scratch, int64_t stride, int64_t total, int n_agents,
                        float lr, float beta1, float beta2, float eps, int step, float max_norm,
-                       float* stats, int stat_col, void* stream);
+                       float grad_scale, float* stats, int stat_col, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,7 +50,7 @@ _SIGNATURES = {
                                         _p, _p, _p, _p, _p, _p, _p]),
     "iplan_learner_gae": (_i, [_p, _p, _p, _f, _f, _i, _i, _i, _i, _p, _p, _p, _p]),
     "iplan_learner_adv_finalize": (_i, [_p, C.c_double, _p, _i, _p]),
-    "iplan_learner_adam": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _f, _f, _i, _f, _p, _i, _p]),
+    "iplan_learner_adam": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _f, _f, _i, _f, _f, _p, _i, _p]),
 }
 
 
@@ -66,7 +66,7 @@ class LearnerCtx(C.Structure):
                 ("logp_out", _p), ("ent_out", _p), ("value_out", _p),
                 ("old_logp", _p), ("old_value", _p), ("returns", _p), ("adv_raw", _p), ("alive", _p),
                 ("norm", _p), ("stats", _p),
-                ("clip", _f), ("ent_coef", _f), ("v_coef", _f), ("huber_delta", _f)]
+                ("clip", _f), ("ent_coef", _f), ("v_coef", _f), ("huber_delta", _f), ("grad_scale", _f)]
 
 
 def _bind(signatures):

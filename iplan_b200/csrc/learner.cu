@@ -21,7 +21,7 @@
 // (compute_returns :344-365 + advantage moments :272-279).
 #include <algorithm>
 
-#include "gemm_tile.cuh"
+#include "mma_tile.cuh"
 
 namespace iplan {
 
@@ -101,7 +101,7 @@ __global__ void fc1_grad_finish_kernel(NetParams P, NetGrads Gr, int F, const fl
 // ---------------------------------------------------------------------------------------
 // Linear layers on 64-wide activations (fc2: N=64, GRU projections: N=192)
 // ---------------------------------------------------------------------------------------
-using LinTile = GemmTile<64, 64, 16, 4, 4>;
+using LinTile = MmaTile<64, 64, 2, 2>;      // 128 threads, 32x32 warp tiles on the tensor cores
 
 // y[r][n] = sum_k x[r][k] W[n][k] + b[n]
 __global__ void __launch_bounds__(LinTile::THREADS) linear_fwd_kernel(
@@ -112,21 +112,19 @@ __global__ void __launch_bounds__(LinTile::THREADS) linear_fwd_kernel(
     const float* p = P.net(a, type);
     const float* W = p + w_off;
     const float* xr = x.row(a, type, 0);
-    float acc[4][4];
-    LinTile::run<true, true>(smem, (int)rows, N, m0, n0, 0, RH,
-                             [&](int m, int k) { return xr[(int64_t)m * x.ld + k]; },
-                             [&](int k, int n) { return W[n * RH + k]; }, acc);
+    float acc[LinTile::MT][LinTile::NT][4];
+    LinTile::run<true, true, false>(smem, (int)rows, N, m0, n0, 0, RH,
+                                    [&](int m, int k) { return xr[(int64_t)m * x.ld + k]; },
+                                    [&](int k, int n) { return W[n * RH + k]; }, acc);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = m0 + LinTile::row_of(i);
-        if (r >= rows) continue;
-        float* yr = y.row(a, type, r);
+    for (int i = 0; i < LinTile::MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + LinTile::col_of(j);
-            if (n < N) yr[n] = acc[i][j] + p[b_off + n];
-        }
-    }
+        for (int j = 0; j < LinTile::NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = m0 + LinTile::row_of(i, e), n = n0 + LinTile::col_of(j, e);
+                if (r < rows && n < N) y.row(a, type, r)[n] = acc[i][j][e] + p[b_off + n];
+            }
 }
 
 // dx[r][k] = sum_n dy[r][n] W[n][k]
@@ -137,18 +135,19 @@ __global__ void __launch_bounds__(LinTile::THREADS) linear_dx_kernel(
     const int m0 = blockIdx.x * 64;
     const float* W = P.net(a, type) + w_off;
     const float* dyr = dy.row(a, type, 0);
-    float acc[4][4];
-    LinTile::run<true, false>(smem, (int)rows, RH, m0, 0, 0, N,
-                              [&](int m, int k) { return dyr[(int64_t)m * dy.ld + k]; },
-                              [&](int k, int n) { return W[k * RH + n]; }, acc);
+    float acc[LinTile::MT][LinTile::NT][4];
+    LinTile::run<true, false, false>(smem, (int)rows, RH, m0, 0, 0, N,
+                                     [&](int m, int k) { return dyr[(int64_t)m * dy.ld + k]; },
+                                     [&](int k, int n) { return W[k * RH + n]; }, acc);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int r = m0 + LinTile::row_of(i);
-        if (r >= rows) continue;
-        float* o = dx.row(a, type, r);
+    for (int i = 0; i < LinTile::MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[LinTile::col_of(j)] = acc[i][j];
-    }
+        for (int j = 0; j < LinTile::NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = m0 + LinTile::row_of(i, e);
+                if (r < rows) dx.row(a, type, r)[LinTile::col_of(j, e)] = acc[i][j][e];
+            }
 }
 
 // dW[n][k] += sum_r dy[r][n] x[r][k]   (row chunks, atomics)
@@ -161,18 +160,20 @@ __global__ void __launch_bounds__(LinTile::THREADS) linear_dw_kernel(
     const int64_t r1 = min(rows, r0 + rows_per_chunk);
     const float* dyr = dy.row(a, type, 0);
     const float* xr = x.row(a, type, 0);
-    float acc[4][4];
-    LinTile::run<false, false>(smem, N, RH, m0, 0, (int)r0, (int)r1,
-                               [&](int m, int k) { return dyr[(int64_t)k * dy.ld + m]; },
-                               [&](int k, int n) { return xr[(int64_t)k * x.ld + n]; }, acc);
+    float acc[LinTile::MT][LinTile::NT][4];
+    LinTile::run<false, false, true>(smem, N, RH, m0, 0, (int)r0, (int)r1,
+                                     [&](int m, int k) { return dyr[(int64_t)k * dy.ld + m]; },
+                                     [&](int k, int n) { return xr[(int64_t)k * x.ld + n]; }, acc);
     float* gw = Gr.net(a, type) + w_off;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = m0 + LinTile::row_of(i);
-        if (n >= N) continue;
+    for (int i = 0; i < LinTile::MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) atomicAdd(&gw[n * RH + LinTile::col_of(j)], acc[i][j]);
-    }
+        for (int j = 0; j < LinTile::NT; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int n = m0 + LinTile::row_of(i, e);
+                if (n < N) atomicAdd(&gw[n * RH + LinTile::col_of(j, e)], acc[i][j][e]);
+            }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -276,7 +277,8 @@ struct HeadArgs {
     const float* old_logp; const float* old_value; const float* returns; const float* adv_raw; const float* alive;
     const float* norm;             // [A][4]: adv mean, 1/(adv std + 1e-5), 1/sum(alive over train rows), 1/n_train_rows
     float clip, ent_coef, v_coef, huber_delta;
-    float* stats;                  // [A][8]: sums of policy-loss, value-loss, entropy, ratio (already normalised)
+    float gscale;                  // power-of-two loss scale applied to d loss / d logits|value (undone in adam)
+    float* stats;                 // [A][8]: sums of policy-loss, value-loss, entropy, ratio (already normalised)
     int train;
 };
 
@@ -388,8 +390,8 @@ __global__ void __launch_bounds__(256) gru_head_kernel(HeadArgs h) {
                 float d = 0.0f;                                   // d min(s1,s2) / d logp
                 if (s1 < s2) d = s1;
                 else if (s1 == s2) d = inside ? s1 : 0.5f * s1;
-                const float g_lp = -m * inv_msum * d;
-                const float g_ent = -h.ent_coef * inv_rows;       // d(-c*mean ent)/d ent_row
+                const float g_lp = -m * inv_msum * d * h.gscale;
+                const float g_ent = -h.ent_coef * inv_rows * h.gscale;       // d(-c*mean ent)/d ent_row
 #pragma unroll
                 for (int l = 0; l < IPLAN_MAX_ACT; ++l) {
                     if (l < nA && !masked[l]) {
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(256) gru_head_kernel(HeadArgs h) {
                 const float go = -huber_os_grad(eo, h.huber_delta);
                 const float gc = inside ? -huber_os_grad(ec, h.huber_delta) : 0.0f;
                 const float g = lo > lc ? go : (lc > lo ? gc : 0.5f * (go + gc));
-                dv = h.v_coef * m * inv_msum * g;
+                dv = h.v_coef * m * inv_msum * g * h.gscale;
                 st_loss += fmaxf(lo, lc) * m * inv_msum;
             }
             dA0 = dv * hw0[0]; dA1 = dv * hw1[0];
@@ -560,11 +562,12 @@ __global__ void adv_finalize_kernel(const double* __restrict__ moments, double n
 // ---------------------------------------------------------------------------------------
 // grad_norm + Adam
 // ---------------------------------------------------------------------------------------
-__global__ void grad_sqnorm_kernel(const float* __restrict__ g, int64_t stride, int64_t total, float* __restrict__ out /* [A] */) {
+__global__ void grad_sqnorm_kernel(const float* __restrict__ g, int64_t stride, int64_t total, float inv_gscale,
+                                   float* __restrict__ out /* [A] */) {
     const int a = blockIdx.y;
     float s = 0.0f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const float v = g[a * stride + i];
+        const float v = g[a * stride + i] * inv_gscale;
         s = fmaf(v, v, s);
     }
     __shared__ float red[32];
@@ -582,7 +585,7 @@ __global__ void grad_sqnorm_kernel(const float* __restrict__ g, int64_t stride, 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ mask, const float* __restrict__ sqnorm, int64_t stride, int64_t total,
                             float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float max_norm,
-                            float* __restrict__ stats, int stat_col) {
+                            float inv_gscale, float* __restrict__ stats, int stat_col) {
     const int a = blockIdx.y;
     const float norm = sqrtf(sqnorm[a]);
     const float coef = max_norm > 0.0f ? fminf(max_norm / (norm + 1e-6f), 1.0f) : 1.0f;
@@ -590,7 +593,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         if (mask[i] == 0.0f) continue;
         const int64_t j = a * stride + i;
-        const float gr = g[j] * coef;
+        const float gr = g[j] * inv_gscale * coef;     // undo the power-of-two loss scale (exact)
         const float mm = b1 * m[j] + (1.0f - b1) * gr;
         const float vv = b2 * v[j] + (1.0f - b2) * gr * gr;
         m[j] = mm; v[j] = vv;
@@ -653,12 +656,13 @@ extern "C" int iplan_learner_tail(const iplan_learner_ctx* c, int train, void* s
     h.logp_out = c->logp_out; h.ent_out = c->ent_out; h.value_out = c->value_out;
     h.old_logp = c->old_logp; h.old_value = c->old_value; h.returns = c->returns; h.adv_raw = c->adv_raw; h.alive = c->alive;
     h.norm = c->norm; h.clip = c->clip; h.ent_coef = c->ent_coef; h.v_coef = c->v_coef; h.huber_delta = c->huber_delta;
+    h.gscale = c->grad_scale > 0.0f ? c->grad_scale : 1.0f;
     h.stats = c->stats; h.train = train;
     if (train) IPLAN_REQUIRE(c->g_actor && c->g_critic && c->old_logp && c->old_value && c->returns && c->adv_raw && c->alive && c->norm && c->stats && c->SM && c->stat,
                              "learner_tail: train mode needs gradient/loss buffers");
     gru_head_kernel<<<dim3(rw, 2 * A), 256, 0, st>>>(h); ++launches;
     if (train) {
-        const int chunk = 4096;
+        const int chunk = 1024;
         const unsigned nchunk = (unsigned)((rows + chunk - 1) / chunk);
         // GRU projections: dW_ih = dGI^T A2, dW_hh = dGH^T H0, dA2 = dGI W_ih (into the A2 buffer)
         linear_dw_kernel<<<dim3(3, nchunk, 2 * A), LinTile::THREADS, 0, st>>>(gi, a2, G, L.wih, rows, chunk, RH3, 2); ++launches;
@@ -713,15 +717,16 @@ extern "C" int iplan_learner_adv_finalize(const double* moments, double n_train_
 extern "C" int iplan_learner_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const float* mask,
                                   float* sqnorm_scratch, int64_t stride, int64_t total, int n_agents,
                                   float lr, float beta1, float beta2, float eps, int step, float max_norm,
-                                  float* stats, int stat_col, void* stream) {
-    IPLAN_REQUIRE(params && grads && exp_avg && exp_avg_sq && mask && sqnorm_scratch && step >= 1, "adam: bad arguments");
+                                  float grad_scale, float* stats, int stat_col, void* stream) {
+    IPLAN_REQUIRE(params && grads && exp_avg && exp_avg_sq && mask && sqnorm_scratch && step >= 1 && grad_scale > 0.f, "adam: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(sqnorm_scratch, 0, sizeof(float) * n_agents, st);
     if (e != cudaSuccess) { set_error("adam: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    grad_sqnorm_kernel<<<dim3(64, n_agents), 256, 0, st>>>(grads, stride, total, sqnorm_scratch);
+    const float inv = 1.0f / grad_scale;
+    grad_sqnorm_kernel<<<dim3(64, n_agents), 256, 0, st>>>(grads, stride, total, inv, sqnorm_scratch);
     const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     adam_kernel<<<dim3(128, n_agents), 256, 0, st>>>(params, grads, exp_avg, exp_avg_sq, mask, sqnorm_scratch, stride, total,
-                                                     lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), max_norm, stats, stat_col);
+                                                     lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), max_norm, inv, stats, stat_col);
     count_launch(2);
     return check_launch("adam");
 }

@@ -114,6 +114,7 @@ class IPPOLearner:
         self.last_pre = None        # pre-update tensors of the last train() (parity tests)
         self.keep_pre = False
         self.bucket = parallel.GradBucket()
+        self.grad_scale = 1.0
 
     # ------------------------------------------------------------------------------
     def lr_decay(self, episode, episodes):
@@ -207,6 +208,7 @@ class IPPOLearner:
         c.alive = P(s["alive"]) if s else None
         c.norm, c.stats = P(w["norm"]), P(w["stats"])
         c.clip, c.ent_coef, c.v_coef, c.huber_delta = self.clip_param, self.entropy_coef, self.value_loss_coef, self.huber_delta
+        c.grad_scale = self.grad_scale
         return c
 
     def _forward(self, w, ctx, X, A, rows, Fp, F, actor, critic, train):
@@ -238,6 +240,9 @@ class IPPOLearner:
         # first batch_size (global) episodes are trained on (generate_data :371-394)
         n_train_global = self.batch_size
         n_train = parallel.shard_train_episodes(rank, world, Bf, n_train_global)
+        # per-row loss gradients are O(1 / sum(alive)) ~ 1 / (rows trained on): scale them by the next
+        # power of two so the split-f16 tensor-core products of the backward see O(1) operands
+        self.grad_scale = float(2 ** max(0, math.ceil(math.log2(max(1, n_train_global * T)))))
         w = self._work_buffers(A, rows, Fp)
         actor, critic = self.stacks["actor"].flat, self.stacks["critic"].flat
         X = s["X"]
@@ -279,7 +284,7 @@ class IPPOLearner:
                 _lib.ptr(w["SM"]), _lib.ptr(w["G"]), st), "fc1_backward")
             self.bucket.allreduce([ga, gc])          # ONE NCCL all-reduce per PPO epoch (no-op at world 1)
             if self.keep_pre and _ == 0:
-                self.first_grads = {"actor": ga.clone(), "critic": gc.clone()}
+                self.first_grads = {"actor": ga / self.grad_scale, "critic": gc / self.grad_scale}
             for kind, g, col in (("actor", ga, 4), ("critic", gc, 5)):
                 self.steps[kind] += 1
                 stack = self.stacks[kind]
@@ -287,7 +292,7 @@ class IPPOLearner:
                     _lib.ptr(stack.flat), _lib.ptr(g), _lib.ptr(self.exp_avg[kind]), _lib.ptr(self.exp_avg_sq[kind]),
                     _lib.ptr(self.masks[kind]), _lib.ptr(w["sq"]), stack.stride(), stack.total, A,
                     self.lrs[kind], 0.9, 0.999, self.optim_eps, self.steps[kind], self.max_grad_norm,
-                    _lib.ptr(w["stats"]), col, st), "adam")
+                    self.grad_scale, _lib.ptr(w["stats"]), col, st), "adam")
 
         # ---- statistics: one device->host read per train() ---------------------------------
         stats = w["stats"].clone()
