@@ -19,9 +19,11 @@
 // Once per train(): row_stats (LayerNorm statistics of X rows, parameter-free), the
 // forward pre-pass (values on all T+1 steps, old log-probs) and K2a gae_adv
 // (compute_returns :344-365 + advantage moments :272-279).
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
-#include "mma_tile.cuh"
+#include "common.cuh"
 
 namespace iplan {
 
@@ -98,83 +100,8 @@ __global__ void fc1_grad_finish_kernel(NetParams P, NetGrads Gr, int F, const fl
     g[L.ln0_b + f] = db;
 }
 
-// ---------------------------------------------------------------------------------------
-// Linear layers on 64-wide activations (fc2: N=64, GRU projections: N=192)
-// ---------------------------------------------------------------------------------------
-using LinTile = MmaTile<64, 64, 2, 2>;      // 128 threads, 32x32 warp tiles on the tensor cores
-
-// y[r][n] = sum_k x[r][k] W[n][k] + b[n]
-__global__ void __launch_bounds__(LinTile::THREADS) linear_fwd_kernel(
-    RowBuf x, RowBuf y, NetParams P, int64_t w_off, int64_t b_off, int64_t rows, int N, int n_types) {
-    __shared__ __align__(16) float smem[LinTile::SMEM_FLOATS];
-    const int a = blockIdx.z / n_types, type = blockIdx.z % n_types;
-    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-    const float* p = P.net(a, type);
-    const float* W = p + w_off;
-    const float* xr = x.row(a, type, 0);
-    float acc[LinTile::MT][LinTile::NT][4];
-    LinTile::run<true, true, false>(smem, (int)rows, N, m0, n0, 0, RH,
-                                    [&](int m, int k) { return xr[(int64_t)m * x.ld + k]; },
-                                    [&](int k, int n) { return W[n * RH + k]; }, acc);
-#pragma unroll
-    for (int i = 0; i < LinTile::MT; ++i)
-#pragma unroll
-        for (int j = 0; j < LinTile::NT; ++j)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = m0 + LinTile::row_of(i, e), n = n0 + LinTile::col_of(j, e);
-                if (r < rows && n < N) y.row(a, type, r)[n] = acc[i][j][e] + p[b_off + n];
-            }
-}
-
-// dx[r][k] = sum_n dy[r][n] W[n][k]
-__global__ void __launch_bounds__(LinTile::THREADS) linear_dx_kernel(
-    RowBuf dy, RowBuf dx, NetParams P, int64_t w_off, int64_t rows, int N, int n_types) {
-    __shared__ __align__(16) float smem[LinTile::SMEM_FLOATS];
-    const int a = blockIdx.z / n_types, type = blockIdx.z % n_types;
-    const int m0 = blockIdx.x * 64;
-    const float* W = P.net(a, type) + w_off;
-    const float* dyr = dy.row(a, type, 0);
-    float acc[LinTile::MT][LinTile::NT][4];
-    LinTile::run<true, false, false>(smem, (int)rows, RH, m0, 0, 0, N,
-                                     [&](int m, int k) { return dyr[(int64_t)m * dy.ld + k]; },
-                                     [&](int k, int n) { return W[k * RH + n]; }, acc);
-#pragma unroll
-    for (int i = 0; i < LinTile::MT; ++i)
-#pragma unroll
-        for (int j = 0; j < LinTile::NT; ++j)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = m0 + LinTile::row_of(i, e);
-                if (r < rows) dx.row(a, type, r)[LinTile::col_of(j, e)] = acc[i][j][e];
-            }
-}
-
-// dW[n][k] += sum_r dy[r][n] x[r][k]   (row chunks, atomics)
-__global__ void __launch_bounds__(LinTile::THREADS) linear_dw_kernel(
-    RowBuf dy, RowBuf x, NetGrads Gr, int64_t w_off, int64_t rows, int rows_per_chunk, int N, int n_types) {
-    __shared__ __align__(16) float smem[LinTile::SMEM_FLOATS];
-    const int a = blockIdx.z / n_types, type = blockIdx.z % n_types;
-    const int m0 = blockIdx.x * 64;                     // tile of output rows n
-    const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
-    const int64_t r1 = min(rows, r0 + rows_per_chunk);
-    const float* dyr = dy.row(a, type, 0);
-    const float* xr = x.row(a, type, 0);
-    float acc[LinTile::MT][LinTile::NT][4];
-    LinTile::run<false, false, true>(smem, N, RH, m0, 0, (int)r0, (int)r1,
-                                     [&](int m, int k) { return dyr[(int64_t)k * dy.ld + m]; },
-                                     [&](int k, int n) { return xr[(int64_t)k * x.ld + n]; }, acc);
-    float* gw = Gr.net(a, type) + w_off;
-#pragma unroll
-    for (int i = 0; i < LinTile::MT; ++i)
-#pragma unroll
-        for (int j = 0; j < LinTile::NT; ++j)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int n = m0 + LinTile::row_of(i, e);
-                if (n < N) atomicAdd(&gw[n * RH + LinTile::col_of(j, e)], acc[i][j][e]);
-            }
-}
+// Linear layers on 64-wide activations (fc2, GRU projections): tensor-core kernels
+#include "lin64_mma.cuh"
 
 // ---------------------------------------------------------------------------------------
 // LayerNorm(ReLU(z)) forward / backward on 64-wide rows; one warp per (row), lane owns c, c+32
@@ -290,7 +217,7 @@ __device__ __forceinline__ float huber_os_grad(float e, float d) {
     return fabsf(e) <= d ? e : (e > d ? d : 0.0f);
 }
 
-__global__ void __launch_bounds__(256) gru_head_kernel(HeadArgs h) {
+__global__ void __launch_bounds__(128, 3) gru_head_kernel(HeadArgs h) {
     const int a = blockIdx.y >> 1, type = blockIdx.y & 1;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const float* p = h.P.net(a, type);
@@ -634,20 +561,30 @@ extern "C" int iplan_learner_tail(const iplan_learner_ctx* c, int train, void* s
     RowBuf gi{c->GI, 2 * rows * RH3, rows * RH3, RH3}, gh{c->GH, 2 * rows * RH3, rows * RH3, RH3};
     // the stored hidden inputs: type 0 reads rnn_a, type 1 reads rnn_c -> two launches for GH
     const unsigned rw = (unsigned)std::min<int64_t>((rows + 7) / 8, 148 * 8);
-    const unsigned mt = (unsigned)((rows + 63) / 64);
+    const unsigned mt = (unsigned)((rows + 63) / 64), mt128 = (unsigned)((rows + 127) / 128);
+    static bool lin_configured = false;
+    if (!lin_configured) {
+        cudaFuncSetAttribute(lin64_rows_kernel<64, 64, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lin64Rows<64, 64, 128, false>::SMEM);
+        cudaFuncSetAttribute(lin64_rows_kernel<64, 192, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lin64Rows<64, 192, 128, false>::SMEM);
+        cudaFuncSetAttribute(lin64_rows_kernel<192, 64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lin64Rows<192, 64, 64, true>::SMEM);
+        cudaFuncSetAttribute(lin64_rows_kernel<64, 64, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lin64Rows<64, 64, 128, true>::SMEM);
+        cudaFuncSetAttribute(lin64_dw_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lin64Dw<192>::SMEM);
+        cudaFuncSetAttribute(lin64_dw_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lin64Dw<64>::SMEM);
+        lin_configured = true;
+    }
     int launches = 0;
     ln_relu_fwd_kernel<<<dim3(rw, 2 * A), 256, 0, st>>>(z1, a1, P, L.ln1_w, L.ln1_b, rows, 2); ++launches;
-    linear_fwd_kernel<<<dim3(mt, 1, 2 * A), LinTile::THREADS, 0, st>>>(a1, z2, P, L.fc2_w, L.fc2_b, rows, RH, 2); ++launches;
+    lin64_rows_kernel<64, 64, 128, false><<<dim3(mt128, 2 * A), 256, Lin64Rows<64, 64, 128, false>::SMEM, st>>>(a1, z2, P, L.fc2_w, L.fc2_b, rows, 2); ++launches;
     ln_relu_fwd_kernel<<<dim3(rw, 2 * A), 256, 0, st>>>(z2, a2, P, L.ln2_w, L.ln2_b, rows, 2); ++launches;
-    linear_fwd_kernel<<<dim3(mt, 3, 2 * A), LinTile::THREADS, 0, st>>>(a2, gi, P, L.wih, L.bih, rows, RH3, 2); ++launches;
+    lin64_rows_kernel<64, 192, 128, false><<<dim3(mt128, 2 * A), 256, Lin64Rows<64, 192, 128, false>::SMEM, st>>>(a2, gi, P, L.wih, L.bih, rows, 2); ++launches;
     {   // GH = H0 W_hh^T + b_hh ; actor and critic hidden inputs live in different arrays
         RowBuf h0a{const_cast<float*>(c->rnn_a), c->rnn_stride_agent, 0, c->rnn_ld};
         RowBuf h0c{const_cast<float*>(c->rnn_c), c->rnn_stride_agent, 0, c->rnn_ld};
         NetParams Pa{c->actor, c->actor, c->actor_stride, c->actor_stride};
         NetParams Pc{c->critic, c->critic, c->critic_stride, c->critic_stride};
         RowBuf gha{c->GH, 2 * rows * RH3, 0, RH3}, ghc{c->GH + rows * RH3, 2 * rows * RH3, 0, RH3};
-        linear_fwd_kernel<<<dim3(mt, 3, A), LinTile::THREADS, 0, st>>>(h0a, gha, Pa, L.whh, L.bhh, rows, RH3, 1); ++launches;
-        linear_fwd_kernel<<<dim3(mt, 3, A), LinTile::THREADS, 0, st>>>(h0c, ghc, Pc, L.whh, L.bhh, rows, RH3, 1); ++launches;
+        lin64_rows_kernel<64, 192, 128, false><<<dim3(mt128, A), 256, Lin64Rows<64, 192, 128, false>::SMEM, st>>>(h0a, gha, Pa, L.whh, L.bhh, rows, 1); ++launches;
+        lin64_rows_kernel<64, 192, 128, false><<<dim3(mt128, A), 256, Lin64Rows<64, 192, 128, false>::SMEM, st>>>(h0c, ghc, Pc, L.whh, L.bhh, rows, 1); ++launches;
     }
     HeadArgs h;
     h.gi = gi; h.gh = gh; h.h0a = c->rnn_a; h.h0c = c->rnn_c; h.h0_sa = c->rnn_stride_agent; h.h0_ld = c->rnn_ld;
@@ -660,25 +597,26 @@ extern "C" int iplan_learner_tail(const iplan_learner_ctx* c, int train, void* s
     h.stats = c->stats; h.train = train;
     if (train) IPLAN_REQUIRE(c->g_actor && c->g_critic && c->old_logp && c->old_value && c->returns && c->adv_raw && c->alive && c->norm && c->stats && c->SM && c->stat,
                              "learner_tail: train mode needs gradient/loss buffers");
-    gru_head_kernel<<<dim3(rw, 2 * A), 256, 0, st>>>(h); ++launches;
+    gru_head_kernel<<<dim3((unsigned)std::min<int64_t>((rows + 3) / 4, 148 * 12), 2 * A), 128, 0, st>>>(h); ++launches;
     if (train) {
-        const int chunk = 1024;
-        const unsigned nchunk = (unsigned)((rows + chunk - 1) / chunk);
+        const int64_t n_tiles64 = (rows + 63) / 64;
+        const unsigned dw_ctas = (unsigned)std::min<int64_t>(n_tiles64, 32);
+        const int dw_tiles = (int)((n_tiles64 + dw_ctas - 1) / dw_ctas);
         // GRU projections: dW_ih = dGI^T A2, dW_hh = dGH^T H0, dA2 = dGI W_ih (into the A2 buffer)
-        linear_dw_kernel<<<dim3(3, nchunk, 2 * A), LinTile::THREADS, 0, st>>>(gi, a2, G, L.wih, rows, chunk, RH3, 2); ++launches;
+        lin64_dw_kernel<192><<<dim3(dw_ctas, 2 * A), 256, Lin64Dw<192>::SMEM, st>>>(gi, a2, G, L.wih, rows, dw_tiles, 2); ++launches;
         {
             RowBuf h0a{const_cast<float*>(c->rnn_a), c->rnn_stride_agent, 0, c->rnn_ld};
             RowBuf h0c{const_cast<float*>(c->rnn_c), c->rnn_stride_agent, 0, c->rnn_ld};
             RowBuf gha{c->GH, 2 * rows * RH3, 0, RH3}, ghc{c->GH + rows * RH3, 2 * rows * RH3, 0, RH3};
             NetGrads Ga{c->g_actor, c->g_actor, c->actor_stride, c->actor_stride};
             NetGrads Gc{c->g_critic, c->g_critic, c->critic_stride, c->critic_stride};
-            linear_dw_kernel<<<dim3(3, nchunk, A), LinTile::THREADS, 0, st>>>(gha, h0a, Ga, L.whh, rows, chunk, RH3, 1); ++launches;
-            linear_dw_kernel<<<dim3(3, nchunk, A), LinTile::THREADS, 0, st>>>(ghc, h0c, Gc, L.whh, rows, chunk, RH3, 1); ++launches;
+            lin64_dw_kernel<192><<<dim3(dw_ctas, A), 256, Lin64Dw<192>::SMEM, st>>>(gha, h0a, Ga, L.whh, rows, dw_tiles, 1); ++launches;
+            lin64_dw_kernel<192><<<dim3(dw_ctas, A), 256, Lin64Dw<192>::SMEM, st>>>(ghc, h0c, Gc, L.whh, rows, dw_tiles, 1); ++launches;
         }
-        linear_dx_kernel<<<dim3(mt, 1, 2 * A), LinTile::THREADS, 0, st>>>(gi, a2, P, L.wih, rows, RH3, 2); ++launches;
+        lin64_rows_kernel<192, 64, 64, true><<<dim3(mt, 2 * A), 128, Lin64Rows<192, 64, 64, true>::SMEM, st>>>(gi, a2, P, L.wih, -1, rows, 2); ++launches;
         ln_relu_bwd_kernel<<<dim3(rw, 2 * A), 256, 0, st>>>(z2, a2, P, G, L.ln2_w, L.ln2_b, L.fc2_b, rows, 2, nullptr, nullptr); ++launches;
-        linear_dw_kernel<<<dim3(1, nchunk, 2 * A), LinTile::THREADS, 0, st>>>(z2, a1, G, L.fc2_w, rows, chunk, RH, 2); ++launches;
-        linear_dx_kernel<<<dim3(mt, 1, 2 * A), LinTile::THREADS, 0, st>>>(z2, a1, P, L.fc2_w, rows, RH, 2); ++launches;
+        lin64_dw_kernel<64><<<dim3(dw_ctas, 2 * A), 256, Lin64Dw<64>::SMEM, st>>>(z2, a1, G, L.fc2_w, rows, dw_tiles, 2); ++launches;
+        lin64_rows_kernel<64, 64, 128, true><<<dim3(mt128, 2 * A), 256, Lin64Rows<64, 64, 128, true>::SMEM, st>>>(z2, a1, P, L.fc2_w, -1, rows, 2); ++launches;
         ln_relu_bwd_kernel<<<dim3(rw, 2 * A), 256, 0, st>>>(z1, a1, P, G, L.ln1_w, L.ln1_b, L.fc1_b, rows, 2, c->stat, c->SM); ++launches;
     }
     count_launch(launches);
