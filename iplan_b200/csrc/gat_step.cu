@@ -53,8 +53,14 @@ __host__ __device__ inline size_t gat_smem_floats(int N) {
 }
 
 // fast, fp32-accurate-enough gates (abs error ~1e-7): ex2.approx + rcp.approx
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+// The recurrence keeps its r|z pre-activations scaled by -log2(e) and its n pre-activation by
+// 2 log2(e) (the scale is folded into W_hh, b_hh, P and Q once per CTA), so that
+//   sigmoid(x) = 1 / (1 + 2^(x'))   and   tanh(x) = 1 - 2 / (1 + 2^(x'))
+// cost one ex2.approx + one add + one rcp.approx each (abs error ~1e-7).
+constexpr float K_RZ = -1.4426950408889634f;      // -log2(e)
+constexpr float K_N = 2.8853900817779268f;        //  2 log2(e)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // (x, y) -> packed f16 hi pair and f16 lo (residual) pair
 __device__ __forceinline__ void split_f16(float x, float y, uint32_t& hi, uint32_t& lo) {
@@ -198,12 +204,16 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
                 const float* wr = whh + (8 * nt + gq) * H + 16 * kb + 2 * tq;
                 const float2 w0 = *reinterpret_cast<const float2*>(wr);
                 const float2 w1 = *reinterpret_cast<const float2*>(wr + 8);
+                const float ks = nt < 8 ? K_RZ : K_N;               // gate-activation scale folded into W_hh
                 uint32_t lo0, lo1;
-                split_f16(w0.x, w0.y, whi[nt][kb][0], lo0);
-                split_f16(w1.x, w1.y, whi[nt][kb][1], lo1);
+                split_f16(ks * w0.x, ks * w0.y, whi[nt][kb][0], lo0);
+                split_f16(ks * w1.x, ks * w1.y, whi[nt][kb][1], lo1);
                 if (mt == 0) s_wlo[((dir * NT_G + nt) * KB_H + kb) * 32 + lane] = make_uint2(lo0, lo1);
             }
     }
+    __syncthreads();
+    for (int idx = tid; idx < 2 * N * G3; idx += GAT_THREADS)       // ... and into the neighbour projection Q
+        s_Q[idx] *= (idx % G3) < 2 * H ? K_RZ : K_N;
     __syncthreads();
 
     // ---- phase 3: the 2N GRU chains on the tensor cores ------------------------------
@@ -225,16 +235,16 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int col = 8 * nt + 2 * tq + (e & 1);
-                    cst[nt][e] = Pd[(e < 2 ? i0 : i1) * G3 + col] + bhh[col];          // r | z : P + b_hh
+                    cst[nt][e] = K_RZ * (Pd[(e < 2 ? i0 : i1) * G3 + col] + bhh[col]);  // r | z : P + b_hh
                 }
 #pragma unroll
             for (int t4 = 0; t4 < 4; ++t4) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) pn[t4][e] = Pd[(e < 2 ? i0 : i1) * G3 + 2 * H + 8 * t4 + 2 * tq + (e & 1)];
+                for (int e = 0; e < 4; ++e) pn[t4][e] = K_N * Pd[(e < 2 ? i0 : i1) * G3 + 2 * H + 8 * t4 + 2 * tq + (e & 1)];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const int c = 8 * t4 + 2 * tq + u;
-                    bn[t4][u] = bhh[2 * H + c];
+                    bn[t4][u] = K_N * bhh[2 * H + c];
                     wd[t4][u] = W[L.he_w + 2 * H + dir * H + c] - W[L.he_w + dir * H + c];
                 }
             }
@@ -298,10 +308,11 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
                     const float qn[4] = {qn0.x, qn0.y, qn1.x, qn1.y};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float r = sigmoid_fast(acc[t4][e] + qr[e]);
-                        const float z = sigmoid_fast(acc[4 + t4][e] + qz[e]);
-                        const float n = tanh_fast(pn[t4][e] + qn[e] + r * acc[8 + t4][e]);
-                        h[t4][e] = n + z * (h[t4][e] - n);                  // (1 - z) n + z h
+                        const float r = rcp_approx(1.0f + ex2_approx(acc[t4][e] + qr[e]));
+                        const float z = rcp_approx(1.0f + ex2_approx(acc[4 + t4][e] + qz[e]));
+                        const float en = ex2_approx(fmaf(r, acc[8 + t4][e], pn[t4][e] + qn[e]));
+                        const float n = fmaf(-2.0f, rcp_approx(1.0f + en), 1.0f);
+                        h[t4][e] = fmaf(z, h[t4][e] - n, n);                // (1 - z) n + z h
                     }
                     pl0 = fmaf(wd[t4][0], h[t4][0], fmaf(wd[t4][1], h[t4][1], pl0));
                     pl1 = fmaf(wd[t4][0], h[t4][2], fmaf(wd[t4][1], h[t4][3], pl1));
