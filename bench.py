@@ -124,25 +124,33 @@ def run_reference(args):
     from iplan_b200.config import make_args
     from oracle import cpu_baseline as cb
     a = make_args("highway", use_cuda=False, device="cpu")
-    cores = os.cpu_count()
+    cores = cb.usable_cpus()
     torch.set_num_threads(cores)
-    B, T = args.envs_per_gpu * args.gpus, a.episode_limit
+    Bl = args.envs_per_gpu
+    B, T = Bl * args.gpus, a.episode_limit
     params = cb.random_params(a)
-    train_eps = 16
+    # size each step's sample from a probe so that K+W steps end within a few minutes
+    probe = cb.time_rollout_steps(a, params, 16, 1, warmup=0)
+    per_step_budget = max(4.0, min(20.0, 150.0 / (args.warmup + args.steps)))
+    Bs = Bl
+    while Bs > 16 and probe * (Bs / 16) > 0.6 * per_step_budget:
+        Bs //= 2
+    train_eps = 8
+    cb._log(f"{cores} threads, probe {probe:.2f} s at 16 envs -> each step: 1 timestep at {Bs} envs + update at {train_eps} episodes")
     times = []
     for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        t_step = cb.time_rollout_steps(a, params, args.envs_per_gpu, 1, warmup=0, seed=it)
-        t_train = cb.time_train(a, params, train_eps, seed=it) * (args.envs_per_gpu / train_eps)
+        t_step = cb.time_rollout_steps(a, params, Bs, 1, warmup=0, seed=it) * (Bl / Bs)
+        t_train = cb.time_train(a, params, train_eps, seed=it) * (Bl / train_eps)
+        cb._log(f"step {it}: timestep {t_step:.2f} s (scaled to {Bl} envs), update {t_train:.2f} s (scaled)")
         if it >= args.warmup:
-            times.append((t_step, t_train, time.perf_counter() - t0))
+            times.append((t_step, t_train))
     t_step = sum(t[0] for t in times) / len(times)
     t_train = sum(t[1] for t in times) / len(times)
     # the CPU path does not shard: N x 512 envs cost N x the 512-env time
     step_s = (T * t_step + t_train) * args.gpus
     value = B * T / step_s
-    sample = (f"each step: 1 rollout timestep at B={args.envs_per_gpu} (x{T}) + one update at Bf={train_eps} episodes "
-              f"scaled x{args.envs_per_gpu / train_eps:g} in rows; x{args.gpus} for the {B}-env job (no sharding on CPU)")
+    sample = (f"each step: 1 rollout timestep at {Bs} envs (scaled x{Bl / Bs:g}, x{T} timesteps) + one update at Bf={train_eps} "
+              f"episodes scaled x{Bl / train_eps:g} in rows; x{args.gpus} for the {B}-env job (no sharding on CPU); {cores} torch threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
@@ -152,6 +160,10 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
 def main():
@@ -184,9 +196,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log(f"rank {rank}/{world}: system built, warm-up x{args.warmup}")
     for _ in range(args.warmup):
         sysm.run_and_train()
     barrier()
+    log("timed region")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -223,6 +237,7 @@ def main():
     gat_mean = sum(gat_ms) / max(1, len(gat_ms))
 
     # ---- e2e: same work through the reference-facing numpy API -----------------------------
+    log(f"timed region done: {ms_per_step:.1f} ms/step; e2e leg")
     e2e = None
     if not args.no_e2e:
         sysm.run_and_train(api=True)                        # warm-up of the API path
@@ -267,6 +282,7 @@ def main():
         "ms_rollout": sum(roll_ms) / max(1, len(roll_ms)), "ms_update": ms_per_step - sum(roll_ms) / max(1, len(roll_ms)),
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
     }
+    log("gpu legs done" + ("; cpu baseline" if world == 1 and not args.no_cpu_baseline else ""))
     if world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline as cb
         from iplan_b200.config import make_args

@@ -88,49 +88,64 @@ __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, co
                                             int warp, int lane) {
     const int gq = lane >> 2, tq = lane & 3;
     const int mtiles = (N + 15) >> 4, ntiles = cols >> 3;
-    int cur_mt = -1;
-    uint32_t ahi[KB_H][4], alo[KB_H][4];
-    for (int task = warp; task < mtiles * ntiles; task += GAT_WARPS) {
-        const int mt = task / ntiles, nt = task - mt * ntiles;      // consecutive tasks share the m-tile
-        const int r0 = mt * 16 + gq, r1 = r0 + 8;
-        if (mt != cur_mt) {
-            cur_mt = mt;
-            const float* x0 = in + min(r0, N - 1) * ldin + 2 * tq;
-            const float* x1 = in + min(r1, N - 1) * ldin + 2 * tq;
+    const int mh = (mtiles + 1) >> 1;                 // a task = one n-tile x one half of the m-tiles
+    const int ntask = ntiles * 2;
+    constexpr int DT = 3;                             // tasks whose weight fragments are fetched together
+    for (int base = warp; base < ntask; base += GAT_WARPS * DT) {
+        float2 wv[DT][4];
 #pragma unroll
-            for (int kb = 0; kb < KB_H; ++kb) {
-                const float2 v00 = *reinterpret_cast<const float2*>(x0 + 16 * kb);
-                const float2 v10 = *reinterpret_cast<const float2*>(x1 + 16 * kb);
-                const float2 v01 = *reinterpret_cast<const float2*>(x0 + 16 * kb + 8);
-                const float2 v11 = *reinterpret_cast<const float2*>(x1 + 16 * kb + 8);
-                split_f16(v00.x, v00.y, ahi[kb][0], alo[kb][0]);
-                split_f16(v10.x, v10.y, ahi[kb][1], alo[kb][1]);
-                split_f16(v01.x, v01.y, ahi[kb][2], alo[kb][2]);
-                split_f16(v11.x, v11.y, ahi[kb][3], alo[kb][3]);
+        for (int i = 0; i < DT; ++i) {                // issue every global load first: one L2 round trip
+            const int task = base + i * GAT_WARPS;
+            if (task < ntask) {
+                const float* wr = Wg + (size_t)(8 * (task >> 1) + gq) * ldw + 2 * tq;
+                wv[i][0] = *reinterpret_cast<const float2*>(wr);
+                wv[i][1] = *reinterpret_cast<const float2*>(wr + 8);
+                wv[i][2] = *reinterpret_cast<const float2*>(wr + 16);
+                wv[i][3] = *reinterpret_cast<const float2*>(wr + 24);
             }
         }
-        const int c0 = 8 * nt + 2 * tq;
-        float acc[4];
-        const float b0 = bias ? bias[c0] : 0.0f, b1 = bias ? bias[c0 + 1] : 0.0f;
-        const float cinit[4] = {b0, b1, b0, b1};
-        const float* wr = Wg + (size_t)(8 * nt + gq) * ldw + 2 * tq;
-        uint32_t bh[KB_H][2], bl[KB_H][2];
 #pragma unroll
-        for (int kb = 0; kb < KB_H; ++kb) {
-            const float2 w0 = *reinterpret_cast<const float2*>(wr + 16 * kb);
-            const float2 w1 = *reinterpret_cast<const float2*>(wr + 16 * kb + 8);
-            split_f16(w0.x, w0.y, bh[kb][0], bl[kb][0]);
-            split_f16(w1.x, w1.y, bh[kb][1], bl[kb][1]);
+        for (int i = 0; i < DT; ++i) {
+            const int task = base + i * GAT_WARPS;
+            if (task >= ntask) break;
+            const int nt = task >> 1, half = task & 1;
+            const int c0 = 8 * nt + 2 * tq;
+            const float b0 = bias ? bias[c0] : 0.0f, b1 = bias ? bias[c0 + 1] : 0.0f;
+            const float cinit[4] = {b0, b1, b0, b1};
+            uint32_t bh[KB_H][2], bl[KB_H][2];
+            split_f16(wv[i][0].x, wv[i][0].y, bh[0][0], bl[0][0]);
+            split_f16(wv[i][1].x, wv[i][1].y, bh[0][1], bl[0][1]);
+            split_f16(wv[i][2].x, wv[i][2].y, bh[1][0], bl[1][0]);
+            split_f16(wv[i][3].x, wv[i][3].y, bh[1][1], bl[1][1]);
+            const int mt_end = min(mtiles, (half + 1) * mh);
+            for (int mt = half * mh; mt < mt_end; ++mt) {
+                const int r0 = mt * 16 + gq, r1 = r0 + 8;
+                const float* x0 = in + min(r0, N - 1) * ldin + 2 * tq;
+                const float* x1 = in + min(r1, N - 1) * ldin + 2 * tq;
+                uint32_t ahi[KB_H][4], alo[KB_H][4];
+#pragma unroll
+                for (int kb = 0; kb < KB_H; ++kb) {
+                    const float2 v00 = *reinterpret_cast<const float2*>(x0 + 16 * kb);
+                    const float2 v10 = *reinterpret_cast<const float2*>(x1 + 16 * kb);
+                    const float2 v01 = *reinterpret_cast<const float2*>(x0 + 16 * kb + 8);
+                    const float2 v11 = *reinterpret_cast<const float2*>(x1 + 16 * kb + 8);
+                    split_f16(v00.x, v00.y, ahi[kb][0], alo[kb][0]);
+                    split_f16(v10.x, v10.y, ahi[kb][1], alo[kb][1]);
+                    split_f16(v01.x, v01.y, ahi[kb][2], alo[kb][2]);
+                    split_f16(v11.x, v11.y, ahi[kb][3], alo[kb][3]);
+                }
+                float acc[4];
+                mma16816(acc, ahi[0], bh[0][0], bh[0][1], cinit);
+                mma16816(acc, ahi[1], bh[1][0], bh[1][1], acc);
+                mma16816(acc, alo[0], bh[0][0], bh[0][1], acc);
+                mma16816(acc, alo[1], bh[1][0], bh[1][1], acc);
+                mma16816(acc, ahi[0], bl[0][0], bl[0][1], acc);
+                mma16816(acc, ahi[1], bl[1][0], bl[1][1], acc);
+                if (relu) { acc[0] = fmaxf(acc[0], 0.f); acc[1] = fmaxf(acc[1], 0.f); acc[2] = fmaxf(acc[2], 0.f); acc[3] = fmaxf(acc[3], 0.f); }
+                if (r0 < N) { out[r0 * ldout + c0] = acc[0]; out[r0 * ldout + c0 + 1] = acc[1]; }
+                if (r1 < N) { out[r1 * ldout + c0] = acc[2]; out[r1 * ldout + c0 + 1] = acc[3]; }
+            }
         }
-        mma16816(acc, ahi[0], bh[0][0], bh[0][1], cinit);
-        mma16816(acc, ahi[1], bh[1][0], bh[1][1], acc);
-        mma16816(acc, alo[0], bh[0][0], bh[0][1], acc);
-        mma16816(acc, alo[1], bh[1][0], bh[1][1], acc);
-        mma16816(acc, ahi[0], bl[0][0], bl[0][1], acc);
-        mma16816(acc, ahi[1], bl[1][0], bl[1][1], acc);
-        if (relu) { acc[0] = fmaxf(acc[0], 0.f); acc[1] = fmaxf(acc[1], 0.f); acc[2] = fmaxf(acc[2], 0.f); acc[3] = fmaxf(acc[3], 0.f); }
-        if (r0 < N) { out[r0 * ldout + c0] = acc[0]; out[r0 * ldout + c0 + 1] = acc[1]; }
-        if (r1 < N) { out[r1 * ldout + c0] = acc[2]; out[r1 * ldout + c0 + 1] = acc[3]; }
     }
 }
 
@@ -342,6 +357,12 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
     float* wbuf = s_w + warp * 64;
     for (int i = warp; i < N; i += GAT_WARPS) {
         float sc[2], hd[2];
+        uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+        if (!a.gumbel) {
+            const int64_t key = (((int64_t)ag * a.n_envs + b) * N + i) * 32 + lane;
+            rnd = philox4x32(make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.counter, (uint32_t)(a.counter >> 32)),
+                             make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int s = lane + 32 * u;
@@ -357,12 +378,9 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
                 if (a.gumbel) {
                     noise = a.gumbel[2 * edge + 1] - a.gumbel[2 * edge];
                 } else {
-                    const uint4 rnd = philox4x32(
-                        make_uint4((uint32_t)edge, (uint32_t)(edge >> 32), (uint32_t)a.counter,
-                                   (uint32_t)(a.counter >> 32)),
-                        make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-                    const float uu = u01(rnd.x);
-                    noise = logf(uu) - log1pf(-uu);          // Gumbel - Gumbel ~ Logistic(0,1)
+                    // one Philox call per (ego, lane) serves both of the lane's edges (s = lane, lane + 32)
+                    const float uu = u01(u == 0 ? rnd.x : rnd.y);
+                    noise = __logf(uu) - __logf(1.0f - uu);  // Gumbel - Gumbel ~ Logistic(0,1)
                 }
                 const float dlog = s_dl[i * NM1 + s] + s_dl[(size_t)N * NM1 + i * NM1 + s] + db;
                 hd[u] = sigmoidf_acc((dlog + noise) * a.inv_tau);

@@ -147,18 +147,50 @@ def time_train(args, params, Bf, seed=0):
     return time.perf_counter() - t0
 
 
-def measure(args, B=512, rollout_steps=2, train_eps=32, threads=None):
-    """env-steps/s of the CPU port for the B-env workload: rollout timesteps timed at the full B,
-    the update timed at `train_eps` episodes and scaled linearly in rows (its cost is
-    row-proportional: GEMMs and row-wise ops over Bf*T rows)."""
-    threads = threads or os.cpu_count()
+def usable_cpus(cap=32):
+    """Host threads torch may use: the scheduler affinity, clipped by the cgroup CPU quota (a
+    container that shows 128 cores but owns 8 of them crawls when 128 OpenMP threads spin)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, cap))
+
+
+def _log(msg):
+    import sys
+    print(f"[cpu_baseline {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def measure(args, B=512, rollout_steps=2, train_eps=32, threads=None, budget_s=25.0):
+    """env-steps/s of the CPU port for the B-env workload, on a BOUNDED sample: a probe timestep
+    at 16 envs sizes the sample so that rollout timing (1 warm-up + `rollout_steps` timesteps at
+    B_s <= B envs) and one update at `train_eps` episodes fit ~`budget_s` seconds.  Rollout cost
+    per env is taken from the B_s-env timing (it improves slowly with B: the reference's per-op
+    overhead amortises), the update is scaled linearly in rows (GEMMs and row-wise ops over Bf*T)."""
+    threads = threads or usable_cpus()
     torch.set_num_threads(threads)
     params = random_params(args)
     T = args.episode_limit
-    t_step = time_rollout_steps(args, params, B, rollout_steps, warmup=1)
-    t_train_small = time_train(args, params, train_eps)
-    t_train = t_train_small * (B / train_eps)
-    value = B * T / (T * t_step + t_train)
-    sample = (f"rollout: 1 warm-up + {rollout_steps} timed timesteps at B={B} (x{T} for the episode); update: one "
-              f"train() at Bf={train_eps} (T={T}, {args.ppo_epoch} epochs, {args.n_agents} agents) scaled x{B / train_eps:g} in rows")
-    return dict(value=value, t_step=t_step, t_train=t_train, cores=threads, sample=sample)
+    t0 = time.perf_counter()
+    probe = time_rollout_steps(args, params, 16, 1, warmup=0)
+    _log(f"{threads} threads; probe timestep at 16 envs: {probe:.2f} s")
+    Bs = B
+    while Bs > 16 and probe * (Bs / 16) * (1 + rollout_steps) > 0.6 * budget_s:
+        Bs //= 2
+    t_step = time_rollout_steps(args, params, Bs, rollout_steps, warmup=1)
+    _log(f"rollout timestep at {Bs} envs: {t_step:.2f} s")
+    eps = train_eps
+    while eps > 4 and (time.perf_counter() - t0) + 0.5 * eps > budget_s * 1.5:
+        eps //= 2
+    t_train_small = time_train(args, params, eps)
+    _log(f"update at {eps} episodes: {t_train_small:.2f} s")
+    t_train = t_train_small * (B / eps)
+    value = B * T / (T * t_step * (B / Bs) + t_train)
+    sample = (f"rollout: 1 warm-up + {rollout_steps} timed timesteps at {Bs} envs (scaled x{B / Bs:g} to {B} envs, x{T} "
+              f"timesteps); update: one train() at Bf={eps} episodes (T={T}, {args.ppo_epoch} epochs, {args.n_agents} agents) "
+              f"scaled x{B / eps:g} in rows; {threads} torch threads")
+    return dict(value=value, t_step=t_step * (B / Bs), t_train=t_train, cores=threads, sample=sample)
