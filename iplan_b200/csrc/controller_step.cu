@@ -8,6 +8,8 @@
 //   actor: Linear(64,n_act), logits[avail==0] = -1e10, Categorical sample/mode, log-prob
 //          (act.py:81-85, distributions.py:14-28,64-68);  critic: Linear(64,1) (popart.py:41-46)
 // One CTA handles CTRL_ROWS envs of one agent; both nets share the staged input rows.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace iplan {
@@ -15,7 +17,7 @@ namespace iplan {
 constexpr int R = IPLAN_RNN;            // 64
 constexpr int CTRL_THREADS = 256;
 constexpr int CTRL_WARPS = CTRL_THREADS / 32;
-constexpr int CTRL_ROWS = 8;
+constexpr int CTRL_ROWS = 16;
 constexpr float LN_EPS = 1e-5f;
 
 struct CtrlArgs {
@@ -55,73 +57,106 @@ __device__ __forceinline__ void ln64(float& v0, float& v1, const float* __restri
     v1 = d1 * rstd * g[lane + 32] + bta[lane + 32];
 }
 
+__device__ __forceinline__ void csplit(float x, float y, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void cmma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cldsm(uint32_t (&r)[4], const void* p) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(s));
+}
+
 __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlArgs a) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ag = blockIdx.y, b0 = blockIdx.x * CTRL_ROWS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int F = a.feat_dim, LD = a.feat_ld;
-    float* s_x = smem;                          // [ROWS][LD] raw rows
-    float* s_y = s_x + CTRL_ROWS * LD;          // [ROWS][LD] normalised rows for the current net
-    float* s_z = s_y + CTRL_ROWS * LD;          // [2][ROWS][64] fc1 pre-activations
+    const int F = a.feat_dim;
+    const int K16 = (F + 15) & ~15, LDH = K16 + 8;              // f16 row pitch: conflict-free ldmatrix
+    __half* s_yh = reinterpret_cast<__half*>(smem_raw);         // [ROWS][LDH] normalised rows, f16 hi
+    __half* s_yl = s_yh + CTRL_ROWS * LDH;                      // [ROWS][LDH] ... f16 lo
+    float* s_z = reinterpret_cast<float*>(s_yl + CTRL_ROWS * LDH);   // [2][ROWS][64] fc1 pre-activations
     float* s_act = s_z + 2 * CTRL_ROWS * R;     // [2*ROWS][64] per-task activation buffer
     float* s_h0 = s_act + 2 * CTRL_ROWS * R;    // [2*ROWS][64] per-task hidden input
     float* s_stat = s_h0 + 2 * CTRL_ROWS * R;   // [ROWS][2] mean, rstd
 
-    // ---- stage rows, LayerNorm statistics over the F input features -----------------
-    for (int r = 0; r < CTRL_ROWS; ++r) {
+    // ---- LayerNorm statistics over the F input features (two passes, rows stay in L1/L2) -------
+    for (int r = warp; r < CTRL_ROWS; r += CTRL_WARPS) {
         const int b = min(b0 + r, a.n_envs - 1);
         const float* src = a.feat + ag * a.feat_sa + b * a.feat_se;
-        for (int f = tid; f < LD; f += CTRL_THREADS) s_x[r * LD + f] = f < F ? src[f] : 0.0f;
-    }
-    __syncthreads();
-    {
-        const int r = warp;                     // CTRL_WARPS == CTRL_ROWS
         float s = 0.0f;
-        for (int f = lane; f < F; f += 32) s += s_x[r * LD + f];
+        for (int f = lane; f < F; f += 32) s += src[f];
         const float mean = warp_sum(s) / (float)F;
         float v = 0.0f;
-        for (int f = lane; f < F; f += 32) { const float d = s_x[r * LD + f] - mean; v = fmaf(d, d, v); }
+        for (int f = lane; f < F; f += 32) { const float d = src[f] - mean; v = fmaf(d, d, v); }
         const float var = warp_sum(v) / (float)F;
         if (lane == 0) { s_stat[2 * r] = mean; s_stat[2 * r + 1] = 1.0f / sqrtf(var + LN_EPS); }
     }
     __syncthreads();
 
-    // ---- fc1 for both nets ------------------------------------------------------------
+    // ---- fc1 for both nets on the tensor cores: [16 rows x K] . W1^T, one 8-output n-tile per warp
+    const int gq = lane >> 2, tq = lane & 3;
     for (int net = 0; net < 2; ++net) {
         const float* P = net == 0 ? a.actor + (int64_t)ag * a.actor_stride : a.critic + (int64_t)ag * a.critic_stride;
         const TrunkLayout L = trunk_layout(F, net == 0 ? a.n_actions : 1, net == 1);
-        for (int f = tid; f < LD; f += CTRL_THREADS) {
+        for (int f = tid; f < K16; f += CTRL_THREADS) {          // y = LN(x) as f16 hi + lo
             const float g = f < F ? P[L.ln0_w + f] : 0.0f;
             const float bt = f < F ? P[L.ln0_b + f] : 0.0f;
-#pragma unroll
-            for (int r = 0; r < CTRL_ROWS; ++r)
-                s_y[r * LD + f] = (s_x[r * LD + f] - s_stat[2 * r]) * s_stat[2 * r + 1] * g + bt;
+#pragma unroll 4
+            for (int r = 0; r < CTRL_ROWS; ++r) {
+                const int b = min(b0 + r, a.n_envs - 1);
+                const float x = f < F ? a.feat[ag * a.feat_sa + b * a.feat_se + f] : 0.0f;
+                const float y = f < F ? (x - s_stat[2 * r]) * s_stat[2 * r + 1] * g + bt : 0.0f;
+                const __half h = __float2half_rn(y);
+                s_yh[r * LDH + f] = h;
+                s_yl[r * LDH + f] = __float2half_rn(y - __half2float(h));
+            }
         }
         __syncthreads();
-        float acc[8][CTRL_ROWS];
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        const float* w1 = P + L.fc1_w + (int64_t)(warp * 8 + gq) * F;       // this lane's weight row
+        const __half* ah_base = s_yh + (lane & 15) * LDH + (lane >> 4) * 8;
+        const __half* al_base = s_yl + (lane & 15) * LDH + (lane >> 4) * 8;
+        const int nkb = K16 >> 4;
+        for (int kc = 0; kc < nkb; kc += 4) {                    // 4 k-blocks: 12 chained MMAs, then fp32 add
+            float wv[4][4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-#pragma unroll
-            for (int r = 0; r < CTRL_ROWS; ++r) acc[k][r] = 0.0f;
-        const float* w1 = P + L.fc1_w + (int64_t)(warp * 8) * F;
-        for (int f = lane; f < F; f += 32) {
-            float yv[CTRL_ROWS];
-#pragma unroll
-            for (int r = 0; r < CTRL_ROWS; ++r) yv[r] = s_y[r * LD + f];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float w = __ldg(w1 + (int64_t)k * F + f);
-#pragma unroll
-                for (int r = 0; r < CTRL_ROWS; ++r) acc[k][r] = fmaf(w, yv[r], acc[k][r]);
+            for (int q = 0; q < 4; ++q) {                        // all weight loads of the chunk first
+                const int k0 = 16 * (kc + q) + 2 * tq;
+                const bool on = kc + q < nkb;
+                wv[q][0] = (on && k0 < F) ? __ldg(w1 + k0) : 0.0f;
+                wv[q][1] = (on && k0 + 1 < F) ? __ldg(w1 + k0 + 1) : 0.0f;
+                wv[q][2] = (on && k0 + 8 < F) ? __ldg(w1 + k0 + 8) : 0.0f;
+                wv[q][3] = (on && k0 + 9 < F) ? __ldg(w1 + k0 + 9) : 0.0f;
             }
+            float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (kc + q < nkb) {
+                    uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+                    cldsm(ah, ah_base + 16 * (kc + q));
+                    cldsm(al, al_base + 16 * (kc + q));
+                    csplit(wv[q][0], wv[q][1], bh0, bl0);
+                    csplit(wv[q][2], wv[q][3], bh1, bl1);
+                    cmma(part, ah, bh0, bh1);
+                    cmma(part, al, bh0, bh1);
+                    cmma(part, ah, bl0, bl1);
+                }
+            }
+            acc[0] += part[0]; acc[1] += part[1]; acc[2] += part[2]; acc[3] += part[3];
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-#pragma unroll
-            for (int r = 0; r < CTRL_ROWS; ++r) {
-                const float t = warp_sum(acc[k][r]);
-                if (lane == 0) s_z[(net * CTRL_ROWS + r) * R + warp * 8 + k] = t + P[L.fc1_b + warp * 8 + k];
-            }
+        const int n0 = warp * 8 + 2 * tq;
+        s_z[(net * CTRL_ROWS + gq) * R + n0] = acc[0] + P[L.fc1_b + n0];
+        s_z[(net * CTRL_ROWS + gq) * R + n0 + 1] = acc[1] + P[L.fc1_b + n0 + 1];
+        s_z[(net * CTRL_ROWS + gq + 8) * R + n0] = acc[2] + P[L.fc1_b + n0];
+        s_z[(net * CTRL_ROWS + gq + 8) * R + n0 + 1] = acc[3] + P[L.fc1_b + n0 + 1];
         __syncthreads();
     }
 
@@ -257,7 +292,8 @@ extern "C" int iplan_controller_step(const float* actor_params, int64_t actor_st
     a.actions = actions; a.logp = logp; a.values = values; a.logits = logits;
     a.next_onehot = next_onehot; a.this_onehot = this_onehot;
     a.n_envs = n_envs; a.feat_dim = feat_dim; a.feat_ld = (feat_dim + 3) & ~3; a.n_actions = n_actions;
-    const size_t smem = ((size_t)2 * CTRL_ROWS * a.feat_ld + 6 * CTRL_ROWS * R + 2 * CTRL_ROWS) * sizeof(float);
+    const size_t ldh = ((feat_dim + 15) & ~15) + 8;
+    const size_t smem = (size_t)2 * CTRL_ROWS * ldh * 2 + ((size_t)6 * CTRL_ROWS * R + 2 * CTRL_ROWS) * sizeof(float);
     IPLAN_REQUIRE(smem <= 227 * 1024, "controller_step: feat_dim %d needs %zu B of shared memory", feat_dim, smem);
     static size_t configured = 0;
     if (smem > configured) {
