@@ -115,6 +115,7 @@ class IPPOLearner:
         self.keep_pre = False
         self.bucket = parallel.GradBucket()
         self.grad_scale = 1.0
+        self.use_dist = True        # False: ignore an active process group (single-rank reference runs in tests)
 
     # ------------------------------------------------------------------------------
     def lr_decay(self, episode, episodes):
@@ -234,7 +235,7 @@ class IPPOLearner:
         Fp = s["X"].shape[-1]
         rows = Bf * T1
         T = T1 - 1
-        dist = parallel.dist_or_none()
+        dist = parallel.dist_or_none() if self.use_dist else None
         world = dist.get_world_size() if dist else 1
         rank = dist.get_rank() if dist else 0
         # first batch_size (global) episodes are trained on (generate_data :371-394)
@@ -260,7 +261,8 @@ class IPPOLearner:
         _lib.check(lib.iplan_learner_gae(_lib.ptr(w["old_value"]), _lib.ptr(s["reward"]), _lib.ptr(s["alive"]),
                                          self.gamma, self.gae_lambda, T1, Bf, n_train, A,
                                          _lib.ptr(w["returns"]), _lib.ptr(w["adv"]), _lib.ptr(w["moments"]), st), "gae")
-        parallel.allreduce_sum_(w["moments"])
+        if dist:
+            dist.all_reduce(w["moments"])
         _lib.check(lib.iplan_learner_adv_finalize(_lib.ptr(w["moments"]), float(n_train_global * T), _lib.ptr(w["norm"]), A, st),
                    "adv_finalize")
         ctx = self._ctx(w, s, A, Bf, T1, n_train, actor, critic, s["rnn_a"], s["rnn_c"], s["rnn_a"].stride(0), R,
@@ -282,7 +284,8 @@ class IPPOLearner:
                 _lib.ptr(ga), _lib.ptr(gc), _lib.ptr(w["Xh"]), _lib.ptr(w["Xl"]), w["Xh"].stride(0), Fp, F, rows, A,
                 _lib.ptr(w["Z1"]), _lib.ptr(w["Dh"]), _lib.ptr(w["Dl"]), _lib.ptr(w["gscale"]),
                 _lib.ptr(w["SM"]), _lib.ptr(w["G"]), st), "fc1_backward")
-            self.bucket.allreduce([ga, gc])          # ONE NCCL all-reduce per PPO epoch (no-op at world 1)
+            if dist:
+                self.bucket.allreduce([ga, gc])      # ONE NCCL all-reduce per PPO epoch
             if self.keep_pre and _ == 0:
                 self.first_grads = {"actor": ga / self.grad_scale, "critic": gc / self.grad_scale}
             for kind, g, col in (("actor", ga, 4), ("critic", gc, 5)):
