@@ -235,6 +235,7 @@ def main():
     gat_ms = [s.elapsed_time(e) for tag, s, e in gat_events if tag == "gat"]
     roll_ms = [s.elapsed_time(e) for tag, s, e in gat_events if tag == "roll"]
     gat_mean = sum(gat_ms) / max(1, len(gat_ms))
+    breakdown = {tag: sum(s.elapsed_time(e) for tg, s, e in gat_events if tg == tag) / args.steps for tag in ("gat", "ctrl", "beh")}
 
     # ---- e2e: same work through the reference-facing numpy API -----------------------------
     log(f"timed region done: {ms_per_step:.1f} ms/step; e2e leg")
@@ -280,7 +281,7 @@ def main():
                    "feat_dim": sysm.mac.input_shape, "episode_limit": T, "ppo_epoch": a.ppo_epoch,
                    "parallelism": f"env-sharded x{world}", "l2": "inputs (2.3 GB episode store) exceed L2"},
         "ms_rollout": sum(roll_ms) / max(1, len(roll_ms)), "ms_update": ms_per_step - sum(roll_ms) / max(1, len(roll_ms)),
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
+        "rollout_kernels_ms": breakdown, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
     }
     log("gpu legs done" + ("; cpu baseline" if world == 1 and not args.no_cpu_baseline else ""))
     if world == 1 and not args.no_cpu_baseline:

@@ -70,7 +70,7 @@ __device__ __forceinline__ void to_afrag(const float (&v)[4][4], uint32_t (&hi)[
     }
 }
 
-__global__ void __launch_bounds__(BEH_THREADS, 1) behavior_step_kernel(BehArgs a) {
+__global__ void __launch_bounds__(BEH_THREADS, 2) behavior_step_kernel(BehArgs a) {
     extern __shared__ __align__(16) unsigned char raw[];
     BehSmem& S = *reinterpret_cast<BehSmem*>(raw);
     const int ag = blockIdx.y;
@@ -177,53 +177,59 @@ __global__ void __launch_bounds__(BEH_THREADS, 1) behavior_step_kernel(BehArgs a
         uint32_t uhi[2][4], ulo[2][4], hhi[2][4], hlo[2][4];
         to_afrag(u, uhi, ulo);
         to_afrag(h, hhi, hlo);
-        float acc[NT3][4], ahn[4][4];
-        // input part: r|z|n tiles from u
+        // hidden units in groups of 8 (t4): the group's r|z|n tiles take their MMA passes (independent
+        // chains), then its gates run while the next group's MMAs are in flight; only one group's
+        // accumulators are live at a time (register budget for 2 CTAs per SM)
 #pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) {
-            const float2 bb = S.bias[nt][tq];
-            const float c[4] = {bb.x, bb.y, bb.x, bb.y};
-            bmma(acc[nt], uhi[0], S.wih[0][nt][0][lane], c);
-        }
+        for (int t4 = 0; t4 < 4; ++t4) {
+            float acc[3][4], ahn[4];
 #pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) bmma(acc[nt], uhi[1], S.wih[0][nt][1][lane], acc[nt]);
-#pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) bmma(acc[nt], ulo[0], S.wih[0][nt][0][lane], acc[nt]);
-#pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) bmma(acc[nt], ulo[1], S.wih[0][nt][1][lane], acc[nt]);
-#pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) bmma(acc[nt], uhi[0], S.wih[1][nt][0][lane], acc[nt]);
-#pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) bmma(acc[nt], uhi[1], S.wih[1][nt][1][lane], acc[nt]);
-        // hidden part: r|z accumulate on top, n kept apart (n = tanh(i_n + r * h_n))
-#pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) {
-            if (nt < 8) bmma(acc[nt], hhi[0], S.whh[0][nt][0][lane], acc[nt]);
-            else {
-                const float2 bb = S.bias[nt + 4][tq];
+            for (int gi = 0; gi < 3; ++gi) {                       // input part from u: bias as C operand
+                const int nt = 4 * gi + t4;
+                const float2 bb = S.bias[nt][tq];
                 const float c[4] = {bb.x, bb.y, bb.x, bb.y};
-                bmma(ahn[nt - 8], hhi[0], S.whh[0][nt][0][lane], c);
+                bmma(acc[gi], uhi[0], S.wih[0][nt][0][lane], c);
             }
-        }
+            {
+                const float2 bb = S.bias[12 + t4][tq];              // b_hn
+                const float c[4] = {bb.x, bb.y, bb.x, bb.y};
+                bmma(ahn, hhi[0], S.whh[0][8 + t4][0][lane], c);
+            }
 #pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) { float (&d)[4] = nt < 8 ? acc[nt] : ahn[nt - 8]; bmma(d, hhi[1], S.whh[0][nt][1][lane], d); }
+            for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; bmma(acc[gi], uhi[1], S.wih[0][nt][1][lane], acc[gi]); }
+            bmma(ahn, hhi[1], S.whh[0][8 + t4][1][lane], ahn);
 #pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) { float (&d)[4] = nt < 8 ? acc[nt] : ahn[nt - 8]; bmma(d, hlo[0], S.whh[0][nt][0][lane], d); }
+            for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; bmma(acc[gi], ulo[0], S.wih[0][nt][0][lane], acc[gi]); }
+            bmma(ahn, hlo[0], S.whh[0][8 + t4][0][lane], ahn);
 #pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) { float (&d)[4] = nt < 8 ? acc[nt] : ahn[nt - 8]; bmma(d, hlo[1], S.whh[0][nt][1][lane], d); }
+            for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; bmma(acc[gi], ulo[1], S.wih[0][nt][1][lane], acc[gi]); }
+            bmma(ahn, hlo[1], S.whh[0][8 + t4][1][lane], ahn);
 #pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) { float (&d)[4] = nt < 8 ? acc[nt] : ahn[nt - 8]; bmma(d, hhi[0], S.whh[1][nt][0][lane], d); }
+            for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; bmma(acc[gi], uhi[0], S.wih[1][nt][0][lane], acc[gi]); }
+            bmma(ahn, hhi[0], S.whh[1][8 + t4][0][lane], ahn);
 #pragma unroll
-        for (int nt = 0; nt < NT3; ++nt) { float (&d)[4] = nt < 8 ? acc[nt] : ahn[nt - 8]; bmma(d, hhi[1], S.whh[1][nt][1][lane], d); }
+            for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; bmma(acc[gi], uhi[1], S.wih[1][nt][1][lane], acc[gi]); }
+            bmma(ahn, hhi[1], S.whh[1][8 + t4][1][lane], ahn);
+            // hidden part of r|z accumulates on top of the input part
 #pragma unroll
-        for (int t4 = 0; t4 < 4; ++t4)
+            for (int gi = 0; gi < 2; ++gi) {
+                const int nt = 4 * gi + t4;
+                bmma(acc[gi], hhi[0], S.whh[0][nt][0][lane], acc[gi]);
+                bmma(acc[gi], hhi[1], S.whh[0][nt][1][lane], acc[gi]);
+                bmma(acc[gi], hlo[0], S.whh[0][nt][0][lane], acc[gi]);
+                bmma(acc[gi], hlo[1], S.whh[0][nt][1][lane], acc[gi]);
+                bmma(acc[gi], hhi[0], S.whh[1][nt][0][lane], acc[gi]);
+                bmma(acc[gi], hhi[1], S.whh[1][nt][1][lane], acc[gi]);
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float r = bsigmoid(acc[t4][e]);
-                const float z = bsigmoid(acc[4 + t4][e]);
-                const float n = btanh(acc[8 + t4][e] + r * ahn[t4][e]);
+                const float r = bsigmoid(acc[0][e]);
+                const float z = bsigmoid(acc[1][e]);
+                const float n = btanh(acc[2][e] + r * ahn[e]);
                 h[t4][e] = n + z * (h[t4][e] - n);
             }
+            asm volatile("" ::: "memory");       // keep the next group's fragment loads from being hoisted (registers)
+        }
     }
 
     // ---- latent = softmax(W_o h + b_o), soft update, stores -----------------------------------------

@@ -17,7 +17,8 @@ namespace iplan {
 constexpr int R = IPLAN_RNN;            // 64
 constexpr int CTRL_THREADS = 256;
 constexpr int CTRL_WARPS = CTRL_THREADS / 32;
-constexpr int CTRL_ROWS = 16;
+constexpr int CTRL_ROWS = 18;            // 512 envs -> 29 row groups x 5 agents = 145 CTAs: one wave on 148 SMs
+constexpr int CTRL_MT = (CTRL_ROWS + 15) / 16;   // MMA m-tiles per CTA
 constexpr float LN_EPS = 1e-5f;
 
 struct CtrlArgs {
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlAr
         for (int f = tid; f < K16; f += CTRL_THREADS) {          // y = LN(x) as f16 hi + lo
             const float g = f < F ? P[L.ln0_w + f] : 0.0f;
             const float bt = f < F ? P[L.ln0_b + f] : 0.0f;
-#pragma unroll 4
+#pragma unroll 2
             for (int r = 0; r < CTRL_ROWS; ++r) {
                 const int b = min(b0 + r, a.n_envs - 1);
                 const float x = f < F ? a.feat[ag * a.feat_sa + b * a.feat_se + f] : 0.0f;
@@ -120,10 +121,18 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlAr
             }
         }
         __syncthreads();
-        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        float acc[CTRL_MT][4];
+#pragma unroll
+        for (int m = 0; m < CTRL_MT; ++m) acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.0f;
         const float* w1 = P + L.fc1_w + (int64_t)(warp * 8 + gq) * F;       // this lane's weight row
-        const __half* ah_base = s_yh + (lane & 15) * LDH + (lane >> 4) * 8;
-        const __half* al_base = s_yl + (lane & 15) * LDH + (lane >> 4) * 8;
+        const __half* ah_base[CTRL_MT];
+        const __half* al_base[CTRL_MT];
+#pragma unroll
+        for (int m = 0; m < CTRL_MT; ++m) {                      // rows past CTRL_ROWS re-read the last row (unused)
+            const int row = min(16 * m + (lane & 15), CTRL_ROWS - 1);
+            ah_base[m] = s_yh + row * LDH + (lane >> 4) * 8;
+            al_base[m] = s_yl + row * LDH + (lane >> 4) * 8;
+        }
         const int nkb = K16 >> 4;
         for (int kc = 0; kc < nkb; kc += 4) {                    // 4 k-blocks: 12 chained MMAs, then fp32 add
             float wv[4][4];
@@ -136,27 +145,42 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlAr
                 wv[q][2] = (on && k0 + 8 < F) ? __ldg(w1 + k0 + 8) : 0.0f;
                 wv[q][3] = (on && k0 + 9 < F) ? __ldg(w1 + k0 + 9) : 0.0f;
             }
-            float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            float part[CTRL_MT][4];
+#pragma unroll
+            for (int m = 0; m < CTRL_MT; ++m) part[m][0] = part[m][1] = part[m][2] = part[m][3] = 0.0f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (kc + q < nkb) {
-                    uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
-                    cldsm(ah, ah_base + 16 * (kc + q));
-                    cldsm(al, al_base + 16 * (kc + q));
+                    uint32_t bh0, bl0, bh1, bl1;
                     csplit(wv[q][0], wv[q][1], bh0, bl0);
                     csplit(wv[q][2], wv[q][3], bh1, bl1);
-                    cmma(part, ah, bh0, bh1);
-                    cmma(part, al, bh0, bh1);
-                    cmma(part, ah, bl0, bl1);
+#pragma unroll
+                    for (int m = 0; m < CTRL_MT; ++m) {
+                        uint32_t ah[4], al[4];
+                        cldsm(ah, ah_base[m] + 16 * (kc + q));
+                        cldsm(al, al_base[m] + 16 * (kc + q));
+                        cmma(part[m], ah, bh0, bh1);
+                        cmma(part[m], al, bh0, bh1);
+                        cmma(part[m], ah, bl0, bl1);
+                    }
                 }
             }
-            acc[0] += part[0]; acc[1] += part[1]; acc[2] += part[2]; acc[3] += part[3];
+#pragma unroll
+            for (int m = 0; m < CTRL_MT; ++m) {
+                acc[m][0] += part[m][0]; acc[m][1] += part[m][1]; acc[m][2] += part[m][2]; acc[m][3] += part[m][3];
+            }
         }
         const int n0 = warp * 8 + 2 * tq;
-        s_z[(net * CTRL_ROWS + gq) * R + n0] = acc[0] + P[L.fc1_b + n0];
-        s_z[(net * CTRL_ROWS + gq) * R + n0 + 1] = acc[1] + P[L.fc1_b + n0 + 1];
-        s_z[(net * CTRL_ROWS + gq + 8) * R + n0] = acc[2] + P[L.fc1_b + n0];
-        s_z[(net * CTRL_ROWS + gq + 8) * R + n0 + 1] = acc[3] + P[L.fc1_b + n0 + 1];
+#pragma unroll
+        for (int m = 0; m < CTRL_MT; ++m)
+#pragma unroll
+            for (int hr = 0; hr < 2; ++hr) {
+                const int row = 16 * m + gq + 8 * hr;
+                if (row < CTRL_ROWS) {
+                    s_z[(net * CTRL_ROWS + row) * R + n0] = acc[m][2 * hr] + P[L.fc1_b + n0];
+                    s_z[(net * CTRL_ROWS + row) * R + n0 + 1] = acc[m][2 * hr + 1] + P[L.fc1_b + n0 + 1];
+                }
+            }
         __syncthreads();
     }
 

@@ -280,38 +280,40 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
                     split_f16(h[2 * kb + 1][0], h[2 * kb + 1][1], ahi[kb][2], alo[kb][2]);  // row g,   k high
                     split_f16(h[2 * kb + 1][2], h[2 * kb + 1][3], ahi[kb][3], alo[kb][3]);  // row g+8, k high
                 }
-                // six passes over the 12 independent n-tiles: consecutive MMAs never depend on
-                // each other, so the tensor pipe stays busy (each pass is one operand pair)
-                float acc[NT_G][4];
-#pragma unroll
-                for (int nt = 0; nt < NT_G; ++nt) {
-                    float c0[4];
-                    if (nt < 8) { c0[0] = cst[nt][0]; c0[1] = cst[nt][1]; c0[2] = cst[nt][2]; c0[3] = cst[nt][3]; }
-                    else { c0[0] = bn[nt - 8][0]; c0[1] = bn[nt - 8][1]; c0[2] = bn[nt - 8][0]; c0[3] = bn[nt - 8][1]; }
-                    mma16816(acc[nt], ahi[0], whi[nt][0][0], whi[nt][0][1], c0);
-                }
-#pragma unroll
-                for (int nt = 0; nt < NT_G; ++nt) mma16816(acc[nt], ahi[1], whi[nt][1][0], whi[nt][1][1], acc[nt]);
-#pragma unroll
-                for (int nt = 0; nt < NT_G; ++nt) mma16816(acc[nt], alo[0], whi[nt][0][0], whi[nt][0][1], acc[nt]);
-#pragma unroll
-                for (int nt = 0; nt < NT_G; ++nt) mma16816(acc[nt], alo[1], whi[nt][1][0], whi[nt][1][1], acc[nt]);
-#pragma unroll
-                for (int nt = 0; nt < NT_G; ++nt) {
-                    const uint2 l0 = wlo[(nt * KB_H + 0) * 32];
-                    mma16816(acc[nt], ahi[0], l0.x, l0.y, acc[nt]);
-                }
-#pragma unroll
-                for (int nt = 0; nt < NT_G; ++nt) {
-                    const uint2 l1 = wlo[(nt * KB_H + 1) * 32];
-                    mma16816(acc[nt], ahi[1], l1.x, l1.y, acc[nt]);
-                }
                 // gates; neighbour of ego i at position s is j = s < i ? s : s + 1
                 const float* q0 = Qd + (s < i0 ? s : s + 1) * G3 + 2 * tq;
                 const float* q1 = Qd + (s < i1 ? s : s + 1) * G3 + 2 * tq;
                 float pl0 = 0.0f, pl1 = 0.0f;
+                // Hidden units in groups of 8 (t4): the r|z|n tiles of a group take their six MMA
+                // passes (three independent chains), then the group's gate math runs while the
+                // next group's MMAs are in flight, so tensor, MUFU and FP32 pipes overlap within one warp.
 #pragma unroll
                 for (int t4 = 0; t4 < 4; ++t4) {
+                    float acc[3][4];
+#pragma unroll
+                    for (int gi = 0; gi < 3; ++gi) {
+                        const int nt = 4 * gi + t4;
+                        float c0[4];
+                        if (gi < 2) { c0[0] = cst[nt][0]; c0[1] = cst[nt][1]; c0[2] = cst[nt][2]; c0[3] = cst[nt][3]; }
+                        else { c0[0] = bn[t4][0]; c0[1] = bn[t4][1]; c0[2] = bn[t4][0]; c0[3] = bn[t4][1]; }
+                        mma16816(acc[gi], ahi[0], whi[nt][0][0], whi[nt][0][1], c0);
+                    }
+#pragma unroll
+                    for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; mma16816(acc[gi], ahi[1], whi[nt][1][0], whi[nt][1][1], acc[gi]); }
+#pragma unroll
+                    for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; mma16816(acc[gi], alo[0], whi[nt][0][0], whi[nt][0][1], acc[gi]); }
+#pragma unroll
+                    for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; mma16816(acc[gi], alo[1], whi[nt][1][0], whi[nt][1][1], acc[gi]); }
+#pragma unroll
+                    for (int gi = 0; gi < 3; ++gi) {
+                        const uint2 l0 = wlo[((4 * gi + t4) * KB_H + 0) * 32];
+                        mma16816(acc[gi], ahi[0], l0.x, l0.y, acc[gi]);
+                    }
+#pragma unroll
+                    for (int gi = 0; gi < 3; ++gi) {
+                        const uint2 l1 = wlo[((4 * gi + t4) * KB_H + 1) * 32];
+                        mma16816(acc[gi], ahi[1], l1.x, l1.y, acc[gi]);
+                    }
                     const float2 qr0 = *reinterpret_cast<const float2*>(q0 + 8 * t4);
                     const float2 qz0 = *reinterpret_cast<const float2*>(q0 + H + 8 * t4);
                     const float2 qn0 = *reinterpret_cast<const float2*>(q0 + 2 * H + 8 * t4);
@@ -323,9 +325,9 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
                     const float qn[4] = {qn0.x, qn0.y, qn1.x, qn1.y};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float r = rcp_approx(1.0f + ex2_approx(acc[t4][e] + qr[e]));
-                        const float z = rcp_approx(1.0f + ex2_approx(acc[4 + t4][e] + qz[e]));
-                        const float en = ex2_approx(fmaf(r, acc[8 + t4][e], pn[t4][e] + qn[e]));
+                        const float r = rcp_approx(1.0f + ex2_approx(acc[0][e] + qr[e]));
+                        const float z = rcp_approx(1.0f + ex2_approx(acc[1][e] + qz[e]));
+                        const float en = ex2_approx(fmaf(r, acc[2][e], pn[t4][e] + qn[e]));
                         const float n = fmaf(-2.0f, rcp_approx(1.0f + en), 1.0f);
                         h[t4][e] = fmaf(z, h[t4][e] - n, n);                // (1 - z) n + z h
                     }

@@ -69,6 +69,18 @@ class SyntheticHighway:
         w[:, :, :, W - (t - lo + 1):] = self.history[lo:t + 1].permute(1, 2, 3, 0, 4)
         return w
 
+    def host_episode(self):
+        """Host-memory copies of the episode (numpy, fp32), as a CPU simulator + observation wrapper
+        would deliver them: history[t] [B,A,N,o], window[t] [B,A,N,W,o], reward [T,B,A],
+        terminated [T,B,A].  Built once per generated episode (2.6 GB at B=512)."""
+        if getattr(self, "_host", None) is None or self._host["episode"] != self.episodes:
+            T = self.T
+            self._host = dict(episode=self.episodes,
+                              history=[self.history[t].cpu().numpy() for t in range(T + 1)],
+                              window=[self.window(t).cpu().numpy() for t in range(T + 1)],
+                              reward=self.reward.cpu().numpy(), terminated=self.terminated.cpu().numpy())
+        return self._host
+
     def close(self):
         pass
 
@@ -166,27 +178,31 @@ class ParallelRunner:
 
         events = getattr(self, "gat_events", None)
 
-        def gat(*a):
-            """K1 launch, optionally bracketed by CUDA events on the launching stream (bench.py)."""
+        def timed(tag, fn, *a, **k):
+            """Kernel launch, optionally bracketed by CUDA events on the launching stream (bench.py)."""
             if events is None:
-                return self.prediction_learner.gat_step(*a)
+                return fn(*a, **k)
             e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
             e0.record()
-            self.prediction_learner.gat_step(*a)
+            out = fn(*a, **k)
             e1.record()
-            events.append(("gat", e0, e1))
+            events.append((tag, e0, e1))
+            return out
+
+        def gat(*a):
+            return timed("gat", self.prediction_learner.gat_step, *a)
 
         push_history(0)
         gat(hist_v[:, :, 0], zeros_beh, zeros_att, att_v[:, :, 0])
         for t in range(T):
-            acts, _, _ = self.mac.controller_step(
+            acts, _, _ = timed("ctrl", self.mac.controller_step,
                 packed[:, :, t], rnn_a[:, :, t], rnn_c[:, :, t], rnn_a[:, :, t + 1], rnn_c[:, :, t + 1],
                 None, test_mode=test_mode, next_onehot=onehot_cols[:, :, t + 1],
                 this_onehot=onehot_cols[:, :, 0] if t == 0 else None)
             actions_all[:, :, t] = acts
             push_history(t + 1)
             gat(hist_v[:, :, t + 1], beh_v[:, :, t], att_v[:, :, t], att_v[:, :, t + 1])
-            self.behavior_learner.behavior_step(window, enc_hid, beh_v[:, :, t], beh_v[:, :, t + 1])
+            timed("beh", self.behavior_learner.behavior_step, window, enc_hid, beh_v[:, :, t], beh_v[:, :, t + 1])
         # episode-level stores in the reference's layout [B,T+1,A,*]
         batch["actions"][..., 0] = actions_all.permute(1, 2, 0).long()
         batch["actions_onehot"].zero_().scatter_(-1, batch["actions"], 1.0)
@@ -213,18 +229,19 @@ class ParallelRunner:
         enc_rnn = np.zeros((B, args.num_encoder_layer, A, N, args.encoder_rnn_dim), dtype=np.float32)
         beh = np.zeros((B, A, N, args.latent_dim), dtype=np.float32)
         att = np.zeros((B, A, N, args.attention_dim), dtype=np.float32)
-        hist_np = [env.history[t].cpu().numpy() for t in range(T + 1)]     # what the env would hand over
+        host = env.host_episode()                     # what the env / observation wrapper hand over (host memory)
+        hist_np, win_np = host["history"], host["window"]
         single = hist_np[0]
         att = self.prediction_learner.GAT_latent_update(single, att, beh)
         batch.update({"avail_actions": avail, "rnn_states_actors": rnn_a, "rnn_states_critics": rnn_c,
                       "history": single, "behavior_latent": beh, "attention_latent": att}, ts=0)
-        rew, term = env.reward.cpu().numpy(), env.terminated.cpu().numpy()
+        rew, term = host["reward"], host["terminated"]
         for t in range(T):
             _, actions, _, rnn_a, rnn_c = self.mac.select_actions_ippo(batch, t_ep=t, test_mode=test_mode)
             batch.update({"actions": actions}, ts=t, mark_filled=False)
             single = hist_np[t + 1]
             att = self.prediction_learner.GAT_latent_update(single, att, beh)
-            beh, enc_rnn = self.behavior_learner.latent_update(env.window(t + 1).cpu().numpy(), enc_rnn, beh)
+            beh, enc_rnn = self.behavior_learner.latent_update(win_np[t + 1], enc_rnn, beh)
             batch.update({"reward": rew[t], "terminated": term[t]}, ts=t, mark_filled=False)
             batch.update({"avail_actions": avail, "rnn_states_actors": rnn_a, "rnn_states_critics": rnn_c,
                           "history": single, "behavior_latent": beh, "attention_latent": att}, ts=t + 1, mark_filled=True)
