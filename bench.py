@@ -206,6 +206,7 @@ def main():
         sampler.start()
     gat_events = []
     sysm.runner.gat_events = gat_events
+    sysm.learner.events = []
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     em = torch.cuda.Event(enable_timing=True)
@@ -226,6 +227,12 @@ def main():
     launches = (_lib.launch_count() - l0) / args.steps
     clocks = sampler.stop() if rank == 0 else None
     sysm.runner.gat_events = None
+    upd = {}
+    lev = sysm.learner.events
+    sysm.learner.events = None
+    for (tag, e0), (_, e1) in zip(lev[:-1], lev[1:]):
+        if tag != "end":
+            upd[tag] = upd.get(tag, 0.0) + e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -281,7 +288,7 @@ def main():
                    "feat_dim": sysm.mac.input_shape, "episode_limit": T, "ppo_epoch": a.ppo_epoch,
                    "parallelism": f"env-sharded x{world}", "l2": "inputs (2.3 GB episode store) exceed L2"},
         "ms_rollout": sum(roll_ms) / max(1, len(roll_ms)), "ms_update": ms_per_step - sum(roll_ms) / max(1, len(roll_ms)),
-        "rollout_kernels_ms": breakdown, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
+        "rollout_kernels_ms": breakdown, "update_phases_ms": upd, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
     }
     log("gpu legs done" + ("; cpu baseline" if world == 1 and not args.no_cpu_baseline else ""))
     if world == 1 and not args.no_cpu_baseline:

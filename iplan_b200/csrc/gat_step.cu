@@ -371,10 +371,15 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
             sc[u] = -INFINITY; hd[u] = 0.0f;
             if (s < NM1) {
                 const int j = s < i ? s : s + 1;
-                float acc = 0.0f;
-#pragma unroll 8
-                for (int k = 0; k < H; ++k) acc = fmaf(s_q[i * 33 + k], s_k[j * 33 + k], acc);
-                sc[u] = acc / 5.656854249492381f;            // np.sqrt(attention_dim), :126
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;     // four independent chains
+#pragma unroll
+                for (int k = 0; k < H; k += 4) {
+                    a0 = fmaf(s_q[i * 33 + k], s_k[j * 33 + k], a0);
+                    a1 = fmaf(s_q[i * 33 + k + 1], s_k[j * 33 + k + 1], a1);
+                    a2 = fmaf(s_q[i * 33 + k + 2], s_k[j * 33 + k + 2], a2);
+                    a3 = fmaf(s_q[i * 33 + k + 3], s_k[j * 33 + k + 3], a3);
+                }
+                sc[u] = ((a0 + a1) + (a2 + a3)) / 5.656854249492381f;   // np.sqrt(attention_dim), :126
                 float noise;
                 const int64_t edge = (((int64_t)ag * a.n_envs + b) * N + i) * NM1 + s;
                 if (a.gumbel) {

@@ -212,14 +212,25 @@ class IPPOLearner:
         c.grad_scale = self.grad_scale
         return c
 
+    def _mark(self, tag):
+        """Optional CUDA-event timeline of the update (bench.py sets ``self.events = []``)."""
+        ev = getattr(self, "events", None)
+        if ev is not None:
+            e = th.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((tag, e))
+
     def _forward(self, w, ctx, X, A, rows, Fp, F, actor, critic, train):
         lib, st = _lib.lib, _lib.stream()
+        self._mark("fc1_fwd")
         _lib.check(lib.iplan_learner_fc1_forward(
             _lib.ptr(actor), self.stacks["actor"].stride(), _lib.ptr(critic), self.stacks["critic"].stride(),
             _lib.ptr(w["Xh"]), _lib.ptr(w["Xl"]), w["Xh"].stride(0), Fp, F, rows, A, _lib.ptr(w["stat"]),
             _lib.ptr(w["Wh"]), _lib.ptr(w["Wl"]), _lib.ptr(w["ws"]), _lib.ptr(w["cc"]), _lib.ptr(w["Z1"]), st), "fc1_forward")
         import ctypes
+        self._mark("tail_train" if train else "tail_eval")
         _lib.check(lib.iplan_learner_tail(ctypes.byref(ctx), 1 if train else 0, st), "learner_tail")
+        self._mark("end")
 
     # ------------------------------------------------------------------------------
     def train(self, t_env):
@@ -279,13 +290,16 @@ class IPPOLearner:
         for _ in range(self.ppo_epoch):
             ga.zero_(); gc.zero_(); w["SM"].zero_()
             self._forward(w, ctx, X, A, rows, Fp, F, actor, critic, train=True)
+            self._mark("fc1_bwd")
             _lib.check(lib.iplan_learner_fc1_backward(
                 _lib.ptr(actor), self.stacks["actor"].stride(), _lib.ptr(critic), self.stacks["critic"].stride(),
                 _lib.ptr(ga), _lib.ptr(gc), _lib.ptr(w["Xh"]), _lib.ptr(w["Xl"]), w["Xh"].stride(0), Fp, F, rows, A,
                 _lib.ptr(w["Z1"]), _lib.ptr(w["Dh"]), _lib.ptr(w["Dl"]), _lib.ptr(w["gscale"]),
                 _lib.ptr(w["SM"]), _lib.ptr(w["G"]), st), "fc1_backward")
+            self._mark("allreduce")
             if dist:
                 self.bucket.allreduce([ga, gc])      # ONE NCCL all-reduce per PPO epoch
+            self._mark("adam")
             if self.keep_pre and _ == 0:
                 self.first_grads = {"actor": ga / self.grad_scale, "critic": gc / self.grad_scale}
             for kind, g, col in (("actor", ga, 4), ("critic", gc, 5)):
@@ -297,6 +311,7 @@ class IPPOLearner:
                     self.lrs[kind], 0.9, 0.999, self.optim_eps, self.steps[kind], self.max_grad_norm,
                     self.grad_scale, _lib.ptr(w["stats"]), col, st), "adam")
 
+        self._mark("end")
         # ---- statistics: one device->host read per train() ---------------------------------
         stats = w["stats"].clone()
         if dist:
