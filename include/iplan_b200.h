@@ -61,18 +61,22 @@ int64_t iplan_critic_layout(int feat_dim, int64_t* offsets);
  * replaces Prediction_policy.GAT_latent_update (nova/prediction_policy.py:92-118)
  * = per agent-net GAT_Net.forward (nova/GAT_Net.py:41-142): encode, hard attention
  * (bidirectional GRU over the N-1 neighbours, gumbel-softmax tau), soft attention,
- * GRUCell.  One CTA per (env, agent-net).
+ * GRUCell.  Two launches: the GRU chains (one CTA per (env, agent-net, direction)), then
+ * attention + GRUCell (one CTA per (env, agent-net)).
  *   hist      [a][b][n][obs_dim]      history_single at time t
  *   beh_prev  [a][b][n][latent_dim]   behaviour latent of time t-1
  *   h_prev    [a][b][n][32]           attention latent of time t-1
  *   out       [a][b][n][32]           attention latent of time t (may alias nothing)
  *   gumbel    NULL -> in-kernel Philox logistic noise keyed by (seed, counter);
  *             else [A][B][N][N-1][2] gumbel pairs (parity mode, reference draw order)
- *   dbg_hard  NULL or [A][B][N][N-1] hard-attention weights (debug/parity) */
+ *   dbg_hard  NULL or [A][B][N][N-1] hard-attention weights (debug/parity)
+ *   scratch   device buffer of >= iplan_gat_scratch_floats(...) floats handed from the first
+ *             launch to the second (per-edge hard-attention logit differences) */
+int64_t iplan_gat_scratch_floats(int n_envs, int n_agents, int n_slots);
 int iplan_gat_step(const float* gat_params, int64_t param_stride,
                    iplan_view hist, iplan_view beh_prev, iplan_view h_prev, iplan_view out,
                    const float* gumbel, uint64_t seed, uint64_t counter,
-                   float tau, float* dbg_hard,
+                   float tau, float* dbg_hard, float* scratch, int64_t scratch_floats,
                    int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
                    void* stream);
 

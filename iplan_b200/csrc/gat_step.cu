@@ -2,7 +2,7 @@
 //
 // Replaces Prediction_policy.GAT_latent_update (reference nova/prediction_policy.py:92-118)
 // and, inside it, GAT_Net.forward (nova/GAT_Net.py:41-142).  One CTA owns one
-// (env b, agent-net a) pair and keeps every intermediate in shared memory:
+// (env b, agent-net a) pair per kernel and keeps every intermediate in shared memory:
 //
 //   x[n]      = [history_t[n] | behaviour_{t-1}[n]]                       (:102-105)
 //   enc[n]    = ReLU(W_e x[n] + b_e)                                       (:50)
@@ -22,8 +22,16 @@
 // dropped lo*lo term is < 2^-22 relative).  The accumulator fragment of step s is, element
 // for element, the A fragment of step s+1, so the hidden state never leaves registers.
 //
+// Two kernels per step, both on the caller's stream:
+//   gat_recur_kernel   grid (B, A, 2 directions), 4 warps: encode, P/Q projections of its
+//                      direction, the N chains of that direction; writes the per-edge logit
+//                      difference dl[dir][s][i] to a scratch buffer (L2 resident, 27 KB per (b,a)).
+//                      ~66 KB smem, <= 168 registers -> 3 CTAs (12 warps) per SM, and CTAs in
+//                      different phases overlap on an SM.
+//   gat_attend_kernel  grid (B, A), 8 warps: encode, q/k/v, hard x soft attention, GRUCell.
+//
 // HBM traffic per (b,a): read N*(o+L+32) floats, write N*32 floats; weights (28.8k floats)
-// come from L2.
+// and the dl scratch come from L2.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -32,8 +40,11 @@ namespace iplan {
 
 constexpr int H = IPLAN_HID;   // 32 == GAT_hidden_dim == attention_dim
 constexpr int G3 = 3 * H;      // gate rows r|z|n
-constexpr int GAT_THREADS = 256;
+constexpr int GAT_THREADS = 256;           // attend kernel
 constexpr int GAT_WARPS = GAT_THREADS / 32;
+constexpr int REC_THREADS = 128;           // recurrence kernel: 4 warps = 4 m-tiles of 16 egos
+constexpr int REC_WARPS = REC_THREADS / 32;
+constexpr int DLP = IPLAN_MAX_SLOTS;       // row pitch of the dl scratch: dl[dir][s][DLP]
 constexpr int IN_MAX = 16;     // obs_dim + latent_dim upper bound
 constexpr int NT_G = G3 / 8;   // 12 n-tiles of 8 gate columns
 constexpr int KB_H = H / 16;   // 2 k-blocks of 16 hidden units
@@ -41,15 +52,17 @@ constexpr int KB_H = H / 16;   // 2 k-blocks of 16 hidden units
 struct GatArgs {
     const float* params; int64_t param_stride;
     iplan_view hist, beh, hprev, out;
-    const float* gumbel; float* dbg_hard;
+    const float* gumbel; float* dbg_hard; float* dl;
     uint64_t seed, counter;
     float inv_tau;
     int n_envs, n_slots, obs_dim, latent_dim;
 };
 
-__host__ __device__ inline size_t gat_smem_floats(int N) {
-    return (size_t)N * IN_MAX + (size_t)N * H + 4 * (size_t)N * G3 + 2 * (size_t)N * (N - 1) +
-           2 * NT_G * KB_H * 32 * 2 + GAT_WARPS * 64;
+__host__ __device__ inline size_t rec_smem_floats(int N) {
+    return (size_t)N * IN_MAX + (size_t)N * H + 2 * (size_t)N * G3 + 4 * NT_G * KB_H * 32 + 64;
+}
+__host__ __device__ inline size_t att_smem_floats(int N) {
+    return (size_t)N * IN_MAX + (size_t)N * H + 354 * (size_t)N + (size_t)N * (N - 1) + GAT_WARPS * 64;
 }
 
 // fast, fp32-accurate-enough gates (abs error ~1e-7): ex2.approx + rcp.approx
@@ -61,6 +74,15 @@ constexpr float K_RZ = -1.4426950408889634f;      // -log2(e)
 constexpr float K_N = 2.8853900817779268f;        //  2 log2(e)
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// volatile: the W_hh fragments are loop-invariant, and hoisting them out of the step loop would cost
+// 96 registers per thread
+__device__ __forceinline__ uint4 lds128(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
 
 // (x, y) -> packed f16 hi pair and f16 lo (residual) pair
 __device__ __forceinline__ void split_f16(float x, float y, uint32_t& hi, uint32_t& lo) {
@@ -83,6 +105,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 // All warps of the CTA cooperate: one task = one 16-node x 8-column tile = 6 MMAs (f16 hi/lo
 // split, see header).  W is read as B fragments straight from global memory: a quad reads 32
 // contiguous bytes of one weight row, so every sector fetched is fully used.
+template <int NW>
 __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, const float* __restrict__ Wg, int ldw,
                                             const float* __restrict__ bias, int cols, float* out, int ldout, bool relu,
                                             int warp, int lane) {
@@ -91,11 +114,11 @@ __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, co
     const int mh = (mtiles + 1) >> 1;                 // a task = one n-tile x one half of the m-tiles
     const int ntask = ntiles * 2;
     constexpr int DT = 3;                             // tasks whose weight fragments are fetched together
-    for (int base = warp; base < ntask; base += GAT_WARPS * DT) {
+    for (int base = warp; base < ntask; base += NW * DT) {
         float2 wv[DT][4];
 #pragma unroll
         for (int i = 0; i < DT; ++i) {                // issue every global load first: one L2 round trip
-            const int task = base + i * GAT_WARPS;
+            const int task = base + i * NW;
             if (task < ntask) {
                 const float* wr = Wg + (size_t)(8 * (task >> 1) + gq) * ldw + 2 * tq;
                 wv[i][0] = *reinterpret_cast<const float2*>(wr);
@@ -106,7 +129,7 @@ __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, co
         }
 #pragma unroll
         for (int i = 0; i < DT; ++i) {
-            const int task = base + i * GAT_WARPS;
+            const int task = base + i * NW;
             if (task >= ntask) break;
             const int nt = task >> 1, half = task & 1;
             const int c0 = 8 * nt + 2 * tq;
@@ -149,7 +172,188 @@ __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, co
     }
 }
 
-__global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
+// phases 0 + 1, shared by both kernels: gather x = [history | behaviour latent], enc = ReLU(W_e x + b_e)
+template <int NT>
+__device__ __forceinline__ void gat_encode(const GatArgs& a, const float* __restrict__ W, const GatLayout& L,
+                                           int b, int ag, float* s_x, float* s_enc) {
+    const int N = a.n_slots, in_dim = a.obs_dim + a.latent_dim, tid = threadIdx.x;
+    const float* hist = a.hist.ptr + ag * a.hist.stride_agent + b * a.hist.stride_env;
+    const float* beh = a.beh.ptr + ag * a.beh.stride_agent + b * a.beh.stride_env;
+    for (int idx = tid; idx < N * in_dim; idx += NT) {
+        const int n = idx / in_dim, c = idx - n * in_dim;
+        s_x[n * IN_MAX + c] = (c < a.obs_dim) ? hist[n * a.hist.stride_slot + c]
+                                              : beh[n * a.beh.stride_slot + (c - a.obs_dim)];
+    }
+    __syncthreads();
+    for (int idx = tid; idx < N * H; idx += NT) {
+        const int n = idx >> 5, c = idx & 31;
+        float acc = W[L.enc_b + c];
+        const float* w = W + L.enc_w + c * in_dim;
+        for (int k = 0; k < in_dim; ++k) acc = fmaf(w[k], s_x[n * IN_MAX + k], acc);
+        s_enc[idx] = fmaxf(acc, 0.0f);
+    }
+    __syncthreads();
+}
+
+// ---- kernel 1 of 2: the N GRU chains of one direction for one (env, agent-net) -------------
+__global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.x, ag = blockIdx.y, dir = blockIdx.z;
+    const int N = a.n_slots, NM1 = N - 1;
+    const int in_dim = a.obs_dim + a.latent_dim;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* __restrict__ W = a.params + (int64_t)ag * a.param_stride;
+    const GatLayout L = gat_layout(in_dim);
+
+    float* s_x = smem;                                  // [N][IN_MAX]
+    float* s_enc = s_x + N * IN_MAX;                    // [N][H]
+    float* s_P = s_enc + N * H;                         // [N][96]  ego part + b_ih (+ b_hh for r|z), gate-scaled
+    float* s_Q = s_P + N * G3;                          // [N][96]  neighbour part, gate-scaled
+    uint4* s_w4 = reinterpret_cast<uint4*>(s_Q + N * G3);   // [12][2][32] W_hh B fragments {hi0, hi1, lo0, lo1}
+    float4* s_bw = reinterpret_cast<float4*>(s_w4 + NT_G * KB_H * 32);   // [4 t4][4 tq] {b_hn pair, logit-diff weight pair}
+
+    gat_encode<REC_THREADS>(a, W, L, b, ag, s_x, s_enc);
+
+    // ---- phase 2: factored input projections P (ego, + b_ih) and Q (neighbour) ------
+    const float* wih = W + (dir ? L.wih_r : L.wih_f);
+    const float* bhh = W + (dir ? L.bhh_r : L.bhh_f);
+    dense32_mma<REC_WARPS>(s_enc, H, N, wih, 2 * H, W + (dir ? L.bih_r : L.bih_f), G3, s_P, G3, false, warp, lane);
+    dense32_mma<REC_WARPS>(s_enc, H, N, wih + H, 2 * H, nullptr, G3, s_Q, G3, false, warp, lane);
+    // W_hh B fragments (mma.m16n8k16 "col" operand: b0 = (k=2t,2t+1 ; n=g), b1 = (k=2t+8,2t+9 ; n=g)),
+    // B[k][n] = W_hh[gate n][hidden k], gate-activation scale folded in, f16 hi and lo parts.
+    {
+        const float* whh = W + (dir ? L.whh_r : L.whh_f);
+        for (int idx = tid; idx < NT_G * KB_H * 32; idx += REC_THREADS) {
+            const int ln = idx & 31, kb = (idx >> 5) & 1, nt = idx >> 6;
+            const float* wr = whh + (8 * nt + (ln >> 2)) * H + 16 * kb + 2 * (ln & 3);
+            const float2 w0 = *reinterpret_cast<const float2*>(wr);
+            const float2 w1 = *reinterpret_cast<const float2*>(wr + 8);
+            const float ks = nt < 8 ? K_RZ : K_N;
+            uint4 f;
+            split_f16(ks * w0.x, ks * w0.y, f.x, f.z);
+            split_f16(ks * w1.x, ks * w1.y, f.y, f.w);
+            s_w4[idx] = f;
+        }
+        if (tid < 16) {
+            const int c = 8 * (tid >> 2) + 2 * (tid & 3);
+            s_bw[tid] = make_float4(K_N * bhh[2 * H + c], K_N * bhh[2 * H + c + 1],
+                                    W[L.he_w + 2 * H + dir * H + c] - W[L.he_w + dir * H + c],
+                                    W[L.he_w + 2 * H + dir * H + c + 1] - W[L.he_w + dir * H + c + 1]);
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < N * G3; idx += REC_THREADS) {          // fold gate scale (and b_hh of r|z) into P, Q
+        const int col = idx % G3;
+        if (col < 2 * H) { s_P[idx] = K_RZ * (s_P[idx] + bhh[col]); s_Q[idx] *= K_RZ; }
+        else { s_P[idx] *= K_N; s_Q[idx] *= K_N; }
+    }
+    __syncthreads();
+
+    // ---- phase 3: the chains on the tensor cores; warp = m-tile of 16 egos -----------
+    const int gq = lane >> 2, tq = lane & 3, mt = warp;
+    if (mt * 16 >= N) return;                                           // warp-uniform; no barrier follows
+    const int row0 = mt * 16 + gq, row1 = row0 + 8;                     // ego indices of this thread's two rows
+    const bool ok0 = row0 < N, ok1 = row1 < N;
+    const int i0 = ok0 ? row0 : N - 1, i1 = ok1 ? row1 : N - 1;
+    float* dl = a.dl + ((((int64_t)ag * a.n_envs + b) * 2 + dir) * NM1) * DLP;
+    const uint4* w4 = s_w4 + lane;
+    // per-chain constants in accumulator-fragment layout: element e of tile nt is
+    // (row e<2 ? row0 : row1, col 8*nt + 2*tq + (e&1))
+    float cst[8][4], pn[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const float2 p0 = *reinterpret_cast<const float2*>(s_P + i0 * G3 + 8 * nt + 2 * tq);
+        const float2 p1 = *reinterpret_cast<const float2*>(s_P + i1 * G3 + 8 * nt + 2 * tq);
+        cst[nt][0] = p0.x; cst[nt][1] = p0.y; cst[nt][2] = p1.x; cst[nt][3] = p1.y;     // r | z : P + b_hh
+    }
+#pragma unroll
+    for (int t4 = 0; t4 < 4; ++t4) {
+        const float2 p0 = *reinterpret_cast<const float2*>(s_P + i0 * G3 + 2 * H + 8 * t4 + 2 * tq);
+        const float2 p1 = *reinterpret_cast<const float2*>(s_P + i1 * G3 + 2 * H + 8 * t4 + 2 * tq);
+        pn[t4][0] = p0.x; pn[t4][1] = p0.y; pn[t4][2] = p1.x; pn[t4][3] = p1.y;
+    }
+    float h[4][4];
+#pragma unroll
+    for (int t4 = 0; t4 < 4; ++t4)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[t4][e] = 0.0f;
+
+    for (int step = 0; step < NM1; ++step) {
+        const int s = dir ? NM1 - 1 - step : step;
+        // A fragments from the hidden state (accumulator layout == A layout, see header)
+        uint32_t ahi[KB_H][4], alo[KB_H][4];
+#pragma unroll
+        for (int kb = 0; kb < KB_H; ++kb) {
+            split_f16(h[2 * kb][0], h[2 * kb][1], ahi[kb][0], alo[kb][0]);          // row g,   k low
+            split_f16(h[2 * kb][2], h[2 * kb][3], ahi[kb][1], alo[kb][1]);          // row g+8, k low
+            split_f16(h[2 * kb + 1][0], h[2 * kb + 1][1], ahi[kb][2], alo[kb][2]);  // row g,   k high
+            split_f16(h[2 * kb + 1][2], h[2 * kb + 1][3], ahi[kb][3], alo[kb][3]);  // row g+8, k high
+        }
+        // neighbour of ego i at position s is j = s < i ? s : s + 1
+        const float* q0 = s_Q + (s < i0 ? s : s + 1) * G3 + 2 * tq;
+        const float* q1 = s_Q + (s < i1 ? s : s + 1) * G3 + 2 * tq;
+        float pl0 = 0.0f, pl1 = 0.0f;
+        // Hidden units in groups of 8 (t4): the r|z|n tiles of a group take their six MMA
+        // passes (three independent chains), then the group's gate math runs while the
+        // next group's MMAs are in flight, so tensor, MUFU and FP32 pipes overlap within one warp.
+#pragma unroll
+        for (int t4 = 0; t4 < 4; ++t4) {
+            float acc[3][4];
+            uint4 w[3][KB_H];
+            const float4 bw = s_bw[4 * t4 + tq];
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi)
+#pragma unroll
+                for (int kb = 0; kb < KB_H; ++kb) w[gi][kb] = lds128(w4 + ((4 * gi + t4) * KB_H + kb) * 32);
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) {
+                float c0[4];
+                if (gi < 2) { const int nt = 4 * gi + t4; c0[0] = cst[nt][0]; c0[1] = cst[nt][1]; c0[2] = cst[nt][2]; c0[3] = cst[nt][3]; }
+                else { c0[0] = bw.x; c0[1] = bw.y; c0[2] = bw.x; c0[3] = bw.y; }
+                mma16816(acc[gi], ahi[0], w[gi][0].x, w[gi][0].y, c0);
+            }
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) mma16816(acc[gi], ahi[1], w[gi][1].x, w[gi][1].y, acc[gi]);
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) mma16816(acc[gi], alo[0], w[gi][0].x, w[gi][0].y, acc[gi]);
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) mma16816(acc[gi], alo[1], w[gi][1].x, w[gi][1].y, acc[gi]);
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) mma16816(acc[gi], ahi[0], w[gi][0].z, w[gi][0].w, acc[gi]);
+#pragma unroll
+            for (int gi = 0; gi < 3; ++gi) mma16816(acc[gi], ahi[1], w[gi][1].z, w[gi][1].w, acc[gi]);
+            const float2 qr0 = *reinterpret_cast<const float2*>(q0 + 8 * t4);
+            const float2 qz0 = *reinterpret_cast<const float2*>(q0 + H + 8 * t4);
+            const float2 qn0 = *reinterpret_cast<const float2*>(q0 + 2 * H + 8 * t4);
+            const float2 qr1 = *reinterpret_cast<const float2*>(q1 + 8 * t4);
+            const float2 qz1 = *reinterpret_cast<const float2*>(q1 + H + 8 * t4);
+            const float2 qn1 = *reinterpret_cast<const float2*>(q1 + 2 * H + 8 * t4);
+            const float qr[4] = {qr0.x, qr0.y, qr1.x, qr1.y};
+            const float qz[4] = {qz0.x, qz0.y, qz1.x, qz1.y};
+            const float qn[4] = {qn0.x, qn0.y, qn1.x, qn1.y};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float r = rcp_approx(1.0f + ex2_approx(acc[0][e] + qr[e]));
+                const float z = rcp_approx(1.0f + ex2_approx(acc[1][e] + qz[e]));
+                const float en = ex2_approx(fmaf(r, acc[2][e], pn[t4][e] + qn[e]));
+                const float n = fmaf(-2.0f, rcp_approx(1.0f + en), 1.0f);
+                h[t4][e] = fmaf(z, h[t4][e] - n, n);                // (1 - z) n + z h
+            }
+            pl0 = fmaf(bw.z, h[t4][0], fmaf(bw.w, h[t4][1], pl0));
+            pl1 = fmaf(bw.z, h[t4][2], fmaf(bw.w, h[t4][3], pl1));
+        }
+        // the 32 hidden units of a row live in the 4 lanes of a quad
+        pl0 += __shfl_xor_sync(0xffffffffu, pl0, 1); pl0 += __shfl_xor_sync(0xffffffffu, pl0, 2);
+        pl1 += __shfl_xor_sync(0xffffffffu, pl1, 1); pl1 += __shfl_xor_sync(0xffffffffu, pl1, 2);
+        if (tq == 0) {                                      // dl[s][i]: a warp's 16 egos are one 64-byte segment
+            if (ok0) dl[s * DLP + i0] = pl0;
+            if (ok1) dl[s * DLP + i1] = pl1;
+        }
+    }
+}
+
+// ---- kernel 2 of 2: q/k/v, hard x soft attention, GRUCell ------------------------------------
+__global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int b = blockIdx.x, ag = blockIdx.y;
     const int N = a.n_slots, NM1 = N - 1;
@@ -160,201 +364,38 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
 
     float* s_x = smem;                                  // [N][IN_MAX]
     float* s_enc = s_x + N * IN_MAX;                    // [N][H]
-    float* s_P = s_enc + N * H;                         // [2][N][96]  ego part + b_ih
-    float* s_Q = s_P + 2 * N * G3;                      // [2][N][96]  neighbour part
-    float* s_dl = s_Q + 2 * N * G3;                     // [2][N][N-1] per-direction logit diff
-    uint2* s_wlo = reinterpret_cast<uint2*>(s_dl + 2 * N * NM1);   // [2][12][2][32] f16 lo parts of W_hh (B fragments)
-    float* s_w = reinterpret_cast<float*>(s_wlo + 2 * NT_G * KB_H * 32);   // [warps][64] attention weights
-    // after the recurrence the P/Q region (4*N*96 floats) is reused:
-    float* s_q = s_P;                                   // [N][33]
+    float* s_q = s_enc + N * H;                         // [N][33]
     float* s_k = s_q + N * 33;                          // [N][33]
     float* s_v = s_k + N * 33;                          // [N][H]
     float* s_xa = s_v + N * H;                          // [N][H] aggregated messages
     float* s_hp = s_xa + N * H;                         // [N][H] h_prev
     float* s_gi = s_hp + N * H;                         // [N][96] GRUCell input pre-activations
-    float* s_gh = s_gi + N * G3;                        // [N][96] GRUCell hidden pre-activations (354 N <= 384 N)
+    float* s_gh = s_gi + N * G3;                        // [N][96] GRUCell hidden pre-activations
+    float* s_dl = s_gh + N * G3;                        // [N][N-1] logit difference, both directions summed
+    float* s_w = s_dl + N * NM1;                        // [warps][64] attention weights
 
-    const float* hist = a.hist.ptr + ag * a.hist.stride_agent + b * a.hist.stride_env;
-    const float* beh = a.beh.ptr + ag * a.beh.stride_agent + b * a.beh.stride_env;
     const float* hprev = a.hprev.ptr + ag * a.hprev.stride_agent + b * a.hprev.stride_env;
     float* outp = a.out.ptr + ag * a.out.stride_agent + b * a.out.stride_env;
 
-    // ---- phase 0: gather x = [history | behaviour latent] ---------------------------
-    for (int idx = tid; idx < N * in_dim; idx += GAT_THREADS) {
-        const int n = idx / in_dim, c = idx - n * in_dim;
-        float v = (c < a.obs_dim) ? hist[n * a.hist.stride_slot + c]
-                                  : beh[n * a.beh.stride_slot + (c - a.obs_dim)];
-        s_x[n * IN_MAX + c] = v;
-    }
-    __syncthreads();
+    gat_encode<GAT_THREADS>(a, W, L, b, ag, s_x, s_enc);
 
-    // ---- phase 1: enc = ReLU(W_e x + b_e) ------------------------------------------
-    for (int idx = tid; idx < N * H; idx += GAT_THREADS) {
-        const int n = idx >> 5, c = idx & 31;
-        float acc = W[L.enc_b + c];
-        const float* w = W + L.enc_w + c * in_dim;
-        for (int k = 0; k < in_dim; ++k) acc = fmaf(w[k], s_x[n * IN_MAX + k], acc);
-        s_enc[idx] = fmaxf(acc, 0.0f);
-    }
-    __syncthreads();
-
-    // ---- phase 2: factored input projections P (ego, + b_ih) and Q (neighbour) ------
-#pragma unroll 1
-    for (int d = 0; d < 2; ++d) {
-        const float* wih = W + (d ? L.wih_r : L.wih_f);
-        dense32_mma(s_enc, H, N, wih, 2 * H, W + (d ? L.bih_r : L.bih_f), G3, s_P + (size_t)d * N * G3, G3, false, warp, lane);
-        dense32_mma(s_enc, H, N, wih + H, 2 * H, nullptr, G3, s_Q + (size_t)d * N * G3, G3, false, warp, lane);
-    }
-    // W_hh B fragments (mma.m16n8k16 "col" operand: b0 = (k=2t,2t+1 ; n=g), b1 = (k=2t+8,2t+9 ; n=g)),
-    // B[k][n] = W_hh[gate n][hidden k]; f16 hi parts stay in registers, lo parts go to shared memory.
-    const int gq = lane >> 2, tq = lane & 3;
-    const int dir = warp >> 2, mt = warp & 3;            // warps 0-3 forward, 4-7 reverse; m-tile of 16 egos
-    uint32_t whi[NT_G][KB_H][2];
+    // ---- phase 4: q, k, v; stage h_prev and the recurrence kernel's dl[dir][s][i] ------
+    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.q_w, H, nullptr, H, s_q, 33, false, warp, lane);
+    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.k_w, H, nullptr, H, s_k, 33, false, warp, lane);
+    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.v_w, H, W + L.v_b, H, s_v, H, true, warp, lane);
+    for (int idx = tid; idx < N * H; idx += GAT_THREADS)
+        s_hp[idx] = hprev[(idx >> 5) * a.hprev.stride_slot + (idx & 31)];
     {
-        const float* whh = W + (dir ? L.whh_r : L.whh_f);
-#pragma unroll
-        for (int nt = 0; nt < NT_G; ++nt)
-#pragma unroll
-            for (int kb = 0; kb < KB_H; ++kb) {
-                const float* wr = whh + (8 * nt + gq) * H + 16 * kb + 2 * tq;
-                const float2 w0 = *reinterpret_cast<const float2*>(wr);
-                const float2 w1 = *reinterpret_cast<const float2*>(wr + 8);
-                const float ks = nt < 8 ? K_RZ : K_N;               // gate-activation scale folded into W_hh
-                uint32_t lo0, lo1;
-                split_f16(ks * w0.x, ks * w0.y, whi[nt][kb][0], lo0);
-                split_f16(ks * w1.x, ks * w1.y, whi[nt][kb][1], lo1);
-                if (mt == 0) s_wlo[((dir * NT_G + nt) * KB_H + kb) * 32 + lane] = make_uint2(lo0, lo1);
-            }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < 2 * N * G3; idx += GAT_THREADS)       // ... and into the neighbour projection Q
-        s_Q[idx] *= (idx % G3) < 2 * H ? K_RZ : K_N;
-    __syncthreads();
-
-    // ---- phase 3: the 2N GRU chains on the tensor cores ------------------------------
-    {
-        const int row0 = mt * 16 + gq, row1 = row0 + 8;                 // ego indices of this thread's two rows
-        const bool ok0 = row0 < N, ok1 = row1 < N;
-        const int i0 = ok0 ? row0 : N - 1, i1 = ok1 ? row1 : N - 1;
-        if (mt * 16 < N) {                                              // warp-uniform: tile has live egos
-            const float* bhh = W + (dir ? L.bhh_r : L.bhh_f);
-            const float* Pd = s_P + (size_t)dir * N * G3;
-            const float* Qd = s_Q + (size_t)dir * N * G3;
-            float* dl = s_dl + (size_t)dir * N * NM1;
-            const uint2* wlo = s_wlo + (size_t)dir * NT_G * KB_H * 32 + lane;
-            // per-chain constants in accumulator-fragment layout: element e of tile nt is
-            // (row e<2 ? row0 : row1, col 8*nt + 2*tq + (e&1))
-            float cst[8][4], pn[4][4], bn[4][2], wd[4][2];
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int col = 8 * nt + 2 * tq + (e & 1);
-                    cst[nt][e] = K_RZ * (Pd[(e < 2 ? i0 : i1) * G3 + col] + bhh[col]);  // r | z : P + b_hh
-                }
-#pragma unroll
-            for (int t4 = 0; t4 < 4; ++t4) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) pn[t4][e] = K_N * Pd[(e < 2 ? i0 : i1) * G3 + 2 * H + 8 * t4 + 2 * tq + (e & 1)];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int c = 8 * t4 + 2 * tq + u;
-                    bn[t4][u] = K_N * bhh[2 * H + c];
-                    wd[t4][u] = W[L.he_w + 2 * H + dir * H + c] - W[L.he_w + dir * H + c];
-                }
-            }
-            float h[4][4];
-#pragma unroll
-            for (int t4 = 0; t4 < 4; ++t4)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h[t4][e] = 0.0f;
-
-            for (int step = 0; step < NM1; ++step) {
-                const int s = dir ? NM1 - 1 - step : step;
-                // A fragments from the hidden state (accumulator layout == A layout, see header)
-                uint32_t ahi[KB_H][4], alo[KB_H][4];
-#pragma unroll
-                for (int kb = 0; kb < KB_H; ++kb) {
-                    split_f16(h[2 * kb][0], h[2 * kb][1], ahi[kb][0], alo[kb][0]);          // row g,   k low
-                    split_f16(h[2 * kb][2], h[2 * kb][3], ahi[kb][1], alo[kb][1]);          // row g+8, k low
-                    split_f16(h[2 * kb + 1][0], h[2 * kb + 1][1], ahi[kb][2], alo[kb][2]);  // row g,   k high
-                    split_f16(h[2 * kb + 1][2], h[2 * kb + 1][3], ahi[kb][3], alo[kb][3]);  // row g+8, k high
-                }
-                // gates; neighbour of ego i at position s is j = s < i ? s : s + 1
-                const float* q0 = Qd + (s < i0 ? s : s + 1) * G3 + 2 * tq;
-                const float* q1 = Qd + (s < i1 ? s : s + 1) * G3 + 2 * tq;
-                float pl0 = 0.0f, pl1 = 0.0f;
-                // Hidden units in groups of 8 (t4): the r|z|n tiles of a group take their six MMA
-                // passes (three independent chains), then the group's gate math runs while the
-                // next group's MMAs are in flight, so tensor, MUFU and FP32 pipes overlap within one warp.
-#pragma unroll
-                for (int t4 = 0; t4 < 4; ++t4) {
-                    float acc[3][4];
-#pragma unroll
-                    for (int gi = 0; gi < 3; ++gi) {
-                        const int nt = 4 * gi + t4;
-                        float c0[4];
-                        if (gi < 2) { c0[0] = cst[nt][0]; c0[1] = cst[nt][1]; c0[2] = cst[nt][2]; c0[3] = cst[nt][3]; }
-                        else { c0[0] = bn[t4][0]; c0[1] = bn[t4][1]; c0[2] = bn[t4][0]; c0[3] = bn[t4][1]; }
-                        mma16816(acc[gi], ahi[0], whi[nt][0][0], whi[nt][0][1], c0);
-                    }
-#pragma unroll
-                    for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; mma16816(acc[gi], ahi[1], whi[nt][1][0], whi[nt][1][1], acc[gi]); }
-#pragma unroll
-                    for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; mma16816(acc[gi], alo[0], whi[nt][0][0], whi[nt][0][1], acc[gi]); }
-#pragma unroll
-                    for (int gi = 0; gi < 3; ++gi) { const int nt = 4 * gi + t4; mma16816(acc[gi], alo[1], whi[nt][1][0], whi[nt][1][1], acc[gi]); }
-#pragma unroll
-                    for (int gi = 0; gi < 3; ++gi) {
-                        const uint2 l0 = wlo[((4 * gi + t4) * KB_H + 0) * 32];
-                        mma16816(acc[gi], ahi[0], l0.x, l0.y, acc[gi]);
-                    }
-#pragma unroll
-                    for (int gi = 0; gi < 3; ++gi) {
-                        const uint2 l1 = wlo[((4 * gi + t4) * KB_H + 1) * 32];
-                        mma16816(acc[gi], ahi[1], l1.x, l1.y, acc[gi]);
-                    }
-                    const float2 qr0 = *reinterpret_cast<const float2*>(q0 + 8 * t4);
-                    const float2 qz0 = *reinterpret_cast<const float2*>(q0 + H + 8 * t4);
-                    const float2 qn0 = *reinterpret_cast<const float2*>(q0 + 2 * H + 8 * t4);
-                    const float2 qr1 = *reinterpret_cast<const float2*>(q1 + 8 * t4);
-                    const float2 qz1 = *reinterpret_cast<const float2*>(q1 + H + 8 * t4);
-                    const float2 qn1 = *reinterpret_cast<const float2*>(q1 + 2 * H + 8 * t4);
-                    const float qr[4] = {qr0.x, qr0.y, qr1.x, qr1.y};
-                    const float qz[4] = {qz0.x, qz0.y, qz1.x, qz1.y};
-                    const float qn[4] = {qn0.x, qn0.y, qn1.x, qn1.y};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float r = rcp_approx(1.0f + ex2_approx(acc[0][e] + qr[e]));
-                        const float z = rcp_approx(1.0f + ex2_approx(acc[1][e] + qz[e]));
-                        const float en = ex2_approx(fmaf(r, acc[2][e], pn[t4][e] + qn[e]));
-                        const float n = fmaf(-2.0f, rcp_approx(1.0f + en), 1.0f);
-                        h[t4][e] = fmaf(z, h[t4][e] - n, n);                // (1 - z) n + z h
-                    }
-                    pl0 = fmaf(wd[t4][0], h[t4][0], fmaf(wd[t4][1], h[t4][1], pl0));
-                    pl1 = fmaf(wd[t4][0], h[t4][2], fmaf(wd[t4][1], h[t4][3], pl1));
-                }
-                // the 32 hidden units of a row live in the 4 lanes of a quad
-                pl0 += __shfl_xor_sync(0xffffffffu, pl0, 1); pl0 += __shfl_xor_sync(0xffffffffu, pl0, 2);
-                pl1 += __shfl_xor_sync(0xffffffffu, pl1, 1); pl1 += __shfl_xor_sync(0xffffffffu, pl1, 2);
-                if (tq == 0) {
-                    if (ok0) dl[i0 * NM1 + s] = pl0;
-                    if (ok1) dl[i1 * NM1 + s] = pl1;
-                }
-            }
+        const float* dlf = a.dl + (((int64_t)ag * a.n_envs + b) * 2) * NM1 * DLP;
+        const float* dlr = dlf + (int64_t)NM1 * DLP;
+        for (int idx = tid; idx < NM1 * DLP; idx += GAT_THREADS) {
+            const int s = idx / DLP, i = idx - s * DLP;
+            if (i < N) s_dl[i * NM1 + s] = dlf[idx] + dlr[idx];
         }
     }
     __syncthreads();
 
-    // ---- phase 4: q, k, v and the transposed GRUCell weights -------------------------
-    dense32_mma(s_enc, H, N, W + L.q_w, H, nullptr, H, s_q, 33, false, warp, lane);
-    dense32_mma(s_enc, H, N, W + L.k_w, H, nullptr, H, s_k, 33, false, warp, lane);
-    dense32_mma(s_enc, H, N, W + L.v_w, H, W + L.v_b, H, s_v, H, true, warp, lane);
-    for (int idx = tid; idx < N * H; idx += GAT_THREADS)          // stage h_prev for the GRUCell product
-        s_hp[idx] = hprev[(idx >> 5) * a.hprev.stride_slot + (idx & 31)];
-    __syncthreads();
-
-    // ---- phase 5: soft x hard attention + GRUCell, one warp per ego ------------------
+    // ---- phase 5: soft x hard attention, one warp per ego -----------------------------
     const float db = W[L.he_b + 1] - W[L.he_b + 0];
     float* wbuf = s_w + warp * 64;
     for (int i = warp; i < N; i += GAT_WARPS) {
@@ -389,7 +430,7 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
                     const float uu = u01(u == 0 ? rnd.x : rnd.y);
                     noise = __logf(uu) - __logf(1.0f - uu);  // Gumbel - Gumbel ~ Logistic(0,1)
                 }
-                const float dlog = s_dl[i * NM1 + s] + s_dl[(size_t)N * NM1 + i * NM1 + s] + db;
+                const float dlog = s_dl[i * NM1 + s] + db;
                 hd[u] = sigmoidf_acc((dlog + noise) * a.inv_tau);
                 if (a.dbg_hard) a.dbg_hard[edge] = hd[u];
             }
@@ -417,8 +458,8 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
     __syncthreads();
 
     // ---- phase 6: GRUCell(x_i, h_prev_i) (:140): two N x 96 x 32 products + gates -----
-    dense32_mma(s_xa, H, N, W + L.c_wih, H, W + L.c_bih, G3, s_gi, G3, false, warp, lane);
-    dense32_mma(s_hp, H, N, W + L.c_whh, H, W + L.c_bhh, G3, s_gh, G3, false, warp, lane);
+    dense32_mma<GAT_WARPS>(s_xa, H, N, W + L.c_wih, H, W + L.c_bih, G3, s_gi, G3, false, warp, lane);
+    dense32_mma<GAT_WARPS>(s_hp, H, N, W + L.c_whh, H, W + L.c_bhh, G3, s_gh, G3, false, warp, lane);
     __syncthreads();
     for (int idx = tid; idx < N * H; idx += GAT_THREADS) {
         const int n = idx >> 5, c = idx & 31;
@@ -433,10 +474,14 @@ __global__ void __launch_bounds__(GAT_THREADS, 1) gat_step_kernel(GatArgs a) {
 
 }  // namespace iplan
 
+extern "C" int64_t iplan_gat_scratch_floats(int n_envs, int n_agents, int n_slots) {
+    return (int64_t)n_envs * n_agents * 2 * (n_slots - 1) * iplan::DLP;
+}
+
 extern "C" int iplan_gat_step(const float* gat_params, int64_t param_stride,
                               iplan_view hist, iplan_view beh_prev, iplan_view h_prev, iplan_view out,
                               const float* gumbel, uint64_t seed, uint64_t counter,
-                              float tau, float* dbg_hard,
+                              float tau, float* dbg_hard, float* scratch, int64_t scratch_floats,
                               int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
                               void* stream) {
     using namespace iplan;
@@ -445,21 +490,32 @@ extern "C" int iplan_gat_step(const float* gat_params, int64_t param_stride,
     IPLAN_REQUIRE(n_envs > 0 && n_agents > 0 && n_agents <= 65535, "gat_step: bad n_envs/n_agents");
     IPLAN_REQUIRE(gat_params && hist.ptr && beh_prev.ptr && h_prev.ptr && out.ptr, "gat_step: null pointer");
     IPLAN_REQUIRE(tau > 0.f, "gat_step: tau must be > 0");
+    IPLAN_REQUIRE(scratch && scratch_floats >= iplan_gat_scratch_floats(n_envs, n_agents, n_slots),
+                  "gat_step: scratch too small (%lld floats, need iplan_gat_scratch_floats)", (long long)scratch_floats);
     GatArgs a;
     a.params = gat_params; a.param_stride = param_stride;
     a.hist = hist; a.beh = beh_prev; a.hprev = h_prev; a.out = out;
-    a.gumbel = gumbel; a.dbg_hard = dbg_hard; a.seed = seed; a.counter = counter;
+    a.gumbel = gumbel; a.dbg_hard = dbg_hard; a.dl = scratch; a.seed = seed; a.counter = counter;
     a.inv_tau = 1.0f / tau;
     a.n_envs = n_envs; a.n_slots = n_slots; a.obs_dim = obs_dim; a.latent_dim = latent_dim;
-    const size_t smem = gat_smem_floats(n_slots) * sizeof(float);
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(gat_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("gat_step: smem attr %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
-        configured = smem;
+    const size_t smem_r = rec_smem_floats(n_slots) * sizeof(float);
+    const size_t smem_a = att_smem_floats(n_slots) * sizeof(float);
+    static size_t conf_r = 0, conf_a = 0;
+    if (smem_r > conf_r) {
+        cudaError_t e = cudaFuncSetAttribute(gat_recur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+        if (e != cudaSuccess) { set_error("gat_step: recur smem attr %zu: %s", smem_r, cudaGetErrorString(e)); return (int)e; }
+        conf_r = smem_r;
     }
-    dim3 grid(n_envs, n_agents);
-    gat_step_kernel<<<grid, GAT_THREADS, smem, (cudaStream_t)stream>>>(a);
+    if (smem_a > conf_a) {
+        cudaError_t e = cudaFuncSetAttribute(gat_attend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+        if (e != cudaSuccess) { set_error("gat_step: attend smem attr %zu: %s", smem_a, cudaGetErrorString(e)); return (int)e; }
+        conf_a = smem_a;
+    }
+    gat_recur_kernel<<<dim3(n_envs, n_agents, 2), REC_THREADS, smem_r, (cudaStream_t)stream>>>(a);
     count_launch();
-    return check_launch("gat_step");
+    int rc = check_launch("gat_step(recur)");
+    if (rc) return rc;
+    gat_attend_kernel<<<dim3(n_envs, n_agents), GAT_THREADS, smem_a, (cudaStream_t)stream>>>(a);
+    count_launch();
+    return check_launch("gat_step(attend)");
 }

@@ -40,6 +40,7 @@ class Prediction_policy:
         self.debug_gumbel = None    # [A,B,N,N-1,2] explicit gumbel noise for the next call (parity tests)
         self.capture_hard = False   # keep the hard-attention weights of the last call in .last_hard
         self.last_hard = None
+        self._scratch = None      # kernel-to-kernel hand-off buffer of K1 (iplan_gat_scratch_floats)
 
     # ---- device path: tensors laid out [A, B, N, *] (any strides) ------------------
     def gat_step(self, hist, beh_prev, h_prev, out, gumbel=None, dbg_hard=None):
@@ -47,10 +48,14 @@ class Prediction_policy:
         A, B, N, o = hist.shape
         if gumbel is not None:
             assert gumbel.is_contiguous() and tuple(gumbel.shape) == (A, B, N, N - 1, 2), gumbel.shape
+        need = _lib.lib.iplan_gat_scratch_floats(B, A, N)
+        if self._scratch is None or self._scratch.numel() < need or self._scratch.device != hist.device:
+            self._scratch = torch.empty(need, device=hist.device, dtype=torch.float32)
         rc = _lib.lib.iplan_gat_step(
             _lib.ptr(self.stack.flat), self.stack.stride(),
             _lib.view(hist), _lib.view(beh_prev), _lib.view(h_prev), _lib.view(out),
             _lib.ptr(gumbel), self.seed, self.calls, self.tau, _lib.ptr(dbg_hard),
+            _lib.ptr(self._scratch), self._scratch.numel(),
             B, A, N, o, beh_prev.shape[-1], _lib.stream())
         _lib.check(rc, "gat_step")
         self.calls += 1

@@ -79,9 +79,10 @@ def test_gat_kernel_vs_reference_golden(golden_dir, case):
     out = torch.zeros(1, B, N, D, device="cuda")
     hard = torch.zeros(1, B, N, N - 1, device="cuda")
     gum = g["gumbel"].cuda().view(1, B, N, N - 1, 2).contiguous()
+    scratch = torch.empty(_lib.lib.iplan_gat_scratch_floats(B, 1, N), device="cuda")
     rc = _lib.lib.iplan_gat_step(_lib.ptr(stack.flat), stack.stride(), _lib.view(hist), _lib.view(beh),
                                  _lib.view(hprev), _lib.view(out), _lib.ptr(gum), 1, 0, 0.01, _lib.ptr(hard),
-                                 B, 1, N, o, L, _lib.stream())
+                                 _lib.ptr(scratch), scratch.numel(), B, 1, N, o, L, _lib.stream())
     _lib.check(rc, "gat_step")
     torch.cuda.synchronize()
     from oracle import iplan_oracle as O
@@ -248,7 +249,7 @@ def test_argument_checks_fail_loudly():
     _need_gpu()
     from iplan_b200 import _lib
     z = _lib.View(0, 0, 0, 0)
-    rc = _lib.lib.iplan_gat_step(None, 0, z, z, z, z, None, 0, 0, 0.01, None, 1, 1, 200, 5, 8, None)
+    rc = _lib.lib.iplan_gat_step(None, 0, z, z, z, z, None, 0, 0, 0.01, None, None, 0, 1, 1, 200, 5, 8, None)
     assert rc != 0 and b"n_slots" in _lib.lib.iplan_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "gat_step")
