@@ -109,9 +109,17 @@ def view(t):
 io_bytes = {"h2d": 0, "d2h": 0}      # host<->device traffic of the reference-facing (numpy) API
 
 
+_copy_stream = None
+
+
 def to_device(x, dtype=torch.float32, device="cuda"):
-    """numpy / CPU tensor -> CUDA tensor of `dtype`, counting the bytes that cross PCIe."""
+    """numpy / CPU tensor -> CUDA tensor of `dtype`, counting the bytes that cross PCIe.
+
+    The host buffer is reusable when this returns (the reference's ``th.tensor(x).to(device)``
+    semantics).  Page-locked sources (e.g. arrays handed out by ``to_host``) are copied on a side
+    stream, so the copy does not queue behind kernels already in flight on the compute stream."""
     import numpy as np
+    global _copy_stream
     if torch.is_tensor(x):
         if x.is_cuda:
             return x.to(dtype)
@@ -120,13 +128,34 @@ def to_device(x, dtype=torch.float32, device="cuda"):
         t = torch.as_tensor(np.asarray(x))
     t = t.to(dtype)
     io_bytes["h2d"] += t.numel() * t.element_size()
-    return t.to(device, non_blocking=True)
+    if t.numel() >= (1 << 16) and t.is_contiguous() and t.is_pinned():
+        if _copy_stream is None:
+            _copy_stream = torch.cuda.Stream()
+        with torch.cuda.stream(_copy_stream):
+            d = t.to(device, non_blocking=True)
+        _copy_stream.synchronize()
+        d.record_stream(torch.cuda.current_stream())
+        return d
+    return t.to(device)
 
 
 def to_host(t):
-    """CUDA tensor -> numpy, counting the bytes."""
+    """CUDA tensor -> fresh numpy array (page-locked, from torch's caching host allocator, so that
+    the copy runs at PCIe speed and a later ``to_device`` of the same array does too)."""
     io_bytes["d2h"] += t.numel() * t.element_size()
-    return t.cpu().numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()
+
+
+def pinned_numpy(t):
+    """Copy of a (CUDA or CPU) tensor as a numpy array in page-locked host memory."""
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t)
+    if t.is_cuda:
+        torch.cuda.current_stream().synchronize()
+    return h.numpy()
 
 
 def stream():

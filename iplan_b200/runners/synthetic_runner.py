@@ -26,6 +26,7 @@ from types import SimpleNamespace
 import numpy as np
 import torch as th
 
+from .. import _lib
 from ..components.episode_buffer import EpisodeBatch
 from ..components.transforms import OneHot
 
@@ -72,13 +73,13 @@ class SyntheticHighway:
     def host_episode(self):
         """Host-memory copies of the episode (numpy, fp32), as a CPU simulator + observation wrapper
         would deliver them: history[t] [B,A,N,o], window[t] [B,A,N,W,o], reward [T,B,A],
-        terminated [T,B,A].  Built once per generated episode (2.6 GB at B=512)."""
+        terminated [T,B,A], in page-locked memory.  Built once per generated episode (2.6 GB at B=512)."""
         if getattr(self, "_host", None) is None or self._host["episode"] != self.episodes:
             T = self.T
             self._host = dict(episode=self.episodes,
-                              history=[self.history[t].cpu().numpy() for t in range(T + 1)],
-                              window=[self.window(t).cpu().numpy() for t in range(T + 1)],
-                              reward=self.reward.cpu().numpy(), terminated=self.terminated.cpu().numpy())
+                              history=[_lib.pinned_numpy(self.history[t]) for t in range(T + 1)],
+                              window=[_lib.pinned_numpy(self.window(t)) for t in range(T + 1)],
+                              reward=_lib.pinned_numpy(self.reward), terminated=_lib.pinned_numpy(self.terminated))
         return self._host
 
     def close(self):
