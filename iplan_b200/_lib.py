@@ -162,6 +162,59 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---- chunk-pipelined host <-> device calls (the reference-facing numpy API) --------------------
+_h2d_stream = None
+_d2h_stream = None
+PIPELINE_CHUNKS = 4          # env-dimension chunks per call
+PIPELINE_MIN_ROWS = 128      # below this many envs a call is one copy-in / launch / copy-out
+
+
+def as_host(x, dtype=torch.float32):
+    """numpy / CPU tensor -> CPU tensor of `dtype` (shares memory when no conversion is needed)."""
+    import numpy as np
+    t = x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x))
+    assert not t.is_cuda
+    return t.to(dtype)
+
+
+def can_pipeline(host_tensors, rows):
+    return rows >= PIPELINE_MIN_ROWS and all(t.is_pinned() and t.is_contiguous() for t in host_tensors)
+
+
+def run_pipelined(host_in, dev_in, host_out, dev_out, launch, n_chunks=None):
+    """Overlap PCIe with compute inside ONE synchronous API call.  The leading (env) dimension is cut into
+    chunks; chunk c's inputs go host -> device on a copy stream, ``launch(lo, hi)`` runs on the current stream
+    as soon as they have landed, and its rows of ``dev_out`` go device -> host on a second copy stream while
+    the next chunk computes.  Host tensors must be page-locked.  Returns when ``host_out`` is complete, so the
+    caller's numpy-in / numpy-out contract (and the reusability of its input buffers) is unchanged."""
+    global _h2d_stream, _d2h_stream
+    if _h2d_stream is None:
+        _h2d_stream, _d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    n = n_chunks or PIPELINE_CHUNKS
+    B = host_out.shape[0]
+    _h2d_stream.wait_stream(main)            # the staging buffers may still be in use by earlier launches
+    for c in range(n):
+        lo, hi = B * c // n, B * (c + 1) // n
+        if hi <= lo:
+            continue
+        with torch.cuda.stream(_h2d_stream):
+            for h, d in zip(host_in, dev_in):
+                d[lo:hi].copy_(h[lo:hi], non_blocking=True)
+                io_bytes["h2d"] += h[lo:hi].numel() * h.element_size()
+            landed = torch.cuda.Event()
+            landed.record(_h2d_stream)
+        main.wait_event(landed)
+        launch(lo, hi)
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(_d2h_stream):
+            _d2h_stream.wait_event(done)
+            host_out[lo:hi].copy_(dev_out[lo:hi], non_blocking=True)
+            io_bytes["d2h"] += host_out[lo:hi].numel() * host_out.element_size()
+    _d2h_stream.synchronize()
+
+
 def layout(kind, *dims):
     """(total floats per agent, [offsets]) of a flat parameter buffer."""
     n = {"gat": 20, "beh": 8, "actor": 22, "critic": 26}[kind]

@@ -10,6 +10,8 @@
 // One CTA handles CTRL_ROWS envs of one agent; both nets share the staged input rows.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace iplan {
@@ -75,6 +77,71 @@ __device__ __forceinline__ void cldsm(uint32_t (&r)[4], const void* p) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(s));
 }
 
+
+constexpr int TAP = R + 8;               // fp32 pitch of the tail's activation rows: conflict-free float2 fragment reads
+
+// out[row][8 nt + c] = bias[8 nt + c] + sum_k A[row][k] * Wg[(8 nt + c) * 64 + k]   for nt in [nt0, nt1), row < CTRL_ROWS
+// A: shared memory rows (pitch TAP) of ONE net; Wg / bias: global.  K = 64: 4 k-blocks x 3 MMAs (f16 hi/lo split)
+// per accumulator.  The weight fragments are read from global exactly once per CTA (a quad reads 32 contiguous
+// bytes of one weight row), instead of once per row as a per-row dot product would.
+__device__ __forceinline__ void tail_gemm64(const float* A, const float* __restrict__ Wg, const float* __restrict__ bias,
+                                            int nt0, int nt1, float* out, int ldout, int lane) {
+    const int gq = lane >> 2, tq = lane & 3;
+    uint32_t ah[CTRL_MT][4][4], al[CTRL_MT][4][4];
+#pragma unroll
+    for (int m = 0; m < CTRL_MT; ++m) {
+        const float* x0 = A + min(16 * m + gq, CTRL_ROWS - 1) * TAP + 2 * tq;
+        const float* x1 = A + min(16 * m + gq + 8, CTRL_ROWS - 1) * TAP + 2 * tq;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            const float2 v00 = *reinterpret_cast<const float2*>(x0 + 16 * kb);
+            const float2 v10 = *reinterpret_cast<const float2*>(x1 + 16 * kb);
+            const float2 v01 = *reinterpret_cast<const float2*>(x0 + 16 * kb + 8);
+            const float2 v11 = *reinterpret_cast<const float2*>(x1 + 16 * kb + 8);
+            csplit(v00.x, v00.y, ah[m][kb][0], al[m][kb][0]);
+            csplit(v10.x, v10.y, ah[m][kb][1], al[m][kb][1]);
+            csplit(v01.x, v01.y, ah[m][kb][2], al[m][kb][2]);
+            csplit(v11.x, v11.y, ah[m][kb][3], al[m][kb][3]);
+        }
+    }
+    float2 wv[2][8];                                            // weight fragments of the current and the next n-tile
+    auto load_w = [&](int nt, float2 (&w)[8]) {
+        const float* wr = Wg + (size_t)(8 * nt + gq) * R + 2 * tq;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            w[2 * kb] = __ldg(reinterpret_cast<const float2*>(wr + 16 * kb));
+            w[2 * kb + 1] = __ldg(reinterpret_cast<const float2*>(wr + 16 * kb + 8));
+        }
+    };
+    load_w(nt0, wv[0]);
+#pragma unroll 2
+    for (int nt = nt0; nt < nt1; ++nt) {
+        const int cur = (nt - nt0) & 1;
+        if (nt + 1 < nt1) load_w(nt + 1, wv[cur ^ 1]);
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            csplit(wv[cur][2 * kb].x, wv[cur][2 * kb].y, bh[kb][0], bl[kb][0]);
+            csplit(wv[cur][2 * kb + 1].x, wv[cur][2 * kb + 1].y, bh[kb][1], bl[kb][1]);
+        }
+        const int c0 = 8 * nt + 2 * tq;
+        const float b0 = bias[c0], b1 = bias[c0 + 1];
+#pragma unroll
+        for (int m = 0; m < CTRL_MT; ++m) {
+            float acc[4] = {b0, b1, b0, b1};
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+                cmma(acc, ah[m][kb], bh[kb][0], bh[kb][1]);
+                cmma(acc, al[m][kb], bh[kb][0], bh[kb][1]);
+                cmma(acc, ah[m][kb], bl[kb][0], bl[kb][1]);
+            }
+            const int r0 = 16 * m + gq, r1 = r0 + 8;
+            if (r0 < CTRL_ROWS) *reinterpret_cast<float2*>(out + r0 * ldout + c0) = make_float2(acc[0], acc[1]);
+            if (r1 < CTRL_ROWS) *reinterpret_cast<float2*>(out + r1 * ldout + c0) = make_float2(acc[2], acc[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ag = blockIdx.y, b0 = blockIdx.x * CTRL_ROWS;
@@ -83,10 +150,14 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlAr
     const int K16 = (F + 15) & ~15, LDH = K16 + 8;              // f16 row pitch: conflict-free ldmatrix
     __half* s_yh = reinterpret_cast<__half*>(smem_raw);         // [ROWS][LDH] normalised rows, f16 hi
     __half* s_yl = s_yh + CTRL_ROWS * LDH;                      // [ROWS][LDH] ... f16 lo
-    float* s_z = reinterpret_cast<float*>(s_yl + CTRL_ROWS * LDH);   // [2][ROWS][64] fc1 pre-activations
-    float* s_act = s_z + 2 * CTRL_ROWS * R;     // [2*ROWS][64] per-task activation buffer
-    float* s_h0 = s_act + 2 * CTRL_ROWS * R;    // [2*ROWS][64] per-task hidden input
-    float* s_stat = s_h0 + 2 * CTRL_ROWS * R;   // [ROWS][2] mean, rstd
+    // the f16 rows are dead after fc1; the GRU projections of the tail reuse their space (s_gi / s_gh below)
+    const size_t stage_bytes = max((size_t)2 * CTRL_ROWS * LDH * sizeof(__half), (size_t)4 * CTRL_ROWS * 3 * R * sizeof(float));
+    float* s_z = reinterpret_cast<float*>(smem_raw + stage_bytes);   // [2][ROWS][64] fc1 pre-activations
+    float* s_act = s_z + 2 * CTRL_ROWS * R;     // [2*ROWS][TAP] per-task activation rows
+    float* s_h0 = s_act + 2 * CTRL_ROWS * TAP;  // [2*ROWS][TAP] per-task hidden input
+    float* s_stat = s_h0 + 2 * CTRL_ROWS * TAP; // [ROWS][2] mean, rstd
+    float* s_gi = reinterpret_cast<float*>(smem_raw);    // [2*ROWS][192] GRU input projections (aliases s_yh/s_yl: dead after fc1)
+    float* s_gh = s_gi + 2 * CTRL_ROWS * 3 * R;          // [2*ROWS][192] GRU hidden projections
 
     // ---- LayerNorm statistics over the F input features (two passes, rows stay in L1/L2) -------
     for (int r = warp; r < CTRL_ROWS; r += CTRL_WARPS) {
@@ -134,17 +205,23 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlAr
             al_base[m] = s_yl + row * LDH + (lane >> 4) * 8;
         }
         const int nkb = K16 >> 4;
-        for (int kc = 0; kc < nkb; kc += 4) {                    // 4 k-blocks: 12 chained MMAs, then fp32 add
-            float wv[4][4];
+        // weights of one chunk (4 k-blocks) as B-fragment scalars; the NEXT chunk's loads are issued before
+        // the current chunk's MMAs, so the L2 round trip overlaps the tensor work
+        auto load_chunk = [&](int kc, float (&w)[4][4]) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {                        // all weight loads of the chunk first
+            for (int q = 0; q < 4; ++q) {
                 const int k0 = 16 * (kc + q) + 2 * tq;
                 const bool on = kc + q < nkb;
-                wv[q][0] = (on && k0 < F) ? __ldg(w1 + k0) : 0.0f;
-                wv[q][1] = (on && k0 + 1 < F) ? __ldg(w1 + k0 + 1) : 0.0f;
-                wv[q][2] = (on && k0 + 8 < F) ? __ldg(w1 + k0 + 8) : 0.0f;
-                wv[q][3] = (on && k0 + 9 < F) ? __ldg(w1 + k0 + 9) : 0.0f;
+                w[q][0] = (on && k0 < F) ? __ldg(w1 + k0) : 0.0f;
+                w[q][1] = (on && k0 + 1 < F) ? __ldg(w1 + k0 + 1) : 0.0f;
+                w[q][2] = (on && k0 + 8 < F) ? __ldg(w1 + k0 + 8) : 0.0f;
+                w[q][3] = (on && k0 + 9 < F) ? __ldg(w1 + k0 + 9) : 0.0f;
             }
+        };
+        float wv[4][4], wn[4][4];
+        load_chunk(0, wv);
+        for (int kc = 0; kc < nkb; kc += 4) {                    // 4 k-blocks: 12 chained MMAs, then fp32 add
+            load_chunk(kc + 4, wn);
             float part[CTRL_MT][4];
 #pragma unroll
             for (int m = 0; m < CTRL_MT; ++m) part[m][0] = part[m][1] = part[m][2] = part[m][3] = 0.0f;
@@ -169,6 +246,10 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlAr
             for (int m = 0; m < CTRL_MT; ++m) {
                 acc[m][0] += part[m][0]; acc[m][1] += part[m][1]; acc[m][2] += part[m][2]; acc[m][3] += part[m][3];
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) wv[q][e] = wn[q][e];
         }
         const int n0 = warp * 8 + 2 * tq;
 #pragma unroll
@@ -184,45 +265,68 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlAr
         __syncthreads();
     }
 
-    // ---- tails: 2*ROWS (net,row) tasks, one warp each ---------------------------------
+    // ---- tails.  Row-wise pieces (LayerNorm, gates, heads): 2*ROWS (net,row) tasks, one warp each;
+    //      the 64-wide products (fc2, GRU projections) on the tensor cores, weights read once per CTA.
+    const float* const Pa = a.actor + (int64_t)ag * a.actor_stride;
+    const float* const Pc = a.critic + (int64_t)ag * a.critic_stride;
+    // actor and critic trunks share every offset up to head_w (state_dict order); only head_b differs
+    const TrunkLayout L = trunk_layout(F, a.n_actions, false);
+    const int64_t critic_head_b = trunk_layout(F, 1, true).head_b;
+    for (int task = warp; task < 2 * CTRL_ROWS; task += CTRL_WARPS) {       // ReLU -> LN1; stage h0
+        const int net = task / CTRL_ROWS, r = task % CTRL_ROWS;
+        const int bc = min(b0 + r, a.n_envs - 1);
+        const float* P = net == 0 ? Pa : Pc;
+        const float* hin = (net == 0 ? a.rnn_a_in : a.rnn_c_in) + ag * a.rnn_sa + bc * a.rnn_se;
+        s_h0[task * TAP + lane] = hin[lane]; s_h0[task * TAP + lane + 32] = hin[lane + 32];
+        float v0 = fmaxf(s_z[task * R + lane], 0.0f), v1 = fmaxf(s_z[task * R + lane + 32], 0.0f);
+        ln64(v0, v1, P + L.ln1_w, P + L.ln1_b, lane);
+        s_act[task * TAP + lane] = v0; s_act[task * TAP + lane + 32] = v1;
+    }
+    __syncthreads();
+    {   // fc2: warp -> (net, two n-tiles); output overwrites s_z
+        const int net = warp >> 2, nt0 = 2 * (warp & 3);
+        const float* P = net == 0 ? Pa : Pc;
+        tail_gemm64(s_act + net * CTRL_ROWS * TAP, P + L.fc2_w, P + L.fc2_b, nt0, nt0 + 2,
+                    s_z + net * CTRL_ROWS * R, R, lane);
+    }
+    __syncthreads();
+    for (int task = warp; task < 2 * CTRL_ROWS; task += CTRL_WARPS) {       // ReLU -> LN2
+        const int net = task / CTRL_ROWS;
+        const float* P = net == 0 ? Pa : Pc;
+        float v0 = fmaxf(s_z[task * R + lane], 0.0f), v1 = fmaxf(s_z[task * R + lane + 32], 0.0f);
+        ln64(v0, v1, P + L.ln2_w, P + L.ln2_b, lane);
+        s_act[task * TAP + lane] = v0; s_act[task * TAP + lane + 32] = v1;
+    }
+    __syncthreads();
+    {   // GRU projections: warp -> (net, input | hidden matrix, half of the 24 n-tiles)
+        const int net = warp >> 2, hid = (warp >> 1) & 1, nt0 = 12 * (warp & 1);
+        const float* P = net == 0 ? Pa : Pc;
+        tail_gemm64((hid ? s_h0 : s_act) + net * CTRL_ROWS * TAP, P + (hid ? L.whh : L.wih),
+                    P + (hid ? L.bhh : L.bih), nt0, nt0 + 12,
+                    (hid ? s_gh : s_gi) + net * CTRL_ROWS * 3 * R, 3 * R, lane);
+    }
+    __syncthreads();
     for (int task = warp; task < 2 * CTRL_ROWS; task += CTRL_WARPS) {
         const int net = task / CTRL_ROWS, r = task % CTRL_ROWS;
         const int b = b0 + r;
         const bool live = b < a.n_envs;          // warp-uniform
         const int bc = live ? b : a.n_envs - 1;
-        const float* P = net == 0 ? a.actor + (int64_t)ag * a.actor_stride : a.critic + (int64_t)ag * a.critic_stride;
-        const TrunkLayout L = trunk_layout(F, net == 0 ? a.n_actions : 1, net == 1);
-        float* act = s_act + task * R;
-        float* h0 = s_h0 + task * R;
-        const float* hin = (net == 0 ? a.rnn_a_in : a.rnn_c_in) + ag * a.rnn_sa + bc * a.rnn_se;
-        h0[lane] = hin[lane]; h0[lane + 32] = hin[lane + 32];
-
-        float v0 = fmaxf(s_z[task * R + lane], 0.0f), v1 = fmaxf(s_z[task * R + lane + 32], 0.0f);
-        ln64(v0, v1, P + L.ln1_w, P + L.ln1_b, lane);
-        act[lane] = v0; act[lane + 32] = v1;
-        __syncwarp();
-        v0 = fmaxf(dot64(P + L.fc2_w + lane * R, act, P[L.fc2_b + lane]), 0.0f);
-        v1 = fmaxf(dot64(P + L.fc2_w + (lane + 32) * R, act, P[L.fc2_b + lane + 32]), 0.0f);
-        ln64(v0, v1, P + L.ln2_w, P + L.ln2_b, lane);
-        __syncwarp();
-        act[lane] = v0; act[lane + 32] = v1;
-        __syncwarp();
-        // GRU step: hidden units c = lane, lane+32; gate rows r: c, z: 64+c, n: 128+c
+        const float* P = net == 0 ? Pa : Pc;
+        float* act = s_act + task * TAP;
+        const float* h0 = s_h0 + task * TAP;
+        const float* gi = s_gi + task * 3 * R;
+        const float* gh = s_gh + task * 3 * R;
+        // GRU gates: hidden units c = lane, lane+32; gate rows r: c, z: 64+c, n: 128+c
         float hn[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int c = lane + 32 * u;
-            const float gi_r = dot64(P + L.wih + (c) * R, act, P[L.bih + c]);
-            const float gi_z = dot64(P + L.wih + (R + c) * R, act, P[L.bih + R + c]);
-            const float gi_n = dot64(P + L.wih + (2 * R + c) * R, act, P[L.bih + 2 * R + c]);
-            const float gh_r = dot64(P + L.whh + (c) * R, h0, P[L.bhh + c]);
-            const float gh_z = dot64(P + L.whh + (R + c) * R, h0, P[L.bhh + R + c]);
-            const float gh_n = dot64(P + L.whh + (2 * R + c) * R, h0, P[L.bhh + 2 * R + c]);
-            const float rg = sigmoidf_acc(gi_r + gh_r);
-            const float zg = sigmoidf_acc(gi_z + gh_z);
-            const float ng = tanhf_acc(gi_n + rg * gh_n);
+            const float rg = sigmoidf_acc(gi[c] + gh[c]);
+            const float zg = sigmoidf_acc(gi[R + c] + gh[R + c]);
+            const float ng = tanhf_acc(gi[2 * R + c] + rg * gh[2 * R + c]);
             hn[u] = (1.0f - zg) * ng + zg * h0[c];
         }
+        float v0, v1;
         if (live) {
             float* hout = (net == 0 ? a.rnn_a_out : a.rnn_c_out) + ag * a.rnn_osa + b * a.rnn_ose;
             hout[lane] = hn[0]; hout[lane + 32] = hn[1];
@@ -234,7 +338,7 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlAr
         __syncwarp();
         const int64_t ob = (int64_t)ag * a.n_envs + bc;
         if (net == 1) {
-            const float val = warp_sum(v0 * P[L.head_w + lane] + v1 * P[L.head_w + lane + 32]) + P[L.head_b];
+            const float val = warp_sum(v0 * P[L.head_w + lane] + v1 * P[L.head_w + lane + 32]) + P[critic_head_b];
             if (live && lane == 0) a.values[ob] = val;
         } else {
             const int nA = a.n_actions;
@@ -317,7 +421,8 @@ extern "C" int iplan_controller_step(const float* actor_params, int64_t actor_st
     a.next_onehot = next_onehot; a.this_onehot = this_onehot;
     a.n_envs = n_envs; a.feat_dim = feat_dim; a.feat_ld = (feat_dim + 3) & ~3; a.n_actions = n_actions;
     const size_t ldh = ((feat_dim + 15) & ~15) + 8;
-    const size_t smem = (size_t)2 * CTRL_ROWS * ldh * 2 + ((size_t)6 * CTRL_ROWS * R + 2 * CTRL_ROWS) * sizeof(float);
+    const size_t stage = std::max((size_t)2 * CTRL_ROWS * ldh * 2, (size_t)4 * CTRL_ROWS * 3 * R * sizeof(float));
+    const size_t smem = stage + ((size_t)2 * CTRL_ROWS * R + 4 * CTRL_ROWS * TAP + 2 * CTRL_ROWS) * sizeof(float);
     IPLAN_REQUIRE(smem <= 227 * 1024, "controller_step: feat_dim %d needs %zu B of shared memory", feat_dim, smem);
     static size_t configured = 0;
     if (smem > configured) {

@@ -59,10 +59,15 @@ struct GatArgs {
 };
 
 __host__ __device__ inline size_t rec_smem_floats(int N) {
-    return (size_t)N * IN_MAX + (size_t)N * H + 2 * (size_t)N * G3 + 4 * NT_G * KB_H * 32 + 64;
+    return (size_t)N * IN_MAX + (size_t)N * H + 2 * (size_t)N * G3 + 4 * NT_G * KB_H * 32 + 64 + 32;
 }
+constexpr int QP = H + 8;       // q / k row pitch (floats): 8-byte aligned, conflict-free fragment reads
+constexpr int WP = 64 + 8;      // attention-weight / V^T row pitch: K = 64 neighbour columns, zero padded
 __host__ __device__ inline size_t att_smem_floats(int N) {
-    return (size_t)N * IN_MAX + (size_t)N * H + 354 * (size_t)N + (size_t)N * (N - 1) + GAT_WARPS * 64;
+    // s_vt (aliases s_x) | s_enc | s_xa | s_hp | region { s_q, s_k, s_dl, s_w }  (s_gi, s_gh alias the region)
+    const size_t region = (size_t)2 * N * QP + (size_t)N * (N - 1) + (size_t)N * WP;
+    const size_t gru = (size_t)2 * N * G3;
+    return (size_t)H * WP + 3 * (size_t)N * H + (region > gru ? region : gru);
 }
 
 // fast, fp32-accurate-enough gates (abs error ~1e-7): ex2.approx + rcp.approx
@@ -74,6 +79,55 @@ constexpr float K_RZ = -1.4426950408889634f;      // -log2(e)
 constexpr float K_N = 2.8853900817779268f;        //  2 log2(e)
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): the gate math of the recurrence is issue-slot
+// bound, and an accumulator fragment is two (col, col+1) pairs, so every elementwise op is done on
+// pairs.  A pair lives in a 64-bit register (lo = first element).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 lds64(const float* p) {
+    f32x2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
+// Four sigmoid denominators with ONE rcp.approx (the XU pipe is the recurrence's busiest unit):
+// given ea = 2^xa (pair) and eb = 2^xb (pair), returns ia = 1/(1+ea), ib = 1/(1+eb) from
+//   p = (1+ea)(1+eb) per pair,  inv = 1/(p0 p1),  q = (inv p1, inv p0) = 1/p,
+//   ia = (1+eb) q,  ib = (1+ea) q.
+// Inputs are clamped to x <= 30 so that p0 p1 <= 2^121 stays finite; the clamp moves a sigmoid by
+// < 1e-9 (the gate is saturated: pre-activation beyond 20.8).
+__device__ __forceinline__ void sigmoid4_den(f32x2 x01, f32x2 x23, f32x2& ia, f32x2& ib) {
+    float x0, x1, x2, x3;
+    upk2(x01, x0, x1); upk2(x23, x2, x3);
+    const f32x2 ea = pk2(ex2_approx(fminf(x0, 30.0f)), ex2_approx(fminf(x1, 30.0f)));
+    const f32x2 eb = pk2(ex2_approx(fminf(x2, 30.0f)), ex2_approx(fminf(x3, 30.0f)));
+    const f32x2 b = add2(eb, pk2(1.0f, 1.0f));
+    const f32x2 p = fma2(ea, b, b);
+    float p0, p1;
+    upk2(p, p0, p1);
+    const float inv = rcp_approx(p0 * p1);
+    const f32x2 q = pk2(inv * p1, inv * p0);
+    ia = mul2(b, q);
+    ib = fma2(ea, q, q);
+}
+// pair -> packed f16 hi pair and f16 lo (residual) pair
+__device__ __forceinline__ void split_f16p(f32x2 v, uint32_t& hi, uint32_t& lo) {
+    float x, y;
+    upk2(v, x, y);
+    const __half2 h = __floats2half2_rn(x, y);
+    const float2 hf = __half22float2(h);
+    float rx, ry;
+    upk2(sub2(v, pk2(hf.x, hf.y)), rx, ry);
+    const __half2 l = __floats2half2_rn(rx, ry);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 // volatile: the W_hh fragments are loop-invariant, and hoisting them out of the step loop would cost
 // 96 registers per thread
@@ -100,12 +154,12 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 }
 
-// out[n][c] = act( sum_{k<32} in[n][k] * Wg[c*ldw + k] + bias[c] )  for n < N, c < cols (cols % 8 == 0)
-// `in` / `out` in shared memory (row pitch ldin / ldout floats), W and bias in global memory.
-// All warps of the CTA cooperate: one task = one 16-node x 8-column tile = 6 MMAs (f16 hi/lo
-// split, see header).  W is read as B fragments straight from global memory: a quad reads 32
-// contiguous bytes of one weight row, so every sector fetched is fully used.
-template <int NW>
+// out[n][c] = act( sum_{k<16 KB} in[n][k] * Wg[c*ldw + k] + bias[c] )  for n < N, c < cols (cols % 8 == 0)
+// `in` / `out` in shared memory (row pitch ldin / ldout floats), W and bias in global OR shared memory.
+// All warps of the CTA cooperate: one task = one 16-node x 8-column tile = 3 KB MMAs (f16 hi/lo
+// split, see header).  W is read as B fragments: a quad reads 32 contiguous bytes of one weight row, so
+// every sector fetched is fully used.  TRANS_OUT stores out[c][n] instead (row pitch ldout).
+template <int NW, int KB = KB_H, bool TRANS_OUT = false>
 __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, const float* __restrict__ Wg, int ldw,
                                             const float* __restrict__ bias, int cols, float* out, int ldout, bool relu,
                                             int warp, int lane) {
@@ -113,18 +167,16 @@ __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, co
     const int mtiles = (N + 15) >> 4, ntiles = cols >> 3;
     const int mh = (mtiles + 1) >> 1;                 // a task = one n-tile x one half of the m-tiles
     const int ntask = ntiles * 2;
-    constexpr int DT = 3;                             // tasks whose weight fragments are fetched together
+    constexpr int DT = KB <= 2 ? 3 : 1;               // tasks whose weight fragments are fetched together
     for (int base = warp; base < ntask; base += NW * DT) {
-        float2 wv[DT][4];
+        float2 wv[DT][2 * KB];
 #pragma unroll
-        for (int i = 0; i < DT; ++i) {                // issue every global load first: one L2 round trip
+        for (int i = 0; i < DT; ++i) {                // issue every load first: one L2 round trip
             const int task = base + i * NW;
             if (task < ntask) {
                 const float* wr = Wg + (size_t)(8 * (task >> 1) + gq) * ldw + 2 * tq;
-                wv[i][0] = *reinterpret_cast<const float2*>(wr);
-                wv[i][1] = *reinterpret_cast<const float2*>(wr + 8);
-                wv[i][2] = *reinterpret_cast<const float2*>(wr + 16);
-                wv[i][3] = *reinterpret_cast<const float2*>(wr + 24);
+#pragma unroll
+                for (int q = 0; q < 2 * KB; ++q) wv[i][q] = *reinterpret_cast<const float2*>(wr + 8 * q);
             }
         }
 #pragma unroll
@@ -134,39 +186,41 @@ __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, co
             const int nt = task >> 1, half = task & 1;
             const int c0 = 8 * nt + 2 * tq;
             const float b0 = bias ? bias[c0] : 0.0f, b1 = bias ? bias[c0 + 1] : 0.0f;
-            const float cinit[4] = {b0, b1, b0, b1};
-            uint32_t bh[KB_H][2], bl[KB_H][2];
-            split_f16(wv[i][0].x, wv[i][0].y, bh[0][0], bl[0][0]);
-            split_f16(wv[i][1].x, wv[i][1].y, bh[0][1], bl[0][1]);
-            split_f16(wv[i][2].x, wv[i][2].y, bh[1][0], bl[1][0]);
-            split_f16(wv[i][3].x, wv[i][3].y, bh[1][1], bl[1][1]);
+            uint32_t bh[KB][2], bl[KB][2];
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                split_f16(wv[i][2 * kb].x, wv[i][2 * kb].y, bh[kb][0], bl[kb][0]);
+                split_f16(wv[i][2 * kb + 1].x, wv[i][2 * kb + 1].y, bh[kb][1], bl[kb][1]);
+            }
             const int mt_end = min(mtiles, (half + 1) * mh);
             for (int mt = half * mh; mt < mt_end; ++mt) {
                 const int r0 = mt * 16 + gq, r1 = r0 + 8;
                 const float* x0 = in + min(r0, N - 1) * ldin + 2 * tq;
                 const float* x1 = in + min(r1, N - 1) * ldin + 2 * tq;
-                uint32_t ahi[KB_H][4], alo[KB_H][4];
+                float acc[4] = {b0, b1, b0, b1};
 #pragma unroll
-                for (int kb = 0; kb < KB_H; ++kb) {
+                for (int kb = 0; kb < KB; ++kb) {      // <= 12 MMAs per accumulator chain (KB <= 4)
+                    uint32_t ahi[4], alo[4];
                     const float2 v00 = *reinterpret_cast<const float2*>(x0 + 16 * kb);
                     const float2 v10 = *reinterpret_cast<const float2*>(x1 + 16 * kb);
                     const float2 v01 = *reinterpret_cast<const float2*>(x0 + 16 * kb + 8);
                     const float2 v11 = *reinterpret_cast<const float2*>(x1 + 16 * kb + 8);
-                    split_f16(v00.x, v00.y, ahi[kb][0], alo[kb][0]);
-                    split_f16(v10.x, v10.y, ahi[kb][1], alo[kb][1]);
-                    split_f16(v01.x, v01.y, ahi[kb][2], alo[kb][2]);
-                    split_f16(v11.x, v11.y, ahi[kb][3], alo[kb][3]);
+                    split_f16(v00.x, v00.y, ahi[0], alo[0]);
+                    split_f16(v10.x, v10.y, ahi[1], alo[1]);
+                    split_f16(v01.x, v01.y, ahi[2], alo[2]);
+                    split_f16(v11.x, v11.y, ahi[3], alo[3]);
+                    mma16816(acc, ahi, bh[kb][0], bh[kb][1], acc);
+                    mma16816(acc, alo, bh[kb][0], bh[kb][1], acc);
+                    mma16816(acc, ahi, bl[kb][0], bl[kb][1], acc);
                 }
-                float acc[4];
-                mma16816(acc, ahi[0], bh[0][0], bh[0][1], cinit);
-                mma16816(acc, ahi[1], bh[1][0], bh[1][1], acc);
-                mma16816(acc, alo[0], bh[0][0], bh[0][1], acc);
-                mma16816(acc, alo[1], bh[1][0], bh[1][1], acc);
-                mma16816(acc, ahi[0], bl[0][0], bl[0][1], acc);
-                mma16816(acc, ahi[1], bl[1][0], bl[1][1], acc);
                 if (relu) { acc[0] = fmaxf(acc[0], 0.f); acc[1] = fmaxf(acc[1], 0.f); acc[2] = fmaxf(acc[2], 0.f); acc[3] = fmaxf(acc[3], 0.f); }
-                if (r0 < N) { out[r0 * ldout + c0] = acc[0]; out[r0 * ldout + c0 + 1] = acc[1]; }
-                if (r1 < N) { out[r1 * ldout + c0] = acc[2]; out[r1 * ldout + c0 + 1] = acc[3]; }
+                if (TRANS_OUT) {
+                    if (r0 < N) { out[c0 * ldout + r0] = acc[0]; out[(c0 + 1) * ldout + r0] = acc[1]; }
+                    if (r1 < N) { out[c0 * ldout + r1] = acc[2]; out[(c0 + 1) * ldout + r1] = acc[3]; }
+                } else {
+                    if (r0 < N) { out[r0 * ldout + c0] = acc[0]; out[r0 * ldout + c0 + 1] = acc[1]; }
+                    if (r1 < N) { out[r1 * ldout + c0] = acc[2]; out[r1 * ldout + c0 + 1] = acc[3]; }
+                }
             }
         }
     }
@@ -210,7 +264,8 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
     float* s_P = s_enc + N * H;                         // [N][96]  ego part + b_ih (+ b_hh for r|z), gate-scaled
     float* s_Q = s_P + N * G3;                          // [N][96]  neighbour part, gate-scaled
     uint4* s_w4 = reinterpret_cast<uint4*>(s_Q + N * G3);   // [12][2][32] W_hh B fragments {hi0, hi1, lo0, lo1}
-    float4* s_bw = reinterpret_cast<float4*>(s_w4 + NT_G * KB_H * 32);   // [4 t4][4 tq] {b_hn pair, logit-diff weight pair}
+    float4* s_bn = reinterpret_cast<float4*>(s_w4 + NT_G * KB_H * 32);   // [4 t4][4 tq] b_hn pair twice = the n tile's initial accumulator
+    float2* s_lw = reinterpret_cast<float2*>(s_bn + 16);                 // [4 t4][4 tq] logit-difference weight pair
 
     gat_encode<REC_THREADS>(a, W, L, b, ag, s_x, s_enc);
 
@@ -236,8 +291,9 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
         }
         if (tid < 16) {
             const int c = 8 * (tid >> 2) + 2 * (tid & 3);
-            s_bw[tid] = make_float4(K_N * bhh[2 * H + c], K_N * bhh[2 * H + c + 1],
-                                    W[L.he_w + 2 * H + dir * H + c] - W[L.he_w + dir * H + c],
+            const float b0 = K_N * bhh[2 * H + c], b1 = K_N * bhh[2 * H + c + 1];
+            s_bn[tid] = make_float4(b0, b1, b0, b1);
+            s_lw[tid] = make_float2(W[L.he_w + 2 * H + dir * H + c] - W[L.he_w + dir * H + c],
                                     W[L.he_w + 2 * H + dir * H + c + 1] - W[L.he_w + dir * H + c + 1]);
         }
     }
@@ -259,7 +315,8 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
     const uint4* w4 = s_w4 + lane;
     // per-chain constants in accumulator-fragment layout: element e of tile nt is
     // (row e<2 ? row0 : row1, col 8*nt + 2*tq + (e&1))
-    float cst[8][4], pn[4][4];
+    float cst[8][4];
+    f32x2 pn01[4], pn23[4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
         const float2 p0 = *reinterpret_cast<const float2*>(s_P + i0 * G3 + 8 * nt + 2 * tq);
@@ -270,13 +327,13 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
     for (int t4 = 0; t4 < 4; ++t4) {
         const float2 p0 = *reinterpret_cast<const float2*>(s_P + i0 * G3 + 2 * H + 8 * t4 + 2 * tq);
         const float2 p1 = *reinterpret_cast<const float2*>(s_P + i1 * G3 + 2 * H + 8 * t4 + 2 * tq);
-        pn[t4][0] = p0.x; pn[t4][1] = p0.y; pn[t4][2] = p1.x; pn[t4][3] = p1.y;
+        pn01[t4] = pk2(p0.x, p0.y); pn23[t4] = pk2(p1.x, p1.y);
     }
-    float h[4][4];
+    // hidden state: h01[t4] = (row0; cols 8 t4 + 2 tq, +1), h23[t4] = the same columns of row1
+    f32x2 h01[4], h23[4];
 #pragma unroll
-    for (int t4 = 0; t4 < 4; ++t4)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) h[t4][e] = 0.0f;
+    for (int t4 = 0; t4 < 4; ++t4) h01[t4] = h23[t4] = pk2(0.0f, 0.0f);
+    const f32x2 one2 = pk2(1.0f, 1.0f), mtwo2 = pk2(-2.0f, -2.0f);
 
     for (int step = 0; step < NM1; ++step) {
         const int s = dir ? NM1 - 1 - step : step;
@@ -284,15 +341,15 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
         uint32_t ahi[KB_H][4], alo[KB_H][4];
 #pragma unroll
         for (int kb = 0; kb < KB_H; ++kb) {
-            split_f16(h[2 * kb][0], h[2 * kb][1], ahi[kb][0], alo[kb][0]);          // row g,   k low
-            split_f16(h[2 * kb][2], h[2 * kb][3], ahi[kb][1], alo[kb][1]);          // row g+8, k low
-            split_f16(h[2 * kb + 1][0], h[2 * kb + 1][1], ahi[kb][2], alo[kb][2]);  // row g,   k high
-            split_f16(h[2 * kb + 1][2], h[2 * kb + 1][3], ahi[kb][3], alo[kb][3]);  // row g+8, k high
+            split_f16p(h01[2 * kb], ahi[kb][0], alo[kb][0]);          // row g,   k low
+            split_f16p(h23[2 * kb], ahi[kb][1], alo[kb][1]);          // row g+8, k low
+            split_f16p(h01[2 * kb + 1], ahi[kb][2], alo[kb][2]);      // row g,   k high
+            split_f16p(h23[2 * kb + 1], ahi[kb][3], alo[kb][3]);      // row g+8, k high
         }
         // neighbour of ego i at position s is j = s < i ? s : s + 1
         const float* q0 = s_Q + (s < i0 ? s : s + 1) * G3 + 2 * tq;
         const float* q1 = s_Q + (s < i1 ? s : s + 1) * G3 + 2 * tq;
-        float pl0 = 0.0f, pl1 = 0.0f;
+        f32x2 pl01 = pk2(0.0f, 0.0f), pl23 = pl01;
         // Hidden units in groups of 8 (t4): the r|z|n tiles of a group take their six MMA
         // passes (three independent chains), then the group's gate math runs while the
         // next group's MMAs are in flight, so tensor, MUFU and FP32 pipes overlap within one warp.
@@ -300,7 +357,7 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
         for (int t4 = 0; t4 < 4; ++t4) {
             float acc[3][4];
             uint4 w[3][KB_H];
-            const float4 bw = s_bw[4 * t4 + tq];
+            const float4 bn = s_bn[4 * t4 + tq];
 #pragma unroll
             for (int gi = 0; gi < 3; ++gi)
 #pragma unroll
@@ -309,7 +366,7 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
             for (int gi = 0; gi < 3; ++gi) {
                 float c0[4];
                 if (gi < 2) { const int nt = 4 * gi + t4; c0[0] = cst[nt][0]; c0[1] = cst[nt][1]; c0[2] = cst[nt][2]; c0[3] = cst[nt][3]; }
-                else { c0[0] = bw.x; c0[1] = bw.y; c0[2] = bw.x; c0[3] = bw.y; }
+                else { c0[0] = bn.x; c0[1] = bn.y; c0[2] = bn.z; c0[3] = bn.w; }
                 mma16816(acc[gi], ahi[0], w[gi][0].x, w[gi][0].y, c0);
             }
 #pragma unroll
@@ -322,27 +379,27 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
             for (int gi = 0; gi < 3; ++gi) mma16816(acc[gi], ahi[0], w[gi][0].z, w[gi][0].w, acc[gi]);
 #pragma unroll
             for (int gi = 0; gi < 3; ++gi) mma16816(acc[gi], ahi[1], w[gi][1].z, w[gi][1].w, acc[gi]);
-            const float2 qr0 = *reinterpret_cast<const float2*>(q0 + 8 * t4);
-            const float2 qz0 = *reinterpret_cast<const float2*>(q0 + H + 8 * t4);
-            const float2 qn0 = *reinterpret_cast<const float2*>(q0 + 2 * H + 8 * t4);
-            const float2 qr1 = *reinterpret_cast<const float2*>(q1 + 8 * t4);
-            const float2 qz1 = *reinterpret_cast<const float2*>(q1 + H + 8 * t4);
-            const float2 qn1 = *reinterpret_cast<const float2*>(q1 + 2 * H + 8 * t4);
-            const float qr[4] = {qr0.x, qr0.y, qr1.x, qr1.y};
-            const float qz[4] = {qz0.x, qz0.y, qz1.x, qz1.y};
-            const float qn[4] = {qn0.x, qn0.y, qn1.x, qn1.y};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float r = rcp_approx(1.0f + ex2_approx(acc[0][e] + qr[e]));
-                const float z = rcp_approx(1.0f + ex2_approx(acc[1][e] + qz[e]));
-                const float en = ex2_approx(fmaf(r, acc[2][e], pn[t4][e] + qn[e]));
-                const float n = fmaf(-2.0f, rcp_approx(1.0f + en), 1.0f);
-                h[t4][e] = fmaf(z, h[t4][e] - n, n);                // (1 - z) n + z h
-            }
-            pl0 = fmaf(bw.z, h[t4][0], fmaf(bw.w, h[t4][1], pl0));
-            pl1 = fmaf(bw.z, h[t4][2], fmaf(bw.w, h[t4][3], pl1));
+            // gates on (col, col+1) pairs; four reciprocals per rcp.approx (rcp4)
+            f32x2 r01, r23, z01, z23, i01, i23;
+            sigmoid4_den(add2(pk2(acc[0][0], acc[0][1]), lds64(q0 + 8 * t4)),
+                         add2(pk2(acc[0][2], acc[0][3]), lds64(q1 + 8 * t4)), r01, r23);      // r = 1 / (1 + 2^x')
+            sigmoid4_den(add2(pk2(acc[1][0], acc[1][1]), lds64(q0 + H + 8 * t4)),
+                         add2(pk2(acc[1][2], acc[1][3]), lds64(q1 + H + 8 * t4)), z01, z23);
+            sigmoid4_den(fma2(r01, pk2(acc[2][0], acc[2][1]), add2(pn01[t4], lds64(q0 + 2 * H + 8 * t4))),
+                         fma2(r23, pk2(acc[2][2], acc[2][3]), add2(pn23[t4], lds64(q1 + 2 * H + 8 * t4))), i01, i23);
+            const f32x2 n01 = fma2(mtwo2, i01, one2), n23 = fma2(mtwo2, i23, one2);   // tanh = 1 - 2 / (1 + 2^x')
+            h01[t4] = fma2(z01, sub2(h01[t4], n01), n01);                   // (1 - z) n + z h
+            h23[t4] = fma2(z23, sub2(h23[t4], n23), n23);
+            const f32x2 lw = lds64(reinterpret_cast<const float*>(s_lw + 4 * t4 + tq));
+            pl01 = fma2(lw, h01[t4], pl01);
+            pl23 = fma2(lw, h23[t4], pl23);
         }
         // the 32 hidden units of a row live in the 4 lanes of a quad
+        float pa, pb;
+        upk2(pl01, pa, pb);
+        float pl0 = pa + pb;
+        upk2(pl23, pa, pb);
+        float pl1 = pa + pb;
         pl0 += __shfl_xor_sync(0xffffffffu, pl0, 1); pl0 += __shfl_xor_sync(0xffffffffu, pl0, 2);
         pl1 += __shfl_xor_sync(0xffffffffu, pl1, 1); pl1 += __shfl_xor_sync(0xffffffffu, pl1, 2);
         if (tq == 0) {                                      // dl[s][i]: a warp's 16 egos are one 64-byte segment
@@ -362,27 +419,29 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
     const float* __restrict__ W = a.params + (int64_t)ag * a.param_stride;
     const GatLayout L = gat_layout(in_dim);
 
-    float* s_x = smem;                                  // [N][IN_MAX]
-    float* s_enc = s_x + N * IN_MAX;                    // [N][H]
-    float* s_q = s_enc + N * H;                         // [N][33]
-    float* s_k = s_q + N * 33;                          // [N][33]
-    float* s_v = s_k + N * 33;                          // [N][H]
-    float* s_xa = s_v + N * H;                          // [N][H] aggregated messages
+    float* s_vt = smem;                                 // [H][WP]  V^T: s_vt[c][j] = v_j[c], columns >= N zero
+    float* s_x = smem;                                  // [N][IN_MAX] (dead after the encode; N*IN_MAX <= H*WP)
+    float* s_enc = s_vt + H * WP;                       // [N][H]
+    float* s_xa = s_enc + N * H;                        // [N][H] aggregated messages
     float* s_hp = s_xa + N * H;                         // [N][H] h_prev
-    float* s_gi = s_hp + N * H;                         // [N][96] GRUCell input pre-activations
+    float* s_q = s_hp + N * H;                          // [N][QP]
+    float* s_k = s_q + N * QP;                          // [N][QP]
+    float* s_dl = s_k + N * QP;                         // [N][N-1] logit difference, both directions summed
+    float* s_w = s_dl + N * NM1;                        // [N][WP] scores, then attention weights over ALL slots j (self = 0)
+    float* s_gi = s_q;                                  // [N][96] GRUCell input pre-activations  (q, k, dl, w are dead by then)
     float* s_gh = s_gi + N * G3;                        // [N][96] GRUCell hidden pre-activations
-    float* s_dl = s_gh + N * G3;                        // [N][N-1] logit difference, both directions summed
-    float* s_w = s_dl + N * NM1;                        // [warps][64] attention weights
 
     const float* hprev = a.hprev.ptr + ag * a.hprev.stride_agent + b * a.hprev.stride_env;
     float* outp = a.out.ptr + ag * a.out.stride_agent + b * a.out.stride_env;
 
     gat_encode<GAT_THREADS>(a, W, L, b, ag, s_x, s_enc);
 
-    // ---- phase 4: q, k, v; stage h_prev and the recurrence kernel's dl[dir][s][i] ------
-    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.q_w, H, nullptr, H, s_q, 33, false, warp, lane);
-    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.k_w, H, nullptr, H, s_k, 33, false, warp, lane);
-    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.v_w, H, W + L.v_b, H, s_v, H, true, warp, lane);
+    // ---- phase 4: q, k, v^T; stage h_prev and the recurrence kernel's dl[dir][s][i] ------
+    for (int idx = tid; idx < H * WP; idx += GAT_THREADS) s_vt[idx] = 0.0f;       // s_x is dead: gat_encode ends with a barrier
+    __syncthreads();
+    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.q_w, H, nullptr, H, s_q, QP, false, warp, lane);
+    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.k_w, H, nullptr, H, s_k, QP, false, warp, lane);
+    dense32_mma<GAT_WARPS, KB_H, true>(s_enc, H, N, W + L.v_w, H, W + L.v_b, H, s_vt, WP, true, warp, lane);
     for (int idx = tid; idx < N * H; idx += GAT_THREADS)
         s_hp[idx] = hprev[(idx >> 5) * a.hprev.stride_slot + (idx & 31)];
     {
@@ -395,9 +454,14 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
     }
     __syncthreads();
 
-    // ---- phase 5: soft x hard attention, one warp per ego -----------------------------
+    // ---- phase 5a: raw scores S[i][j] = q_i . k_j for every slot pair, on the tensor cores --------
+    // (columns are padded to a multiple of 8: rows of s_k past N-1 are whatever follows in shared memory;
+    //  those columns are never read)
+    dense32_mma<GAT_WARPS>(s_q, QP, N, s_k, QP, nullptr, (N + 7) & ~7, s_w, WP, false, warp, lane);
+    __syncthreads();
+
+    // ---- phase 5b: soft x hard attention weights, one warp per ego; lane -> slots j = lane, lane + 32 ----
     const float db = W[L.he_b + 1] - W[L.he_b + 0];
-    float* wbuf = s_w + warp * 64;
     for (int i = warp; i < N; i += GAT_WARPS) {
         float sc[2], hd[2];
         uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
@@ -406,27 +470,20 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
             rnd = philox4x32(make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.counter, (uint32_t)(a.counter >> 32)),
                              make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
         }
+        float* wrow = s_w + i * WP;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const int s = lane + 32 * u;
+            const int j = lane + 32 * u;
             sc[u] = -INFINITY; hd[u] = 0.0f;
-            if (s < NM1) {
-                const int j = s < i ? s : s + 1;
-                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;     // four independent chains
-#pragma unroll
-                for (int k = 0; k < H; k += 4) {
-                    a0 = fmaf(s_q[i * 33 + k], s_k[j * 33 + k], a0);
-                    a1 = fmaf(s_q[i * 33 + k + 1], s_k[j * 33 + k + 1], a1);
-                    a2 = fmaf(s_q[i * 33 + k + 2], s_k[j * 33 + k + 2], a2);
-                    a3 = fmaf(s_q[i * 33 + k + 3], s_k[j * 33 + k + 3], a3);
-                }
-                sc[u] = ((a0 + a1) + (a2 + a3)) / 5.656854249492381f;   // np.sqrt(attention_dim), :126
+            if (j < N && j != i) {
+                const int s = j < i ? j : j - 1;                         // position of neighbour j in ego i's sequence
+                sc[u] = wrow[j] / 5.656854249492381f;                    // np.sqrt(attention_dim), :126
                 float noise;
                 const int64_t edge = (((int64_t)ag * a.n_envs + b) * N + i) * NM1 + s;
                 if (a.gumbel) {
                     noise = a.gumbel[2 * edge + 1] - a.gumbel[2 * edge];
                 } else {
-                    // one Philox call per (ego, lane) serves both of the lane's edges (s = lane, lane + 32)
+                    // one Philox call per (ego, lane) serves both of the lane's slots
                     const float uu = u01(u == 0 ? rnd.x : rnd.y);
                     noise = __logf(uu) - __logf(1.0f - uu);  // Gumbel - Gumbel ~ Logistic(0,1)
                 }
@@ -436,25 +493,16 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
             }
         }
         const float mx = warp_max(fmaxf(sc[0], sc[1]));
-        const float e0 = (lane < NM1) ? expf(sc[0] - mx) : 0.0f;
-        const float e1 = (lane + 32 < NM1) ? expf(sc[1] - mx) : 0.0f;
+        const float e0 = expf(sc[0] - mx);                               // exp(-inf) = 0 for self / padding
+        const float e1 = expf(sc[1] - mx);
         const float den = warp_sum(e0 + e1);
-        wbuf[lane] = (e0 / den) * hd[0];
-        wbuf[lane + 32] = (e1 / den) * hd[1];
-        __syncwarp();
-        // x_i = sum_s w[s] * v[j(s)]: four independent partial sums per lane
-        float xa0 = 0.0f, xa1 = 0.0f, xa2 = 0.0f, xa3 = 0.0f;
-        int s = 0;
-        for (; s + 3 < NM1; s += 4) {
-            xa0 = fmaf(wbuf[s], s_v[(s < i ? s : s + 1) * H + lane], xa0);
-            xa1 = fmaf(wbuf[s + 1], s_v[(s + 1 < i ? s + 1 : s + 2) * H + lane], xa1);
-            xa2 = fmaf(wbuf[s + 2], s_v[(s + 2 < i ? s + 2 : s + 3) * H + lane], xa2);
-            xa3 = fmaf(wbuf[s + 3], s_v[(s + 3 < i ? s + 3 : s + 4) * H + lane], xa3);
-        }
-        for (; s < NM1; ++s) xa0 = fmaf(wbuf[s], s_v[(s < i ? s : s + 1) * H + lane], xa0);
-        s_xa[i * H + lane] = (xa0 + xa1) + (xa2 + xa3);
-        __syncwarp();
+        wrow[lane] = (e0 / den) * hd[0];
+        wrow[lane + 32] = (e1 / den) * hd[1];
     }
+    __syncthreads();
+
+    // ---- phase 5c: x_i = sum_j w[i][j] v_j  =  W (N x 64) . V (64 x 32), on the tensor cores -------
+    dense32_mma<GAT_WARPS, 4>(s_w, WP, N, s_vt, WP, nullptr, H, s_xa, H, false, warp, lane);
     __syncthreads();
 
     // ---- phase 6: GRUCell(x_i, h_prev_i) (:140): two N x 96 x 32 products + gates -----

@@ -41,6 +41,7 @@ class Prediction_policy:
         self.capture_hard = False   # keep the hard-attention weights of the last call in .last_hard
         self.last_hard = None
         self._scratch = None      # kernel-to-kernel hand-off buffer of K1 (iplan_gat_scratch_floats)
+        self._stage = None        # device staging buffers of the pipelined numpy entry point
 
     # ---- device path: tensors laid out [A, B, N, *] (any strides) ------------------
     def gat_step(self, hist, beh_prev, h_prev, out, gumbel=None, dbg_hard=None):
@@ -64,13 +65,30 @@ class Prediction_policy:
     # ---- reference-compatible numpy entry point (reference :92-118) -----------------
     def GAT_latent_update(self, history_single, encoder_hidden, behavior_latent=None):
         dev = self.device
-        hs = _lib.to_device(history_single)
-        eh = _lib.to_device(encoder_hidden)
-        bl = _lib.to_device(behavior_latent)
-        out = torch.empty_like(eh)
-        perm = (1, 0, 2, 3)       # [B,A,N,*] -> [A,B,N,*] views, no copy
         gum = self.debug_gumbel
         self.debug_gumbel = None
+        perm = (1, 0, 2, 3)       # [B,A,N,*] -> [A,B,N,*] views, no copy
+        hs_h, eh_h, bl_h = _lib.as_host(history_single), _lib.as_host(encoder_hidden), _lib.as_host(behavior_latent)
+        B = hs_h.shape[0]
+        if gum is None and not self.capture_hard and _lib.can_pipeline((hs_h, eh_h, bl_h), B):
+            # page-locked inputs: copy-in, K1 and copy-out overlap chunk by chunk over the envs
+            key = (tuple(hs_h.shape), tuple(eh_h.shape), tuple(bl_h.shape))
+            if self._stage is None or self._stage[0] != key:
+                self._stage = (key, torch.empty(hs_h.shape, device=dev), torch.empty(eh_h.shape, device=dev),
+                               torch.empty(bl_h.shape, device=dev), torch.empty(eh_h.shape, device=dev))
+            _, hs, eh, bl, out = self._stage
+            out_h = torch.empty(eh_h.shape, dtype=torch.float32, pin_memory=True)
+
+            def launch(lo, hi):
+                self.gat_step(hs[lo:hi].permute(perm), bl[lo:hi].permute(perm), eh[lo:hi].permute(perm),
+                              out[lo:hi].permute(perm))
+
+            _lib.run_pipelined((hs_h, eh_h, bl_h), (hs, eh, bl), out_h, out, launch)
+            return out_h.numpy()
+        hs = _lib.to_device(hs_h)
+        eh = _lib.to_device(eh_h)
+        bl = _lib.to_device(bl_h)
+        out = torch.empty_like(eh)
         dbg = None
         if self.capture_hard:
             B, A, N, _ = hs.shape

@@ -35,6 +35,7 @@ class Behavior_policy:
         assert args.encoder_rnn_dim == 32 and args.num_encoder_layer == 1, "kernel K1b is built for E = 32, one layer"
         self.stack = ParamStack("beh", self.n_agents, (args.obs_shape_single, args.latent_dim), device=self.device)
         self.behavior_encoder = self.stack.nets
+        self._stage = None        # device staging buffers of the pipelined numpy entry point
 
     # ---- device path: tensors laid out [A, B, N, *] ----------------------------------
     def behavior_step(self, window, hid_io, lat_prev, lat_out):
@@ -51,17 +52,34 @@ class Behavior_policy:
     # ---- reference-compatible entry point (reference :83-123) -------------------------
     def latent_update(self, history, encoder_hidden, prev_latent):
         dev = self.device
-        hist = _lib.to_device(history)
-        B, A, N, W, o = hist.shape
+        hist_h, prev_h = _lib.as_host(history), _lib.as_host(prev_latent)
+        B, A, N, W, o = hist_h.shape
         if torch.is_tensor(encoder_hidden) and encoder_hidden.is_cuda:
             hid = encoder_hidden.detach().to(torch.float32).clone()
         else:
             hid = _lib.to_device(encoder_hidden)
-        prev = _lib.to_device(prev_latent)
+        perm = (1, 0, 2, 3)
+        if _lib.can_pipeline((hist_h, prev_h), B):
+            # page-locked inputs: copy-in, K1b and copy-out overlap chunk by chunk over the envs
+            key = (tuple(hist_h.shape), tuple(prev_h.shape))
+            if self._stage is None or self._stage[0] != key:
+                self._stage = (key, torch.empty(hist_h.shape, device=dev), torch.empty(prev_h.shape, device=dev),
+                               torch.empty(prev_h.shape, device=dev))
+            _, hist, prev, new = self._stage
+            new_h = torch.empty(prev_h.shape, dtype=torch.float32, pin_memory=True)
+
+            def launch(lo, hi):
+                self.behavior_step(hist[lo:hi].reshape(hi - lo, A, N, W * o).permute(perm), hid[lo:hi, 0].permute(perm),
+                                   prev[lo:hi].permute(perm), new[lo:hi].permute(perm))
+
+            _lib.run_pipelined((hist_h, prev_h), (hist, prev), new_h, new, launch)
+            return new_h.numpy(), hid
+        hist = _lib.to_device(hist_h)
+        prev = _lib.to_device(prev_h)
         new = torch.empty_like(prev)
-        hid_v = hid[:, 0].permute(1, 0, 2, 3)                    # [B,1,A,N,E] -> [A,B,N,E] view
-        self.behavior_step(hist.reshape(B, A, N, W * o).permute(1, 0, 2, 3), hid_v,
-                           prev.permute(1, 0, 2, 3), new.permute(1, 0, 2, 3))
+        hid_v = hid[:, 0].permute(perm)                          # [B,1,A,N,E] -> [A,B,N,E] view
+        self.behavior_step(hist.reshape(B, A, N, W * o).permute(perm), hid_v,
+                           prev.permute(perm), new.permute(perm))
         return _lib.to_host(new), hid
 
     def learn(self, batch, t_env):
