@@ -143,6 +143,14 @@ int iplan_learner_fc1_forward(const float* actor, int64_t actor_stride, const fl
                               int64_t rows, int n_agents, const float* stat, void* Wh, void* Wl,
                               float* ws, float* cc, float* Z1, void* stream);
 
+/* Same contract, same operands, same results to fp32 rounding; the product runs on the 5th-generation tensor cores
+ * (tcgen05.mma, accumulators in TMEM, operand stages filled by TMA — csrc/fc1_tc5.cu).  X must be contiguous over
+ * agents (x_stride_agent == rows * ldx); ldx % 8 == 0. */
+int iplan_learner_fc1_forward_tc5(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
+                                  const void* Xh, const void* Xl, int64_t x_stride_agent, int ldx, int feat_dim,
+                                  int64_t rows, int n_agents, const float* stat, void* Wh, void* Wl,
+                                  float* ws, float* cc, float* Z1, void* stream);
+
 typedef struct {
     const float* actor; const float* critic; int64_t actor_stride, critic_stride;   /* parameters */
     float* g_actor; float* g_critic;                                                /* gradients (train) */

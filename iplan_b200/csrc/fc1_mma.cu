@@ -402,6 +402,31 @@ extern "C" int iplan_learner_fc1_forward(const float* actor, int64_t actor_strid
 // defined in learner.cu
 namespace iplan { int launch_fc1_grad_finish(const float*, int64_t, const float*, int64_t, float*, float*, int, const float*, int, const float*, int, cudaStream_t); }
 
+namespace iplan {
+int launch_fc1_fwd_tc5(const void* Xh, const void* Xl, int ldx, int64_t rows, int n_agents, const void* Wh, const void* Wl,
+                       const float* ws, const float* cc, const float* stat, float* Z1, cudaStream_t st);   // fc1_tc5.cu
+}
+
+// Same contract as iplan_learner_fc1_forward; the product runs on tcgen05 tensor cores with TMEM accumulators and
+// TMA-fed operand stages (fc1_tc5.cu).  Requires X contiguous over agents (x_stride_agent == rows * ldx).
+extern "C" int iplan_learner_fc1_forward_tc5(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
+                                             const void* Xh, const void* Xl, int64_t x_stride_agent, int ldx, int feat_dim,
+                                             int64_t rows, int n_agents, const float* stat, void* Wh, void* Wl,
+                                             float* ws, float* cc, float* Z1, void* stream) {
+    IPLAN_REQUIRE(actor && critic && Xh && Xl && stat && Wh && Wl && ws && cc && Z1, "fc1_forward_tc5: null pointer");
+    IPLAN_REQUIRE(ldx % 8 == 0 && ldx >= feat_dim, "fc1_forward_tc5: ldx must be a multiple of 8 and >= feat_dim");
+    IPLAN_REQUIRE(rows > 0 && (int64_t)n_agents * rows < (1ll << 31), "fc1_forward_tc5: bad row count");
+    IPLAN_REQUIRE(x_stride_agent == rows * (int64_t)ldx, "fc1_forward_tc5: X must be contiguous over agents");
+    IPLAN_REQUIRE(((uintptr_t)Xh | (uintptr_t)Xl | (uintptr_t)Wh | (uintptr_t)Wl) % 16 == 0, "fc1_forward_tc5: operands must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    NetP P{actor, critic, actor_stride, critic_stride};
+    fc1_prep16_kernel<<<dim3(128, n_agents), 256, 0, st>>>(P, feat_dim, ldx, (__half*)Wh, (__half*)Wl, ws, cc);
+    int rc = launch_fc1_fwd_tc5(Xh, Xl, ldx, rows, n_agents, Wh, Wl, ws, cc, stat, Z1, st);
+    if (rc) return rc;
+    count_launch(2);
+    return check_launch("fc1_forward_tc5");
+}
+
 extern "C" int iplan_learner_fc1_backward(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
                                           float* g_actor, float* g_critic,
                                           const void* Xh, const void* Xl, int64_t x_stride_agent, int ldx, int feat_dim,

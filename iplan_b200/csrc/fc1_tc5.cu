@@ -1,0 +1,276 @@
+// fc1 forward of the IPPO update on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+//   Z1[a][r][0..128) = rstd_r * (X_a[r] . W'_a[n] - mean_r * ws[n]) + cc[n]
+//
+// (feature LayerNorm + fc1 of the actor, n < 64, and the critic, n >= 64, in ONE pass over the packed
+// episode rows; reference utils/mappo_utils/mlp.py:50-56, called from learners/ippo_learner.py:267-288.)
+// Same operands and the same arithmetic contract as fc1_fwd_mma_kernel (fc1_mma.cu): X and W' as f16
+// hi + lo copies, products hi*hi + lo*hi + hi*lo accumulated in fp32, i.e. fp32-class accuracy.
+//
+// One CTA = one 128-row tile of one agent, 6 warps with fixed roles:
+//   warp 0      TMA producer: per 64-wide k-block four 128x64 f16 boxes (Xh, Xl, W'h, W'l; 64 KB) land in a
+//               128B-swizzled K-major stage, completion counted on the stage's `full` mbarrier
+//   warp 1      TMEM owner + MMA issuer: one lane issues 12 tcgen05.mma (M=128, N=128, K=16) per k-block
+//               into one of two 128-column TMEM accumulators, then tcgen05.commit -> `empty` (stage free)
+//               and -> `tfull` (accumulator ready)
+//   warps 2..5  drain: tcgen05.ld the finished accumulator (thread = one row, 128 columns) and add it to a
+//               running fp32 sum in registers.  The tensor core's own fp32 accumulation truncates, so a
+//               chain is kept to the 12 MMAs of one k-block and the 39 partial sums are added in fp32 RN
+//               on the CUDA cores (same policy as the mma.sync kernels); then the LayerNorm fold + store.
+// The drain of k-block i overlaps the MMAs of k-block i+1 (two accumulators) and the TMA of i+2, i+3.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace iplan {
+
+constexpr int T5_BM = 128, T5_BN = 128, T5_BK = 64, T5_STAGES = 3;
+constexpr int T5_THREADS = 192;
+constexpr int T5_TILE_BYTES = T5_BM * T5_BK * 2;               // 16 KB: one 128 x 64 f16 operand tile
+constexpr int T5_STAGE_BYTES = 4 * T5_TILE_BYTES;              // Xh, Xl, Wh, Wl
+constexpr size_t T5_SMEM = (size_t)T5_STAGES * T5_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int T5_TMEM_COLS = 256;                              // two 128-column fp32 accumulators
+
+// ---- raw PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] . B[smem]^T, f16 inputs, f32 accumulate; issued by ONE thread for the CTA
+__device__ __forceinline__ void tc5_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// the mbarrier is signalled when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void tc5_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread = TMEM lane (row), v[j] = column j
+__device__ __forceinline__ void tc5_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// K-major operand tile, 128B swizzle (what TMA SWIZZLE_128B writes for a 64 x f16 box row): rows of 128 B,
+// 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t tc5_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address, 16-byte units          bits [0,14)
+    d |= (uint64_t)0 << 16;                                 // leading byte offset (unused: K fits one swizzle atom)
+    d |= (uint64_t)(1024 >> 4) << 32;                       // stride byte offset: 8 rows x 128 B    bits [32,46)
+    d |= (uint64_t)1 << 46;                                 // descriptor version                    bits [46,48)
+    d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B                          bits [61,64)
+    return d;
+}
+// kind::f16: D = F32 (bit 4), A = B = F16 (0), both K-major (0), N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t T5_IDESC = (1u << 4) | ((uint32_t)(T5_BN >> 3) << 17) | ((uint32_t)(T5_BM >> 4) << 24);
+
+struct Tc5Maps { CUtensorMap xh, xl, wh, wl; };
+
+__global__ void __launch_bounds__(T5_THREADS, 1) fc1_fwd_tc5_kernel(
+    const __grid_constant__ Tc5Maps maps, int rows, int ldx,
+    const float* __restrict__ ws, const float* __restrict__ cc, const float* __restrict__ stat, float* __restrict__ Z1) {
+    extern __shared__ unsigned char t5_raw[];
+    const int a = blockIdx.y, m0 = blockIdx.x * T5_BM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t base = (smem_u32(t5_raw) + 1023u) & ~1023u;            // swizzle atoms are 1024-byte aligned
+    const uint32_t bars = base + T5_STAGES * T5_STAGE_BYTES;              // full[3] | empty[3] | tfull[2] | tempty[2] | tmem ptr
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (T5_STAGES + s); };
+    auto tfull = [&](int b) { return bars + 8u * (2 * T5_STAGES + b); };
+    auto tempty = [&](int b) { return bars + 8u * (2 * T5_STAGES + 2 + b); };
+    const uint32_t tmem_slot = bars + 8u * (2 * T5_STAGES + 4);
+    const int nkb = (ldx + T5_BK - 1) / T5_BK;                     // a ragged last k-block is zero-filled by TMA
+
+    if (tid == 0) {
+        for (int s = 0; s < T5_STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tfull(b), 1); mbar_init(tempty(b), 4); }    // 4 drain warps
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(T5_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc5_fence_before();
+    __syncthreads();
+    tc5_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % T5_STAGES, it = kb / T5_STAGES;
+                if (it > 0) mbar_wait(empty(s), (it - 1) & 1);
+                mbar_expect_tx(full(s), T5_STAGE_BYTES);
+                const uint32_t dst = base + s * T5_STAGE_BYTES;
+                tma_load_2d(dst + 0 * T5_TILE_BYTES, &maps.xh, kb * T5_BK, a * rows + m0, full(s));
+                tma_load_2d(dst + 1 * T5_TILE_BYTES, &maps.xl, kb * T5_BK, a * rows + m0, full(s));
+                tma_load_2d(dst + 2 * T5_TILE_BYTES, &maps.wh, kb * T5_BK, a * T5_BN, full(s));
+                tma_load_2d(dst + 3 * T5_TILE_BYTES, &maps.wl, kb * T5_BK, a * T5_BN, full(s));
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % T5_STAGES, buf = kb & 1, ib = kb >> 1;
+                if (ib > 0) mbar_wait(tempty(buf), (ib - 1) & 1);          // the drain warps have emptied this accumulator
+                mbar_wait(full(s), (kb / T5_STAGES) & 1);
+                tc5_fence_after();
+                const uint32_t st = base + s * T5_STAGE_BYTES;
+                const uint64_t ah = tc5_smem_desc(st + 0 * T5_TILE_BYTES), al = tc5_smem_desc(st + 1 * T5_TILE_BYTES);
+                const uint64_t bh = tc5_smem_desc(st + 2 * T5_TILE_BYTES), bl = tc5_smem_desc(st + 3 * T5_TILE_BYTES);
+                const uint32_t d = tmem_base + buf * T5_BN;
+#pragma unroll
+                for (int k = 0; k < T5_BK / 16; ++k) {                       // 16 f16 = 32 B = 2 descriptor units along K
+                    tc5_mma(d, ah + 2 * k, bh + 2 * k, T5_IDESC, k > 0);
+                    tc5_mma(d, al + 2 * k, bh + 2 * k, T5_IDESC, 1);
+                    tc5_mma(d, ah + 2 * k, bl + 2 * k, T5_IDESC, 1);
+                }
+                tc5_commit(empty(s));                                      // stage reusable once these MMAs have read it
+                tc5_commit(tfull(buf));                                    // accumulator complete
+            }
+        }
+    } else {
+        // ===== drain warps: TMEM lane group = warp % 4 =====
+        const int lg = warp & 3;
+        const int r = m0 + 32 * lg + lane;                                  // this thread's row
+        float acc[T5_BN];
+#pragma unroll
+        for (int j = 0; j < T5_BN; ++j) acc[j] = 0.0f;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int buf = kb & 1, ib = kb >> 1;
+            mbar_wait(tfull(buf), ib & 1);
+            tc5_fence_after();
+            const uint32_t t = tmem_base + ((uint32_t)(32 * lg) << 16) + buf * T5_BN;
+#pragma unroll
+            for (int q = 0; q < T5_BN / 32; ++q) {
+                float v[32];
+                tc5_ld32(t + 32 * q, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[32 * q + j] += v[j];
+            }
+            tc5_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty(buf));
+        }
+        if (r < rows) {                                                     // epilogue: fold the LayerNorm statistics
+            const float mean = stat[((int64_t)a * rows + r) * 2], rstd = stat[((int64_t)a * rows + r) * 2 + 1];
+            float4* zr = reinterpret_cast<float4*>(Z1 + ((int64_t)a * rows + r) * T5_BN);
+            const float4* ws4 = reinterpret_cast<const float4*>(ws + a * T5_BN);
+            const float4* cc4 = reinterpret_cast<const float4*>(cc + a * T5_BN);
+#pragma unroll
+            for (int j = 0; j < T5_BN / 4; ++j) {
+                const float4 w = __ldg(ws4 + j), c = __ldg(cc4 + j);
+                float4 o;
+                o.x = rstd * (acc[4 * j + 0] - mean * w.x) + c.x;
+                o.y = rstd * (acc[4 * j + 1] - mean * w.y) + c.y;
+                o.z = rstd * (acc[4 * j + 2] - mean * w.z) + c.z;
+                o.w = rstd * (acc[4 * j + 3] - mean * w.w) + c.w;
+                zr[j] = o;
+            }
+        }
+    }
+    tc5_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc5_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(T5_TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host: tensor maps ----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [n_rows][ldx] f16 row-major, box = 64 columns x 128 rows, 128B swizzle
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t n_rows, uint64_t ldx) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) { set_error("fc1_forward_tc5: cuTensorMapEncodeTiled not available from the driver"); return -2; }
+    const cuuint64_t gdim[2] = {ldx, n_rows};
+    const cuuint64_t gstr[1] = {ldx * sizeof(__half)};
+    const cuuint32_t box[2] = {(cuuint32_t)T5_BK, (cuuint32_t)T5_BM};
+    const cuuint32_t est[2] = {1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, est,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("fc1_forward_tc5: cuTensorMapEncodeTiled failed (%d)", (int)r); return -3; }
+    return 0;
+}
+
+int launch_fc1_fwd_tc5(const void* Xh, const void* Xl, int ldx, int64_t rows, int n_agents, const void* Wh, const void* Wl,
+                       const float* ws, const float* cc, const float* stat, float* Z1, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fc1_fwd_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T5_SMEM);
+        if (e != cudaSuccess) { set_error("fc1_forward_tc5: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    // the operand buffers live for a whole train(): encode the four maps once per (pointers, shape)
+    static Tc5Maps maps;
+    static const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
+    static int64_t key_rows = -1; static int key_ldx = -1, key_agents = -1;
+    if (key[0] != Xh || key[1] != Xl || key[2] != Wh || key[3] != Wl || key_rows != rows || key_ldx != ldx || key_agents != n_agents) {
+        int rc;
+        if ((rc = make_map(&maps.xh, Xh, (uint64_t)n_agents * rows, ldx))) return rc;
+        if ((rc = make_map(&maps.xl, Xl, (uint64_t)n_agents * rows, ldx))) return rc;
+        if ((rc = make_map(&maps.wh, Wh, (uint64_t)n_agents * T5_BN, ldx))) return rc;
+        if ((rc = make_map(&maps.wl, Wl, (uint64_t)n_agents * T5_BN, ldx))) return rc;
+        key[0] = Xh; key[1] = Xl; key[2] = Wh; key[3] = Wl; key_rows = rows; key_ldx = ldx; key_agents = n_agents;
+    }
+    dim3 grid((unsigned)((rows + T5_BM - 1) / T5_BM), n_agents);
+    fc1_fwd_tc5_kernel<<<grid, T5_THREADS, T5_SMEM, st>>>(maps, (int)rows, ldx, ws, cc, stat, Z1);
+    return 0;
+}
+
+}  // namespace iplan

@@ -47,6 +47,7 @@ constexpr int REC_WARPS = REC_THREADS / 32;
 constexpr int DLP = IPLAN_MAX_SLOTS;       // row pitch of the dl scratch: dl[dir][s][DLP]
 constexpr int IN_MAX = 16;     // obs_dim + latent_dim upper bound
 constexpr int NT_G = G3 / 8;   // 12 n-tiles of 8 gate columns
+constexpr int PP = G3 + 8;     // row pitch of the ego projections P: rows of different chains fall in different banks
 constexpr int KB_H = H / 16;   // 2 k-blocks of 16 hidden units
 
 struct GatArgs {
@@ -59,7 +60,9 @@ struct GatArgs {
 };
 
 __host__ __device__ inline size_t rec_smem_floats(int N) {
-    return (size_t)N * IN_MAX + (size_t)N * H + 2 * (size_t)N * G3 + 4 * NT_G * KB_H * 32 + 64 + 32;
+    // s_P | s_Q | union { s_x, s_enc  (prologue) ; W_hh fragments, b_hn, logit weights (recurrence) }
+    const size_t pro = (size_t)N * IN_MAX + (size_t)H * IN_MAX + (size_t)N * H, rec = 4 * NT_G * KB_H * 32 + 64 + 32;
+    return (size_t)N * PP + (size_t)N * G3 + (pro > rec ? pro : rec);
 }
 constexpr int QP = H + 8;       // q / k row pitch (floats): 8-byte aligned, conflict-free fragment reads
 constexpr int WP = 64 + 8;      // attention-weight / V^T row pitch: K = 64 neighbour columns, zero padded
@@ -159,15 +162,17 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 // All warps of the CTA cooperate: one task = one 16-node x 8-column tile = 3 KB MMAs (f16 hi/lo
 // split, see header).  W is read as B fragments: a quad reads 32 contiguous bytes of one weight row, so
 // every sector fetched is fully used.  TRANS_OUT stores out[c][n] instead (row pitch ldout).
-template <int NW, int KB = KB_H, bool TRANS_OUT = false>
+struct EpiNone { __device__ __forceinline__ float operator()(int, float v) const { return v; } };
+
+template <int NW, int KB = KB_H, bool TRANS_OUT = false, class Epi = EpiNone>
 __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, const float* __restrict__ Wg, int ldw,
                                             const float* __restrict__ bias, int cols, float* out, int ldout, bool relu,
-                                            int warp, int lane) {
+                                            int warp, int lane, Epi epi = Epi()) {
     const int gq = lane >> 2, tq = lane & 3;
     const int mtiles = (N + 15) >> 4, ntiles = cols >> 3;
     const int mh = (mtiles + 1) >> 1;                 // a task = one n-tile x one half of the m-tiles
     const int ntask = ntiles * 2;
-    constexpr int DT = KB <= 2 ? 3 : 1;               // tasks whose weight fragments are fetched together
+    constexpr int DT = KB == 1 ? 4 : (KB == 2 ? 6 : 1);   // tasks whose weight fragments are fetched together
     for (int base = warp; base < ntask; base += NW * DT) {
         float2 wv[DT][2 * KB];
 #pragma unroll
@@ -214,6 +219,7 @@ __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, co
                     mma16816(acc, ahi, bl[kb][0], bl[kb][1], acc);
                 }
                 if (relu) { acc[0] = fmaxf(acc[0], 0.f); acc[1] = fmaxf(acc[1], 0.f); acc[2] = fmaxf(acc[2], 0.f); acc[3] = fmaxf(acc[3], 0.f); }
+                acc[0] = epi(c0, acc[0]); acc[1] = epi(c0 + 1, acc[1]); acc[2] = epi(c0, acc[2]); acc[3] = epi(c0 + 1, acc[3]);
                 if (TRANS_OUT) {
                     if (r0 < N) { out[c0 * ldout + r0] = acc[0]; out[(c0 + 1) * ldout + r0] = acc[1]; }
                     if (r1 < N) { out[c0 * ldout + r1] = acc[2]; out[(c0 + 1) * ldout + r1] = acc[3]; }
@@ -226,31 +232,32 @@ __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, co
     }
 }
 
-// phases 0 + 1, shared by both kernels: gather x = [history | behaviour latent], enc = ReLU(W_e x + b_e)
+// phases 0 + 1, shared by both kernels: gather x = [history | behaviour latent] (zero padded to IN_MAX columns),
+// enc = ReLU(W_e x + b_e) as one N x 32 x 16 tensor-core product.  s_we: [H][IN_MAX] staging of W_e (zero padded).
 template <int NT>
 __device__ __forceinline__ void gat_encode(const GatArgs& a, const float* __restrict__ W, const GatLayout& L,
-                                           int b, int ag, float* s_x, float* s_enc) {
+                                           int b, int ag, float* s_x, float* s_we, float* s_enc) {
     const int N = a.n_slots, in_dim = a.obs_dim + a.latent_dim, tid = threadIdx.x;
     const float* hist = a.hist.ptr + ag * a.hist.stride_agent + b * a.hist.stride_env;
     const float* beh = a.beh.ptr + ag * a.beh.stride_agent + b * a.beh.stride_env;
-    for (int idx = tid; idx < N * in_dim; idx += NT) {
-        const int n = idx / in_dim, c = idx - n * in_dim;
-        s_x[n * IN_MAX + c] = (c < a.obs_dim) ? hist[n * a.hist.stride_slot + c]
-                                              : beh[n * a.beh.stride_slot + (c - a.obs_dim)];
+    for (int idx = tid; idx < N * IN_MAX; idx += NT) {
+        const int n = idx / IN_MAX, c = idx - n * IN_MAX;
+        float v = 0.0f;
+        if (c < a.obs_dim) v = hist[n * a.hist.stride_slot + c];
+        else if (c < in_dim) v = beh[n * a.beh.stride_slot + (c - a.obs_dim)];
+        s_x[idx] = v;
+    }
+    for (int idx = tid; idx < H * IN_MAX; idx += NT) {
+        const int c = idx / IN_MAX, k = idx - c * IN_MAX;
+        s_we[idx] = k < in_dim ? W[L.enc_w + c * in_dim + k] : 0.0f;
     }
     __syncthreads();
-    for (int idx = tid; idx < N * H; idx += NT) {
-        const int n = idx >> 5, c = idx & 31;
-        float acc = W[L.enc_b + c];
-        const float* w = W + L.enc_w + c * in_dim;
-        for (int k = 0; k < in_dim; ++k) acc = fmaf(w[k], s_x[n * IN_MAX + k], acc);
-        s_enc[idx] = fmaxf(acc, 0.0f);
-    }
+    dense32_mma<NT / 32, 1>(s_x, IN_MAX, N, s_we, IN_MAX, W + L.enc_b, H, s_enc, H, true, tid >> 5, tid & 31);
     __syncthreads();
 }
 
 // ---- kernel 1 of 2: the N GRU chains of one direction for one (env, agent-net) -------------
-__global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
+__global__ void __launch_bounds__(REC_THREADS, 4) gat_recur_kernel(GatArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int b = blockIdx.x, ag = blockIdx.y, dir = blockIdx.z;
     const int N = a.n_slots, NM1 = N - 1;
@@ -259,21 +266,26 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
     const float* __restrict__ W = a.params + (int64_t)ag * a.param_stride;
     const GatLayout L = gat_layout(in_dim);
 
-    float* s_x = smem;                                  // [N][IN_MAX]
-    float* s_enc = s_x + N * IN_MAX;                    // [N][H]
-    float* s_P = s_enc + N * H;                         // [N][96]  ego part + b_ih (+ b_hh for r|z), gate-scaled
-    float* s_Q = s_P + N * G3;                          // [N][96]  neighbour part, gate-scaled
+    float* s_P = smem;                                  // [N][PP]  ego part + b_ih (+ b_hh for r|z), gate-scaled
+    float* s_Q = s_P + N * PP;                          // [N][96]  neighbour part, gate-scaled
+    float* s_x = s_Q + N * G3;                          // [N][IN_MAX]   } prologue only; the W_hh fragments below
+    float* s_we = s_x + N * IN_MAX;                     // [H][IN_MAX]   } take their place for the recurrence
+    float* s_enc = s_we + H * IN_MAX;                   // [N][H]        }
     uint4* s_w4 = reinterpret_cast<uint4*>(s_Q + N * G3);   // [12][2][32] W_hh B fragments {hi0, hi1, lo0, lo1}
     float4* s_bn = reinterpret_cast<float4*>(s_w4 + NT_G * KB_H * 32);   // [4 t4][4 tq] b_hn pair twice = the n tile's initial accumulator
     float2* s_lw = reinterpret_cast<float2*>(s_bn + 16);                 // [4 t4][4 tq] logit-difference weight pair
 
-    gat_encode<REC_THREADS>(a, W, L, b, ag, s_x, s_enc);
+    gat_encode<REC_THREADS>(a, W, L, b, ag, s_x, s_we, s_enc);
 
     // ---- phase 2: factored input projections P (ego, + b_ih) and Q (neighbour) ------
     const float* wih = W + (dir ? L.wih_r : L.wih_f);
     const float* bhh = W + (dir ? L.bhh_r : L.bhh_f);
-    dense32_mma<REC_WARPS>(s_enc, H, N, wih, 2 * H, W + (dir ? L.bih_r : L.bih_f), G3, s_P, G3, false, warp, lane);
-    dense32_mma<REC_WARPS>(s_enc, H, N, wih + H, 2 * H, nullptr, G3, s_Q, G3, false, warp, lane);
+    // the gate-activation scale (and b_hh of r|z) is folded into P and Q as they are produced
+    auto epi_p = [bhh](int c, float v) { return c < 2 * H ? K_RZ * (v + bhh[c]) : K_N * v; };
+    auto epi_q = [](int c, float v) { return (c < 2 * H ? K_RZ : K_N) * v; };
+    dense32_mma<REC_WARPS, KB_H, false>(s_enc, H, N, wih, 2 * H, W + (dir ? L.bih_r : L.bih_f), G3, s_P, PP, false, warp, lane, epi_p);
+    dense32_mma<REC_WARPS, KB_H, false>(s_enc, H, N, wih + H, 2 * H, nullptr, G3, s_Q, G3, false, warp, lane, epi_q);
+    __syncthreads();                                    // s_enc is dead from here: its space takes the W_hh fragments
     // W_hh B fragments (mma.m16n8k16 "col" operand: b0 = (k=2t,2t+1 ; n=g), b1 = (k=2t+8,2t+9 ; n=g)),
     // B[k][n] = W_hh[gate n][hidden k], gate-activation scale folded in, f16 hi and lo parts.
     {
@@ -298,13 +310,6 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
         }
     }
     __syncthreads();
-    for (int idx = tid; idx < N * G3; idx += REC_THREADS) {          // fold gate scale (and b_hh of r|z) into P, Q
-        const int col = idx % G3;
-        if (col < 2 * H) { s_P[idx] = K_RZ * (s_P[idx] + bhh[col]); s_Q[idx] *= K_RZ; }
-        else { s_P[idx] *= K_N; s_Q[idx] *= K_N; }
-    }
-    __syncthreads();
-
     // ---- phase 3: the chains on the tensor cores; warp = m-tile of 16 egos -----------
     const int gq = lane >> 2, tq = lane & 3, mt = warp;
     if (mt * 16 >= N) return;                                           // warp-uniform; no barrier follows
@@ -315,20 +320,11 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
     const uint4* w4 = s_w4 + lane;
     // per-chain constants in accumulator-fragment layout: element e of tile nt is
     // (row e<2 ? row0 : row1, col 8*nt + 2*tq + (e&1))
-    float cst[8][4];
-    f32x2 pn01[4], pn23[4];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        const float2 p0 = *reinterpret_cast<const float2*>(s_P + i0 * G3 + 8 * nt + 2 * tq);
-        const float2 p1 = *reinterpret_cast<const float2*>(s_P + i1 * G3 + 8 * nt + 2 * tq);
-        cst[nt][0] = p0.x; cst[nt][1] = p0.y; cst[nt][2] = p1.x; cst[nt][3] = p1.y;     // r | z : P + b_hh
-    }
-#pragma unroll
-    for (int t4 = 0; t4 < 4; ++t4) {
-        const float2 p0 = *reinterpret_cast<const float2*>(s_P + i0 * G3 + 2 * H + 8 * t4 + 2 * tq);
-        const float2 p1 = *reinterpret_cast<const float2*>(s_P + i1 * G3 + 2 * H + 8 * t4 + 2 * tq);
-        pn01[t4] = pk2(p0.x, p0.y); pn23[t4] = pk2(p1.x, p1.y);
-    }
+    // per-chain constants (ego part of the input projection) stay in shared memory: element e of tile nt is
+    // (row e<2 ? row0 : row1, col 8*nt + 2*tq + (e&1)); reading them per step keeps the kernel at 128 registers
+    // (4 CTAs = 16 warps per SM)
+    const float* p0row = s_P + i0 * PP + 2 * tq;
+    const float* p1row = s_P + i1 * PP + 2 * tq;
     // hidden state: h01[t4] = (row0; cols 8 t4 + 2 tq, +1), h23[t4] = the same columns of row1
     f32x2 h01[4], h23[4];
 #pragma unroll
@@ -365,7 +361,12 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
 #pragma unroll
             for (int gi = 0; gi < 3; ++gi) {
                 float c0[4];
-                if (gi < 2) { const int nt = 4 * gi + t4; c0[0] = cst[nt][0]; c0[1] = cst[nt][1]; c0[2] = cst[nt][2]; c0[3] = cst[nt][3]; }
+                if (gi < 2) {
+                    const int nt = 4 * gi + t4;
+                    const float2 c01 = *reinterpret_cast<const float2*>(p0row + 8 * nt);
+                    const float2 c23 = *reinterpret_cast<const float2*>(p1row + 8 * nt);
+                    c0[0] = c01.x; c0[1] = c01.y; c0[2] = c23.x; c0[3] = c23.y;
+                }
                 else { c0[0] = bn.x; c0[1] = bn.y; c0[2] = bn.z; c0[3] = bn.w; }
                 mma16816(acc[gi], ahi[0], w[gi][0].x, w[gi][0].y, c0);
             }
@@ -385,8 +386,8 @@ __global__ void __launch_bounds__(REC_THREADS, 3) gat_recur_kernel(GatArgs a) {
                          add2(pk2(acc[0][2], acc[0][3]), lds64(q1 + 8 * t4)), r01, r23);      // r = 1 / (1 + 2^x')
             sigmoid4_den(add2(pk2(acc[1][0], acc[1][1]), lds64(q0 + H + 8 * t4)),
                          add2(pk2(acc[1][2], acc[1][3]), lds64(q1 + H + 8 * t4)), z01, z23);
-            sigmoid4_den(fma2(r01, pk2(acc[2][0], acc[2][1]), add2(pn01[t4], lds64(q0 + 2 * H + 8 * t4))),
-                         fma2(r23, pk2(acc[2][2], acc[2][3]), add2(pn23[t4], lds64(q1 + 2 * H + 8 * t4))), i01, i23);
+            sigmoid4_den(fma2(r01, pk2(acc[2][0], acc[2][1]), add2(lds64(p0row + 2 * H + 8 * t4), lds64(q0 + 2 * H + 8 * t4))),
+                         fma2(r23, pk2(acc[2][2], acc[2][3]), add2(lds64(p1row + 2 * H + 8 * t4), lds64(q1 + 2 * H + 8 * t4))), i01, i23);
             const f32x2 n01 = fma2(mtwo2, i01, one2), n23 = fma2(mtwo2, i23, one2);   // tanh = 1 - 2 / (1 + 2^x')
             h01[t4] = fma2(z01, sub2(h01[t4], n01), n01);                   // (1 - z) n + z h
             h23[t4] = fma2(z23, sub2(h23[t4], n23), n23);
@@ -420,7 +421,8 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
     const GatLayout L = gat_layout(in_dim);
 
     float* s_vt = smem;                                 // [H][WP]  V^T: s_vt[c][j] = v_j[c], columns >= N zero
-    float* s_x = smem;                                  // [N][IN_MAX] (dead after the encode; N*IN_MAX <= H*WP)
+    float* s_x = smem;                                  // [N][IN_MAX] (dead after the encode; (N+H)*IN_MAX <= H*WP)
+    float* s_we = s_x + N * IN_MAX;                     // [H][IN_MAX]  likewise
     float* s_enc = s_vt + H * WP;                       // [N][H]
     float* s_xa = s_enc + N * H;                        // [N][H] aggregated messages
     float* s_hp = s_xa + N * H;                         // [N][H] h_prev
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
     const float* hprev = a.hprev.ptr + ag * a.hprev.stride_agent + b * a.hprev.stride_env;
     float* outp = a.out.ptr + ag * a.out.stride_agent + b * a.out.stride_env;
 
-    gat_encode<GAT_THREADS>(a, W, L, b, ag, s_x, s_enc);
+    gat_encode<GAT_THREADS>(a, W, L, b, ag, s_x, s_we, s_enc);
 
     // ---- phase 4: q, k, v^T; stage h_prev and the recurrence kernel's dl[dir][s][i] ------
     for (int idx = tid; idx < H * WP; idx += GAT_THREADS) s_vt[idx] = 0.0f;       // s_x is dead: gat_encode ends with a barrier
