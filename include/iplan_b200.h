@@ -188,6 +188,15 @@ int iplan_learner_fc1_backward(const float* actor, int64_t actor_stride, const f
                                const float* dZ1, void* Dh, void* Dl, float* gscale,
                                const float* SM, float* G, void* stream);
 
+/* Same contract and results to fp32 rounding as iplan_learner_fc1_backward; the product runs on tcgen05 tensor cores
+ * (csrc/fc1_tc5.cu).  X must be contiguous over agents (x_stride_agent == rows * ldx). */
+int iplan_learner_fc1_backward_tc5(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
+                                   float* g_actor, float* g_critic,
+                                   const void* Xh, const void* Xl, int64_t x_stride_agent, int ldx, int feat_dim,
+                                   int64_t rows, int n_agents,
+                                   const float* dZ1, void* Dh, void* Dl, float* gscale,
+                                   const float* SM, float* G, void* stream);
+
 /* K2a: GAE backward scan (compute_returns :344-365), raw advantages zeroed where the agent is
  * dead (:273-277) and their moments: moments [A][4] = (sum, sum of squares, count, sum of
  * alive over the training rows) in double — all-reduce them across ranks, then finalise:

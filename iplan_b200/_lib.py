@@ -50,6 +50,8 @@ _SIGNATURES = {
     "iplan_learner_tail": (_i, [_p, _i, _p]),
     "iplan_learner_fc1_backward": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i, _i, _i64, _i,
                                         _p, _p, _p, _p, _p, _p, _p]),
+    "iplan_learner_fc1_backward_tc5": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _i, _i, _i64, _i,
+                                            _p, _p, _p, _p, _p, _p, _p]),
     "iplan_learner_gae": (_i, [_p, _p, _p, _f, _f, _i, _i, _i, _i, _p, _p, _p, _p]),
     "iplan_learner_adv_finalize": (_i, [_p, C.c_double, _p, _i, _p]),
     "iplan_learner_adam": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i64, _i, _f, _f, _f, _f, _i, _f, _f, _p, _i, _p]),

@@ -405,6 +405,8 @@ namespace iplan { int launch_fc1_grad_finish(const float*, int64_t, const float*
 namespace iplan {
 int launch_fc1_fwd_tc5(const void* Xh, const void* Xl, int ldx, int64_t rows, int n_agents, const void* Wh, const void* Wl,
                        const float* ws, const float* cc, const float* stat, float* Z1, cudaStream_t st);   // fc1_tc5.cu
+int launch_fc1_bwd_tc5(const void* Xh, const void* Xl, int ldx, int64_t rows, int n_agents, const void* Dh, const void* Dl,
+                       const float* unscale, float* G, cudaStream_t st);                                     // fc1_tc5.cu
 }
 
 // Same contract as iplan_learner_fc1_forward; the product runs on tcgen05 tensor cores with TMEM accumulators and
@@ -456,6 +458,34 @@ extern "C" int iplan_learner_fc1_backward(const float* actor, int64_t actor_stri
                                                            (const __half*)Dh, (const __half*)Dl, unscale, G);
     count_launch(3);
     int rc = check_launch("fc1_backward");
+    if (rc) return rc;
+    return launch_fc1_grad_finish(actor, actor_stride, critic, critic_stride, g_actor, g_critic, feat_dim, G, ldx, SM, n_agents, st);
+}
+
+// Same contract as iplan_learner_fc1_backward; the product G = dZ1^T X runs on tcgen05 (fc1_tc5.cu).
+// Requires X contiguous over agents (x_stride_agent == rows * ldx).
+extern "C" int iplan_learner_fc1_backward_tc5(const float* actor, int64_t actor_stride, const float* critic, int64_t critic_stride,
+                                              float* g_actor, float* g_critic,
+                                              const void* Xh, const void* Xl, int64_t x_stride_agent, int ldx, int feat_dim,
+                                              int64_t rows, int n_agents,
+                                              const float* dZ1, void* Dh, void* Dl, float* gscale /* [A][2] */,
+                                              const float* SM, float* G, void* stream) {
+    IPLAN_REQUIRE(actor && critic && g_actor && g_critic && Xh && Xl && dZ1 && Dh && Dl && gscale && SM && G, "fc1_backward_tc5: null pointer");
+    IPLAN_REQUIRE(ldx % 8 == 0 && rows > 0 && rows < (1ll << 31), "fc1_backward_tc5: bad sizes");
+    IPLAN_REQUIRE(x_stride_agent == rows * (int64_t)ldx, "fc1_backward_tc5: X must be contiguous over agents");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(G, 0, sizeof(float) * (size_t)n_agents * 128 * ldx, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gscale, 0, sizeof(float) * 2 * n_agents, st);
+    if (e != cudaSuccess) { set_error("fc1_backward_tc5: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    unsigned* amax = reinterpret_cast<unsigned*>(gscale);          // [A] max bits | [A] 2^-e
+    float* unscale = gscale + n_agents;
+    const int64_t npa = rows * 128;
+    absmax_kernel<<<dim3(148, n_agents), 256, 0, st>>>(dZ1, npa, amax);
+    dz_split_kernel<<<dim3(148 * 2, n_agents), 256, 0, st>>>(dZ1, npa, amax, (__half*)Dh, (__half*)Dl, unscale);
+    int rc = launch_fc1_bwd_tc5(Xh, Xl, ldx, rows, n_agents, Dh, Dl, unscale, G, st);
+    if (rc) return rc;
+    count_launch(3);
+    rc = check_launch("fc1_backward_tc5");
     if (rc) return rc;
     return launch_fc1_grad_finish(actor, actor_stride, critic, critic_stride, g_actor, g_critic, feat_dim, G, ldx, SM, n_agents, st);
 }

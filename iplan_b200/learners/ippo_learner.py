@@ -291,7 +291,7 @@ class IPPOLearner:
             ga.zero_(); gc.zero_(); w["SM"].zero_()
             self._forward(w, ctx, X, A, rows, Fp, F, actor, critic, train=True)
             self._mark("fc1_bwd")
-            _lib.check(lib.iplan_learner_fc1_backward(
+            _lib.check(lib.iplan_learner_fc1_backward_tc5(     # tcgen05 / TMEM / TMA product (csrc/fc1_tc5.cu)
                 _lib.ptr(actor), self.stacks["actor"].stride(), _lib.ptr(critic), self.stacks["critic"].stride(),
                 _lib.ptr(ga), _lib.ptr(gc), _lib.ptr(w["Xh"]), _lib.ptr(w["Xl"]), w["Xh"].stride(0), Fp, F, rows, A,
                 _lib.ptr(w["Z1"]), _lib.ptr(w["Dh"]), _lib.ptr(w["Dl"]), _lib.ptr(w["gscale"]),

@@ -62,7 +62,35 @@ def run(A, rows, F, n_act=5, reps=5):
     print(f"A={A} rows={rows} F={F}: mma {out['iplan_learner_fc1_forward'][1]:.3f} ms, tc5 {out['iplan_learner_fc1_forward_tc5'][1]:.3f} ms; "
           f"max|mma - tc5| = {d:.3e}; max|mma - fp64| = {(za.double() - zr).abs().max().item():.3e}; "
           f"max|tc5 - fp64| = {(zt.double() - zr).abs().max().item():.3e}; nan in tc5: {bool(torch.isnan(zt).any())}", flush=True)
-    return d
+    # ---- backward: G = dZ1^T X and the fc1.weight / feature_norm gradients -------------------------------
+    dZ = torch.randn(A, rows, 128, device=dev) * 1e-3
+    SM = torch.randn(A, 2, 128, device=dev) * 1e-3
+    Dh, Dl, gs, G = hz(A, rows, 128), hz(A, rows, 128), z(2 * A), z(A, 128, Fp)
+    res = {}
+    for name in ("iplan_learner_fc1_backward", "iplan_learner_fc1_backward_tc5"):
+        fn = getattr(lib, name)
+        ga, gc = torch.zeros_like(actor.flat), torch.zeros_like(critic.flat)
+        call = lambda: _lib.check(fn(P(actor.flat), actor.stride(), P(critic.flat), critic.stride(), P(ga), P(gc), P(Xh), P(Xl),
+                                     Xh.stride(0), Fp, F, rows, A, P(dZ), P(Dh), P(Dl), P(gs), P(SM), P(G), st), name)
+        call()
+        torch.cuda.synchronize()
+        g_first = (G.clone(), ga.clone(), gc.clone())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = (g_first, e0.elapsed_time(e1) / reps)
+    Gref = torch.einsum("ark,arf->akf", dZ.double(), X.double())
+    (Gm, gam, gcm), tm = res["iplan_learner_fc1_backward"]
+    (Gt, gat, gct), tt = res["iplan_learner_fc1_backward_tc5"]
+    scale = Gref.abs().max().item()
+    db = max((Gm - Gt).abs().max().item(), (gam - gat).abs().max().item(), (gcm - gct).abs().max().item()) / scale
+    print(f"   backward (all launches): mma {tm:.3f} ms, tc5 {tt:.3f} ms; max rel|mma - tc5| = {db:.3e}; "
+          f"max rel|mma - fp64| = {(Gm.double() - Gref).abs().max().item() / scale:.3e}; "
+          f"max rel|tc5 - fp64| = {(Gt.double() - Gref).abs().max().item() / scale:.3e}; nan: {bool(torch.isnan(Gt).any())}", flush=True)
+    return max(d, db)
 
 
 if __name__ == "__main__":
