@@ -102,17 +102,31 @@ class ClockSampler:
 
 
 def gat_algorithmic(B, A, N, o, L, H=32):
-    """Algorithmic FLOPs and HBM bytes of ONE K1 launch."""
+    """Algorithmic FLOPs and HBM bytes of ONE K1 step, split over its two kernels:
+    {"recur": (flops, bytes), "attend": (flops, bytes), "step": (flops, bytes)}.  Each node's inputs are counted
+    once per kernel that needs them; the kernel-to-kernel logit scratch is not algorithmic traffic."""
     in_dim = o + L
-    per_node = (2 * H * in_dim                      # encode
-                + 2 * 2 * 2 * 3 * H * H             # factored input projections P,Q x 2 directions
-                + 2 * (N - 1) * 2 * 3 * H * H       # bidirectional GRU recurrence
-                + 2 * (N - 1) * 2 * 2 * H           # hard-attention logits
-                + 3 * 2 * H * H                     # q, k, v
-                + (N - 1) * 2 * H * 2               # scores + weighted sum
-                + 2 * 2 * 3 * H * H)                # GRUCell
     nodes = B * A * N
-    return per_node * nodes, nodes * (in_dim + 2 * H) * 4
+    recur = (2 * H * in_dim                     # encode
+             + 2 * 2 * 2 * 3 * H * H            # factored input projections P, Q x 2 directions
+             + 2 * (N - 1) * 2 * 3 * H * H      # bidirectional GRU recurrence
+             + 2 * (N - 1) * 2 * 2 * H)         # hard-attention logits
+    attend = (3 * 2 * H * H                     # q, k, v
+              + (N - 1) * 2 * H * 2             # scores + weighted sum
+              + 2 * 2 * 3 * H * H)              # GRUCell
+    return {"recur": (recur * nodes, nodes * in_dim * 4),
+            "attend": (attend * nodes, nodes * (in_dim + 2 * H) * 4),
+            "step": ((recur + attend) * nodes, nodes * (in_dim + 2 * H) * 4)}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed `ncu --set full`
+    summary (profiles/r1_k1_ncu_summary.json); None if that file does not name the kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_k1_ncu_summary.json")) as f:
+            return json.load(f)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def run_reference(args):
@@ -239,10 +253,14 @@ def main():
     ms = float(t)
     ms_per_step = ms / args.steps
     value = Bl * world * T / (ms_per_step / 1e3)
-    gat_ms = [s.elapsed_time(e) for tag, s, e in gat_events if tag == "gat"]
-    roll_ms = [s.elapsed_time(e) for tag, s, e in gat_events if tag == "roll"]
+    def times(tag):
+        return [s.elapsed_time(e) for tg, s, e in gat_events if tg == tag]
+
+    gat_ms, rec_ms, att_ms = times("gat"), times("gat_recur"), times("gat_attend")
+    roll_ms = times("roll")
     gat_mean = sum(gat_ms) / max(1, len(gat_ms))
-    breakdown = {tag: sum(s.elapsed_time(e) for tg, s, e in gat_events if tg == tag) / args.steps for tag in ("gat", "ctrl", "beh")}
+    rec_mean = sum(rec_ms) / max(1, len(rec_ms))
+    breakdown = {tag: sum(times(tag)) / args.steps for tag in ("gat", "gat_recur", "gat_attend", "ctrl", "beh")}
 
     # ---- e2e: same work through the reference-facing numpy API -----------------------------
     log(f"timed region done: {ms_per_step:.1f} ms/step; e2e leg")
@@ -269,16 +287,25 @@ def main():
             dist.destroy_process_group()
         return
     pk = peaks()
-    flops, hbm_bytes = gat_algorithmic(Bl, a.n_agents, a.max_vehicle_num, a.obs_shape_single, a.latent_dim)
-    ach_tf = flops / (gat_mean * 1e-3) / 1e12 if gat_mean > 0 else 0.0
-    roofline = {"kernel": "gat_step_kernel (K1)", "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sus"],
-                "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sus"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
-                "launch_ms": gat_mean, "launches_timed": len(gat_ms),
+    alg = gat_algorithmic(Bl, a.n_agents, a.max_vehicle_num, a.obs_shape_single, a.latent_dim)
+    flops, hbm_bytes = alg["recur"]
+    ach_tf = flops / (rec_mean * 1e-3) / 1e12 if rec_mean > 0 else 0.0
+    step_tf = alg["step"][0] / (gat_mean * 1e-3) / 1e12 if gat_mean > 0 else 0.0
+    roofline = {"kernel": "gat_recur_kernel (K1: encode, input projections, 2N GRU chains x N-1 steps, hard-attention logits)",
+                "bound": "tensor", "achieved": ach_tf, "peak": pk["tf_sus"],
+                "unit": "TFLOP/s", "frac": ach_tf / pk["tf_sus"], "traffic": ncu_traffic("gat_recur_kernel"),
+                "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)",
+                "launch_ms": rec_mean, "launches_timed": len(rec_ms),
                 "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": hbm_bytes,
-                "hbm_achieved_gbs": hbm_bytes / (gat_mean * 1e-3) / 1e9 if gat_mean > 0 else 0.0,
-                "hbm_frac": (hbm_bytes / (gat_mean * 1e-3) / 1e9) / pk["hbm"] if gat_mean > 0 else 0.0,
-                "share_of_step": sum(gat_ms) / ms if ms > 0 else None,
-                "note": "fp32 FMA + MUFU bound recurrence (54-step bi-GRU per ego); see DESIGN.md"}
+                "hbm_achieved_gbs": hbm_bytes / (rec_mean * 1e-3) / 1e9 if rec_mean > 0 else 0.0,
+                "hbm_frac": (hbm_bytes / (rec_mean * 1e-3) / 1e9) / pk["hbm"] if rec_mean > 0 else 0.0,
+                "share_of_step": sum(rec_ms) / ms if ms > 0 else None,
+                "k1_step": {"launch_ms": gat_mean, "attend_ms": sum(att_ms) / max(1, len(att_ms)), "tflops": step_tf,
+                            "algorithmic_flops": alg["step"][0], "algorithmic_bytes": alg["step"][1],
+                            "share_of_step": sum(gat_ms) / ms if ms > 0 else None,
+                            "traffic_attend": ncu_traffic("gat_attend_kernel")},
+                "note": "fp32-accurate products cost 3 f16 mma.sync each (hi/lo split); the recurrence is a 54-step serial chain "
+                        "bound by the legacy tensor pipe, MUFU and issue slots, not by HBM (AI ~ 2400 FLOP/B); see DESIGN.md"}
     out = {
         "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",

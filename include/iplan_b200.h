@@ -80,6 +80,16 @@ int iplan_gat_step(const float* gat_params, int64_t param_stride,
                    int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
                    void* stream);
 
+/* iplan_gat_step with optional cudaEvent_t handles (NULL = skip) recorded on `stream` before the recurrence kernel,
+ * between the two kernels and after the attention kernel: per-kernel timing of the dominant kernel inside a running
+ * rollout (bench.py's roofline) without a profiler. */
+int iplan_gat_step_ex(const float* gat_params, int64_t param_stride,
+                      iplan_view hist, iplan_view beh_prev, iplan_view h_prev, iplan_view out,
+                      const float* gumbel, uint64_t seed, uint64_t counter,
+                      float tau, float* dbg_hard, float* scratch, int64_t scratch_floats,
+                      int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
+                      void* ev_begin, void* ev_mid, void* ev_end, void* stream);
+
 /* ---- K1b: behaviour-encoder step -----------------------------------------------
  * replaces Behavior_policy.latent_update (nova/stable_behavior_policy.py:83-123)
  * = EncoderRNN.forward (nova/behavior_net.py:17-22) over the history window from the

@@ -528,12 +528,12 @@ extern "C" int64_t iplan_gat_scratch_floats(int n_envs, int n_agents, int n_slot
     return (int64_t)n_envs * n_agents * 2 * (n_slots - 1) * iplan::DLP;
 }
 
-extern "C" int iplan_gat_step(const float* gat_params, int64_t param_stride,
-                              iplan_view hist, iplan_view beh_prev, iplan_view h_prev, iplan_view out,
-                              const float* gumbel, uint64_t seed, uint64_t counter,
-                              float tau, float* dbg_hard, float* scratch, int64_t scratch_floats,
-                              int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
-                              void* stream) {
+extern "C" int iplan_gat_step_ex(const float* gat_params, int64_t param_stride,
+                                 iplan_view hist, iplan_view beh_prev, iplan_view h_prev, iplan_view out,
+                                 const float* gumbel, uint64_t seed, uint64_t counter,
+                                 float tau, float* dbg_hard, float* scratch, int64_t scratch_floats,
+                                 int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
+                                 void* ev_begin, void* ev_mid, void* ev_end, void* stream) {
     using namespace iplan;
     IPLAN_REQUIRE(n_slots >= 2 && n_slots <= IPLAN_MAX_SLOTS, "gat_step: n_slots %d not in [2,%d]", n_slots, IPLAN_MAX_SLOTS);
     IPLAN_REQUIRE(obs_dim + latent_dim <= IN_MAX && obs_dim > 0 && latent_dim >= 0, "gat_step: obs_dim+latent_dim %d > %d", obs_dim + latent_dim, IN_MAX);
@@ -561,11 +561,26 @@ extern "C" int iplan_gat_step(const float* gat_params, int64_t param_stride,
         if (e != cudaSuccess) { set_error("gat_step: attend smem attr %zu: %s", smem_a, cudaGetErrorString(e)); return (int)e; }
         conf_a = smem_a;
     }
+    if (ev_begin) cudaEventRecord((cudaEvent_t)ev_begin, (cudaStream_t)stream);
     gat_recur_kernel<<<dim3(n_envs, n_agents, 2), REC_THREADS, smem_r, (cudaStream_t)stream>>>(a);
     count_launch();
     int rc = check_launch("gat_step(recur)");
     if (rc) return rc;
+    if (ev_mid) cudaEventRecord((cudaEvent_t)ev_mid, (cudaStream_t)stream);
     gat_attend_kernel<<<dim3(n_envs, n_agents), GAT_THREADS, smem_a, (cudaStream_t)stream>>>(a);
     count_launch();
-    return check_launch("gat_step(attend)");
+    rc = check_launch("gat_step(attend)");
+    if (ev_end) cudaEventRecord((cudaEvent_t)ev_end, (cudaStream_t)stream);
+    return rc;
+}
+
+extern "C" int iplan_gat_step(const float* gat_params, int64_t param_stride,
+                              iplan_view hist, iplan_view beh_prev, iplan_view h_prev, iplan_view out,
+                              const float* gumbel, uint64_t seed, uint64_t counter,
+                              float tau, float* dbg_hard, float* scratch, int64_t scratch_floats,
+                              int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
+                              void* stream) {
+    return iplan_gat_step_ex(gat_params, param_stride, hist, beh_prev, h_prev, out, gumbel, seed, counter, tau, dbg_hard,
+                             scratch, scratch_floats, n_envs, n_agents, n_slots, obs_dim, latent_dim,
+                             nullptr, nullptr, nullptr, stream);
 }

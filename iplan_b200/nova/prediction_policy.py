@@ -44,20 +44,23 @@ class Prediction_policy:
         self._stage = None        # device staging buffers of the pipelined numpy entry point
 
     # ---- device path: tensors laid out [A, B, N, *] (any strides) ------------------
-    def gat_step(self, hist, beh_prev, h_prev, out, gumbel=None, dbg_hard=None):
-        """out[a,b,n,:] = GAT_a(hist[a,b], beh_prev[a,b], h_prev[a,b]); all CUDA fp32."""
+    def gat_step(self, hist, beh_prev, h_prev, out, gumbel=None, dbg_hard=None, events=None):
+        """out[a,b,n,:] = GAT_a(hist[a,b], beh_prev[a,b], h_prev[a,b]); all CUDA fp32.
+        ``events``: optional three recorded ``torch.cuda.Event(enable_timing=True)``; they are re-recorded on the
+        launching stream before the recurrence kernel, between the two kernels and after the attention kernel."""
         A, B, N, o = hist.shape
         if gumbel is not None:
             assert gumbel.is_contiguous() and tuple(gumbel.shape) == (A, B, N, N - 1, 2), gumbel.shape
         need = _lib.lib.iplan_gat_scratch_floats(B, A, N)
         if self._scratch is None or self._scratch.numel() < need or self._scratch.device != hist.device:
             self._scratch = torch.empty(need, device=hist.device, dtype=torch.float32)
-        rc = _lib.lib.iplan_gat_step(
+        ev = [None, None, None] if events is None else [e.cuda_event for e in events]
+        rc = _lib.lib.iplan_gat_step_ex(
             _lib.ptr(self.stack.flat), self.stack.stride(),
             _lib.view(hist), _lib.view(beh_prev), _lib.view(h_prev), _lib.view(out),
             _lib.ptr(gumbel), self.seed, self.calls, self.tau, _lib.ptr(dbg_hard),
             _lib.ptr(self._scratch), self._scratch.numel(),
-            B, A, N, o, beh_prev.shape[-1], _lib.stream())
+            B, A, N, o, beh_prev.shape[-1], ev[0], ev[1], ev[2], _lib.stream())
         _lib.check(rc, "gat_step")
         self.calls += 1
         return out

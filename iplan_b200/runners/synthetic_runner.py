@@ -191,7 +191,16 @@ class ParallelRunner:
             return out
 
         def gat(*a):
-            return timed("gat", self.prediction_learner.gat_step, *a)
+            if events is None:
+                return self.prediction_learner.gat_step(*a)
+            ev = [th.cuda.Event(enable_timing=True) for _ in range(3)]
+            for e in ev:
+                e.record()                   # creates the handles; the library re-records them around its two kernels
+            out = self.prediction_learner.gat_step(*a, events=ev)
+            events.append(("gat_recur", ev[0], ev[1]))
+            events.append(("gat_attend", ev[1], ev[2]))
+            events.append(("gat", ev[0], ev[2]))
+            return out
 
         push_history(0)
         gat(hist_v[:, :, 0], zeros_beh, zeros_att, att_v[:, :, 0])

@@ -173,3 +173,17 @@ def test_train_vs_oracle_highway_shape():
     # a property of ReLU + fp32 (the reference vs its own GPU build shows the same), so allow a
     # small fraction of such weights but bound them by a few learning rates.
     assert worst < 4 * args.lr and n_off < 0.01 * n_all
+
+
+@pytest.mark.parametrize("shape", [(2, 300, 272), (1, 128, 2485), (3, 1000, 2485)])
+def test_fc1_tcgen05_matches_mma_sync_and_fp64(shape):
+    """The tcgen05 / TMEM / TMA fc1 forward and backward (csrc/fc1_tc5.cu) against the mma.sync kernels and an
+    fp64 reference on the same operands: ragged rows, ragged K (Fp = 288 is not a multiple of the 64-wide k-block)."""
+    _need_gpu()
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "check_fc1_tc5", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_fc1_tc5.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(*shape, reps=1) < 1e-5
