@@ -34,6 +34,8 @@
 // and the dl scratch come from L2.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace iplan {
@@ -64,13 +66,14 @@ __host__ __device__ inline size_t rec_smem_floats(int N) {
     const size_t pro = (size_t)N * IN_MAX + (size_t)H * IN_MAX + (size_t)N * H, rec = 4 * NT_G * KB_H * 32 + 64 + 32;
     return (size_t)N * PP + (size_t)N * G3 + (pro > rec ? pro : rec);
 }
-constexpr int QP = H + 8;       // q / k row pitch (floats): 8-byte aligned, conflict-free fragment reads
+constexpr int QKP = 72;         // row pitch of the q|k buffer: q at columns 0..31, k at columns KOFF..KOFF+31
+constexpr int KOFF = 36;        //   (8-byte aligned, (72 g + 2 t) mod 32 distinct over a half-warp: conflict-free fragment reads)
 constexpr int WP = 64 + 8;      // attention-weight / V^T row pitch: K = 64 neighbour columns, zero padded
 __host__ __device__ inline size_t att_smem_floats(int N) {
-    // s_vt (aliases s_x) | s_enc | s_xa | s_hp | region { s_q, s_k, s_dl, s_w }  (s_gi, s_gh alias the region)
-    const size_t region = (size_t)2 * N * QP + (size_t)N * (N - 1) + (size_t)N * WP;
-    const size_t gru = (size_t)2 * N * G3;
-    return (size_t)H * WP + 3 * (size_t)N * H + (region > gru ? region : gru);
+    // s_vt (aliases s_x, s_we) | s_enc | s_xa | s_hp | s_gh | region { s_qk, s_dl, s_w }  (s_gi aliases the region)
+    const size_t region = (size_t)N * QKP + (size_t)N * (N - 1) + (size_t)N * WP;
+    const size_t gru = (size_t)N * G3;
+    return (size_t)H * WP + 3 * (size_t)N * H + (size_t)N * G3 + (region > gru ? region : gru);
 }
 
 // fast, fp32-accurate-enough gates (abs error ~1e-7): ex2.approx + rcp.approx
@@ -164,10 +167,12 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 // every sector fetched is fully used.  TRANS_OUT stores out[c][n] instead (row pitch ldout).
 struct EpiNone { __device__ __forceinline__ float operator()(int, float v) const { return v; } };
 
-template <int NW, int KB = KB_H, bool TRANS_OUT = false, class Epi = EpiNone>
+struct StoreNone {};            // default: out[r][c] (or out[c][r] with TRANS_OUT)
+
+template <int NW, int KB = KB_H, bool TRANS_OUT = false, class Epi = EpiNone, class Store = StoreNone>
 __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, const float* __restrict__ Wg, int ldw,
                                             const float* __restrict__ bias, int cols, float* out, int ldout, bool relu,
-                                            int warp, int lane, Epi epi = Epi()) {
+                                            int warp, int lane, Epi epi = Epi(), Store store = Store()) {
     const int gq = lane >> 2, tq = lane & 3;
     const int mtiles = (N + 15) >> 4, ntiles = cols >> 3;
     const int mh = (mtiles + 1) >> 1;                 // a task = one n-tile x one half of the m-tiles
@@ -220,7 +225,10 @@ __device__ __forceinline__ void dense32_mma(const float* in, int ldin, int N, co
                 }
                 if (relu) { acc[0] = fmaxf(acc[0], 0.f); acc[1] = fmaxf(acc[1], 0.f); acc[2] = fmaxf(acc[2], 0.f); acc[3] = fmaxf(acc[3], 0.f); }
                 acc[0] = epi(c0, acc[0]); acc[1] = epi(c0 + 1, acc[1]); acc[2] = epi(c0, acc[2]); acc[3] = epi(c0 + 1, acc[3]);
-                if (TRANS_OUT) {
+                if constexpr (!std::is_same<Store, StoreNone>::value) {       // caller-defined placement: store(row, col, value)
+                    if (r0 < N) { store(r0, c0, acc[0]); store(r0, c0 + 1, acc[1]); }
+                    if (r1 < N) { store(r1, c0, acc[2]); store(r1, c0 + 1, acc[3]); }
+                } else if (TRANS_OUT) {
                     if (r0 < N) { out[c0 * ldout + r0] = acc[0]; out[(c0 + 1) * ldout + r0] = acc[1]; }
                     if (r1 < N) { out[c0 * ldout + r1] = acc[2]; out[(c0 + 1) * ldout + r1] = acc[3]; }
                 } else {
@@ -426,26 +434,22 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
     float* s_enc = s_vt + H * WP;                       // [N][H]
     float* s_xa = s_enc + N * H;                        // [N][H] aggregated messages
     float* s_hp = s_xa + N * H;                         // [N][H] h_prev
-    float* s_q = s_hp + N * H;                          // [N][QP]
-    float* s_k = s_q + N * QP;                          // [N][QP]
-    float* s_dl = s_k + N * QP;                         // [N][N-1] logit difference, both directions summed
+    float* s_gh = s_hp + N * H;                         // [N][96] GRUCell hidden pre-activations
+    float* s_qk = s_gh + N * G3;                        // [N][QKP] q | k
+    float* s_dl = s_qk + N * QKP;                       // [N][N-1] logit difference, both directions summed
     float* s_w = s_dl + N * NM1;                        // [N][WP] scores, then attention weights over ALL slots j (self = 0)
-    float* s_gi = s_q;                                  // [N][96] GRUCell input pre-activations  (q, k, dl, w are dead by then)
-    float* s_gh = s_gi + N * G3;                        // [N][96] GRUCell hidden pre-activations
+    float* s_gi = s_qk;                                 // [N][96] GRUCell input pre-activations  (q, k, dl, w are dead by then)
 
     const float* hprev = a.hprev.ptr + ag * a.hprev.stride_agent + b * a.hprev.stride_env;
     float* outp = a.out.ptr + ag * a.out.stride_agent + b * a.out.stride_env;
 
-    gat_encode<GAT_THREADS>(a, W, L, b, ag, s_x, s_we, s_enc);
-
-    // ---- phase 4: q, k, v^T; stage h_prev and the recurrence kernel's dl[dir][s][i] ------
-    for (int idx = tid; idx < H * WP; idx += GAT_THREADS) s_vt[idx] = 0.0f;       // s_x is dead: gat_encode ends with a barrier
-    __syncthreads();
-    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.q_w, H, nullptr, H, s_q, QP, false, warp, lane);
-    dense32_mma<GAT_WARPS>(s_enc, H, N, W + L.k_w, H, nullptr, H, s_k, QP, false, warp, lane);
-    dense32_mma<GAT_WARPS, KB_H, true>(s_enc, H, N, W + L.v_w, H, W + L.v_b, H, s_vt, WP, true, warp, lane);
-    for (int idx = tid; idx < N * H; idx += GAT_THREADS)
-        s_hp[idx] = hprev[(idx >> 5) * a.hprev.stride_slot + (idx & 31)];
+    // ---- everything that only depends on the kernel's inputs is fetched first, so its L2 latency overlaps the encode:
+    //      h_prev (cp.async) and the recurrence kernel's dl[dir][s][i] (summed over the two directions, transposed)
+    for (int idx = tid; idx < N * H; idx += GAT_THREADS) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_hp + idx);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(hprev + (idx >> 5) * a.hprev.stride_slot + (idx & 31)));
+    }
+    asm volatile("cp.async.commit_group;");
     {
         const float* dlf = a.dl + (((int64_t)ag * a.n_envs + b) * 2) * NM1 * DLP;
         const float* dlr = dlf + (int64_t)NM1 * DLP;
@@ -454,12 +458,28 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
             if (i < N) s_dl[i * NM1 + s] = dlf[idx] + dlr[idx];
         }
     }
+    gat_encode<GAT_THREADS>(a, W, L, b, ag, s_x, s_we, s_enc);
+
+    // ---- phase 4: q | k | v^T as ONE product over the three consecutive weight tensors; gh = h_prev W_hh^T + b_hh ------
+    for (int idx = tid; idx < H * WP; idx += GAT_THREADS) s_vt[idx] = 0.0f;       // s_x is dead: gat_encode ends with a barrier
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    {
+        const float* vb = W + L.v_b;
+        auto store_qkv = [=](int r, int c, float v) {
+            if (c < H) s_qk[r * QKP + c] = v;
+            else if (c < 2 * H) s_qk[r * QKP + KOFF + (c - H)] = v;
+            else s_vt[(c - 2 * H) * WP + r] = fmaxf(v + vb[c - 2 * H], 0.0f);     // v = ReLU(W_v enc + b_v), transposed
+        };
+        dense32_mma<GAT_WARPS, KB_H, false, EpiNone>(s_enc, H, N, W + L.q_w, H, nullptr, 3 * H, nullptr, 0, false, warp, lane, EpiNone(), store_qkv);
+    }
+    dense32_mma<GAT_WARPS>(s_hp, H, N, W + L.c_whh, H, W + L.c_bhh, G3, s_gh, G3, false, warp, lane);
     __syncthreads();
 
     // ---- phase 5a: raw scores S[i][j] = q_i . k_j for every slot pair, on the tensor cores --------
-    // (columns are padded to a multiple of 8: rows of s_k past N-1 are whatever follows in shared memory;
+    // (columns are padded to a multiple of 8: rows of the q|k buffer past N-1 are whatever follows in shared memory;
     //  those columns are never read)
-    dense32_mma<GAT_WARPS>(s_q, QP, N, s_k, QP, nullptr, (N + 7) & ~7, s_w, WP, false, warp, lane);
+    dense32_mma<GAT_WARPS>(s_qk, QKP, N, s_qk + KOFF, QKP, nullptr, (N + 7) & ~7, s_w, WP, false, warp, lane);
     __syncthreads();
 
     // ---- phase 5b: soft x hard attention weights, one warp per ego; lane -> slots j = lane, lane + 32 ----
@@ -507,9 +527,8 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
     dense32_mma<GAT_WARPS, 4>(s_w, WP, N, s_vt, WP, nullptr, H, s_xa, H, false, warp, lane);
     __syncthreads();
 
-    // ---- phase 6: GRUCell(x_i, h_prev_i) (:140): two N x 96 x 32 products + gates -----
+    // ---- phase 6: GRUCell(x_i, h_prev_i) (:140): gi = x W_ih^T + b_ih (gh was computed in phase 4), gates -----
     dense32_mma<GAT_WARPS>(s_xa, H, N, W + L.c_wih, H, W + L.c_bih, G3, s_gi, G3, false, warp, lane);
-    dense32_mma<GAT_WARPS>(s_hp, H, N, W + L.c_whh, H, W + L.c_bhh, G3, s_gh, G3, false, warp, lane);
     __syncthreads();
     for (int idx = tid; idx < N * H; idx += GAT_THREADS) {
         const int n = idx >> 5, c = idx & 31;

@@ -217,129 +217,187 @@ __device__ __forceinline__ float huber_os_grad(float e, float d) {
     return fabsf(e) <= d ? e : (e > d ? d : 0.0f);
 }
 
-__global__ void __launch_bounds__(128, 3) gru_head_kernel(HeadArgs h) {
-    const int a = blockIdx.y >> 1, type = blockIdx.y & 1;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+// 16 lanes per row, two rows per warp: lane `sub` of a half-warp owns the hidden units / features
+// c = sub + 16 u (u = 0..3), so the per-row scalar work (soft-max, losses) is shared by 16 lanes instead of 32 and
+// a warp carries two independent dependency chains.  Reductions over a row's 64 features = 4 local adds + 4 shuffles.
+constexpr int HU = 4;                       // units per lane
+constexpr int HEAD_THREADS = 128;
+constexpr int HEAD_WARPS = HEAD_THREADS / 32;
+// lane-local gradient accumulators flushed through shared memory at the end: per feature-lane values
+//   dW[n_out][HU], dg3[HU], db3[HU], dbi[3][HU], dbh[3][HU]  and per-row scalars dB[n_out], 3 statistics
+
+__device__ __forceinline__ float half_sum(float v) {                 // sum over the 16 lanes of a half-warp
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// TYPE 0 = actor (NOUT >= n_actions head rows kept in registers), TYPE 1 = critic (NOUT = 1); blockIdx.y = agent
+template <int TYPE, int NOUT>
+__global__ void __launch_bounds__(HEAD_THREADS, 3) gru_head_kernel(HeadArgs h) {
+    constexpr int HEAD_NV = NOUT * HU + 2 * HU + 6 * HU;        // vector slots of the gradient flush
+    constexpr int HEAD_NS = NOUT + 3;                            // scalar slots
+    __shared__ float red_v[HEAD_WARPS][HEAD_NV][32];
+    __shared__ float red_s[HEAD_WARPS][2][HEAD_NS];
+    const int a = blockIdx.y;
+    constexpr int type = TYPE;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int sub = lane & 15, half = lane >> 4;
     const float* p = h.P.net(a, type);
     const TrunkLayout L = trunk_layout(h.F, type == 0 ? h.n_actions : 1, type == 1);
     const int nA = h.n_actions;
-    const float g3_0 = p[L.ln3_w + lane], g3_1 = p[L.ln3_w + lane + 32];
-    const float b3_0 = p[L.ln3_b + lane], b3_1 = p[L.ln3_b + lane + 32];
-    float hw0[IPLAN_MAX_ACT], hw1[IPLAN_MAX_ACT], hb[IPLAN_MAX_ACT];
     const int n_out = type == 0 ? nA : 1;
+    float g3[HU], b3[HU], hw[NOUT][HU], hb[NOUT];
 #pragma unroll
-    for (int l = 0; l < IPLAN_MAX_ACT; ++l) {
-        hw0[l] = l < n_out ? p[L.head_w + l * RH + lane] : 0.0f;
-        hw1[l] = l < n_out ? p[L.head_w + l * RH + lane + 32] : 0.0f;
+    for (int u = 0; u < HU; ++u) { g3[u] = p[L.ln3_w + sub + 16 * u]; b3[u] = p[L.ln3_b + sub + 16 * u]; }
+#pragma unroll
+    for (int l = 0; l < NOUT; ++l) {
+#pragma unroll
+        for (int u = 0; u < HU; ++u) hw[l][u] = l < n_out ? p[L.head_w + l * RH + sub + 16 * u] : 0.0f;
         hb[l] = l < n_out ? p[L.head_b + l] : 0.0f;
     }
     float nrm_mean = 0, nrm_istd = 0, inv_msum = 0, inv_rows = 0;
     if (h.train) { nrm_mean = h.norm[a * 4]; nrm_istd = h.norm[a * 4 + 1]; inv_msum = h.norm[a * 4 + 2]; inv_rows = h.norm[a * 4 + 3]; }
 
     // lane-local gradient accumulators
-    float dW0[IPLAN_MAX_ACT], dW1[IPLAN_MAX_ACT], dB[IPLAN_MAX_ACT];
+    float dW[NOUT][HU], dB[NOUT];
 #pragma unroll
-    for (int l = 0; l < IPLAN_MAX_ACT; ++l) { dW0[l] = 0; dW1[l] = 0; dB[l] = 0; }
-    float dg3_0 = 0, dg3_1 = 0, db3_0 = 0, db3_1 = 0;
-    float dbi[6] = {0, 0, 0, 0, 0, 0}, dbh[6] = {0, 0, 0, 0, 0, 0};
+    for (int l = 0; l < NOUT; ++l) {
+        dB[l] = 0.0f;
+#pragma unroll
+        for (int u = 0; u < HU; ++u) dW[l][u] = 0.0f;
+    }
+    float dg3[HU], db3[HU], dbi[3][HU], dbh[3][HU];
+#pragma unroll
+    for (int u = 0; u < HU; ++u) {
+        dg3[u] = db3[u] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) dbi[q][u] = dbh[q][u] = 0.0f;
+    }
     float st_loss = 0, st_ent = 0, st_ratio = 0;
 
-    const int64_t warp = (int64_t)blockIdx.x * nw + w;
-    const int64_t nwarps = (int64_t)gridDim.x * nw;
-    for (int64_t r = warp; r < h.rows; r += nwarps) {
+    const int64_t pair0 = ((int64_t)blockIdx.x * HEAD_WARPS + w) * 2;           // first row of this warp's first pair
+    const int64_t stride = (int64_t)gridDim.x * HEAD_WARPS * 2;
+    for (int64_t rp = pair0; rp < h.rows; rp += stride) {                       // warp-uniform trip count
+        const int64_t r_raw = rp + half;
+        const bool valid = r_raw < h.rows;                                       // half-uniform
+        const int64_t r = valid ? r_raw : h.rows - 1;
         const int b = (int)(r / h.T1), t = (int)(r - (int64_t)b * h.T1);
         float* gi = h.gi.row(a, type, r);
         float* gh = h.gh.row(a, type, r);
         const float* h0 = (type == 0 ? h.h0a : h.h0c) + a * h.h0_sa + r * h.h0_ld;
-        float rg[2], zg[2], ng[2], ghn[2], h1[2], h0v[2];
+        float rg[HU], zg[HU], ng[HU], ghn[HU], h1[HU], h0v[HU];
+        float s1 = 0.0f;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int c = lane + 32 * u;
+        for (int u = 0; u < HU; ++u) {
+            const int c = sub + 16 * u;
             rg[u] = sigmoidf_acc(gi[c] + gh[c]);
             zg[u] = sigmoidf_acc(gi[RH + c] + gh[RH + c]);
             ghn[u] = gh[2 * RH + c];
             ng[u] = tanhf_acc(gi[2 * RH + c] + rg[u] * ghn[u]);
             h0v[u] = h0[c];
             h1[u] = (1.0f - zg[u]) * ng[u] + zg[u] * h0v[u];
+            s1 += h1[u];
         }
-        const float mean = warp_sum(h1[0] + h1[1]) * (1.0f / RH);
-        const float c0 = h1[0] - mean, c1 = h1[1] - mean;
-        const float rstd = 1.0f / sqrtf(warp_sum(c0 * c0 + c1 * c1) * (1.0f / RH) + LEPS);
-        const float x0 = c0 * rstd, x1 = c1 * rstd;
-        const float a0 = x0 * g3_0 + b3_0, a1 = x1 * g3_1 + b3_1;
-        float outv[IPLAN_MAX_ACT];
+        const float mean = half_sum(s1) * (1.0f / RH);
+        float cen[HU], s2 = 0.0f;
 #pragma unroll
-        for (int l = 0; l < IPLAN_MAX_ACT; ++l)
-            outv[l] = l < n_out ? warp_sum(hw0[l] * a0 + hw1[l] * a1) + hb[l] : -INFINITY;
+        for (int u = 0; u < HU; ++u) { cen[u] = h1[u] - mean; s2 = fmaf(cen[u], cen[u], s2); }
+        const float rstd = 1.0f / sqrtf(half_sum(s2) * (1.0f / RH) + LEPS);
+        float xh[HU], av[HU];
+#pragma unroll
+        for (int u = 0; u < HU; ++u) { xh[u] = cen[u] * rstd; av[u] = xh[u] * g3[u] + b3[u]; }
+        float outv[NOUT];
+#pragma unroll
+        for (int l = 0; l < NOUT; ++l) {
+            if (l < n_out) {                                                     // block-uniform
+                float d = 0.0f;
+#pragma unroll
+                for (int u = 0; u < HU; ++u) d = fmaf(hw[l][u], av[u], d);
+                outv[l] = half_sum(d) + hb[l];
+            } else {
+                outv[l] = -INFINITY;
+            }
+        }
 
         const int64_t ridx = (int64_t)a * h.rows + r;
-        const bool train_row = h.train && t < h.T1 - 1 && b < h.n_train_eps;
-        float dA0 = 0.0f, dA1 = 0.0f;         // gradient wrt the LN3 output (features lane, lane+32)
+        const bool train_row = valid && h.train && t < h.T1 - 1 && b < h.n_train_eps;
+        float dA[HU];                         // gradient wrt the LN3 output
+#pragma unroll
+        for (int u = 0; u < HU; ++u) dA[u] = 0.0f;
         if (type == 0) {
             const int act = h.actions[ridx];
-            bool masked[IPLAN_MAX_ACT];
+            bool masked[NOUT];
             float mx = -INFINITY;
 #pragma unroll
-            for (int l = 0; l < IPLAN_MAX_ACT; ++l) {
+            for (int l = 0; l < NOUT; ++l) {
                 masked[l] = l < nA && h.avail && h.avail[ridx * nA + l] == 0;
                 if (masked[l]) outv[l] = -1e10f;
                 if (l < nA) mx = fmaxf(mx, outv[l]);
             }
             float den = 0.0f;
 #pragma unroll
-            for (int l = 0; l < IPLAN_MAX_ACT; ++l) if (l < nA) den += expf(outv[l] - mx);
+            for (int l = 0; l < NOUT; ++l) if (l < nA) den += expf(outv[l] - mx);
             const float lse = mx + logf(den);
-            float ent = 0.0f, lp_a = 0.0f, pl[IPLAN_MAX_ACT], lpl[IPLAN_MAX_ACT];
+            float ent = 0.0f, lp_a = 0.0f, pl[NOUT], lpl[NOUT];
 #pragma unroll
-            for (int l = 0; l < IPLAN_MAX_ACT; ++l) {
+            for (int l = 0; l < NOUT; ++l) {
                 lpl[l] = l < nA ? outv[l] - lse : 0.0f;
                 pl[l] = l < nA ? expf(lpl[l]) : 0.0f;
                 ent -= pl[l] * lpl[l];
                 if (l == act) lp_a = lpl[l];
             }
-            if (!h.train) {
-                if (lane == 0) {
+            if (!h.train) {                                                      // block-uniform
+                if (sub == 0 && valid) {
                     if (h.logp_out) h.logp_out[ridx] = lp_a;
                     if (h.ent_out) h.ent_out[ridx] = ent;
                 }
                 continue;
             }
-            float dl[IPLAN_MAX_ACT];
+            float dl[NOUT];
 #pragma unroll
-            for (int l = 0; l < IPLAN_MAX_ACT; ++l) dl[l] = 0.0f;
+            for (int l = 0; l < NOUT; ++l) dl[l] = 0.0f;
             if (train_row) {
                 const float m = h.alive[ridx];
                 const float adv = (h.adv_raw[ridx] - nrm_mean) * nrm_istd;
                 const float ratio = expf(lp_a - h.old_logp[ridx]);
-                const float s1 = ratio * adv;
-                const float s2 = fminf(fmaxf(ratio, 1.0f - h.clip), 1.0f + h.clip) * adv;
+                const float s1_ = ratio * adv;
+                const float s2_ = fminf(fmaxf(ratio, 1.0f - h.clip), 1.0f + h.clip) * adv;
                 const bool inside = ratio >= 1.0f - h.clip && ratio <= 1.0f + h.clip;
                 float d = 0.0f;                                   // d min(s1,s2) / d logp
-                if (s1 < s2) d = s1;
-                else if (s1 == s2) d = inside ? s1 : 0.5f * s1;
+                if (s1_ < s2_) d = s1_;
+                else if (s1_ == s2_) d = inside ? s1_ : 0.5f * s1_;
                 const float g_lp = -m * inv_msum * d * h.gscale;
                 const float g_ent = -h.ent_coef * inv_rows * h.gscale;       // d(-c*mean ent)/d ent_row
 #pragma unroll
-                for (int l = 0; l < IPLAN_MAX_ACT; ++l) {
+                for (int l = 0; l < NOUT; ++l) {
                     if (l < nA && !masked[l]) {
                         const float dlp = g_lp * ((l == act ? 1.0f : 0.0f) - pl[l]);
                         const float dent = g_ent * (-pl[l] * (lpl[l] + ent));
                         dl[l] = dlp + dent;
                     }
                 }
-                st_loss += -fminf(s1, s2) * m * inv_msum;
-                st_ent += ent * inv_rows;
-                st_ratio += ratio * inv_rows;
+                if (sub == 0) {                                  // per-row scalars: one lane of the half-warp carries them
+                    st_loss += -fminf(s1_, s2_) * m * inv_msum;
+                    st_ent += ent * inv_rows;
+                    st_ratio += ratio * inv_rows;
+                }
             }
 #pragma unroll
-            for (int l = 0; l < IPLAN_MAX_ACT; ++l) {
-                dA0 = fmaf(dl[l], hw0[l], dA0); dA1 = fmaf(dl[l], hw1[l], dA1);
-                dW0[l] = fmaf(dl[l], a0, dW0[l]); dW1[l] = fmaf(dl[l], a1, dW1[l]); dB[l] += dl[l];
+            for (int l = 0; l < NOUT; ++l) {
+#pragma unroll
+                for (int u = 0; u < HU; ++u) {
+                    dA[u] = fmaf(dl[l], hw[l][u], dA[u]);
+                    dW[l][u] = fmaf(dl[l], av[u], dW[l][u]);
+                }
+                if (sub == 0) dB[l] += dl[l];
             }
         } else {
             const float v = outv[0];
             if (!h.train) {
-                if (lane == 0 && h.value_out) h.value_out[ridx] = v;
+                if (sub == 0 && valid && h.value_out) h.value_out[ridx] = v;
                 continue;
             }
             float dv = 0.0f;
@@ -359,74 +417,91 @@ __global__ void __launch_bounds__(128, 3) gru_head_kernel(HeadArgs h) {
                 const float gc = inside ? -huber_os_grad(ec, h.huber_delta) : 0.0f;
                 const float g = lo > lc ? go : (lc > lo ? gc : 0.5f * (go + gc));
                 dv = h.v_coef * m * inv_msum * g * h.gscale;
-                st_loss += fmaxf(lo, lc) * m * inv_msum;
+                if (sub == 0) st_loss += fmaxf(lo, lc) * m * inv_msum;
             }
-            dA0 = dv * hw0[0]; dA1 = dv * hw1[0];
-            dW0[0] = fmaf(dv, a0, dW0[0]); dW1[0] = fmaf(dv, a1, dW1[0]); dB[0] += dv;
-        }
-        // ---- backward: LN3, GRU gates -------------------------------------------------
-        dg3_0 = fmaf(dA0, x0, dg3_0); dg3_1 = fmaf(dA1, x1, dg3_1); db3_0 += dA0; db3_1 += dA1;
-        const float dx0 = dA0 * g3_0, dx1 = dA1 * g3_1;
-        const float m1_ = warp_sum(dx0 + dx1) * (1.0f / RH);
-        const float m2_ = warp_sum(dx0 * x0 + dx1 * x1) * (1.0f / RH);
-        const float dh[2] = {rstd * (dx0 - m1_ - x0 * m2_), rstd * (dx1 - m1_ - x1 * m2_)};
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int c = lane + 32 * u;
-            const float dn = dh[u] * (1.0f - zg[u]);
-            const float dz = dh[u] * (h0v[u] - ng[u]);
+            for (int u = 0; u < HU; ++u) { dA[u] = dv * hw[0][u]; dW[0][u] = fmaf(dv, av[u], dW[0][u]); }
+            if (sub == 0) dB[0] += dv;
+        }
+        // ---- backward: LN3, GRU gates (rows past the end carry dA = 0 and store nothing) --------
+        float dx[HU], t1 = 0.0f, t2 = 0.0f;
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+            dg3[u] = fmaf(dA[u], xh[u], dg3[u]); db3[u] += dA[u];
+            dx[u] = dA[u] * g3[u];
+            t1 += dx[u]; t2 = fmaf(dx[u], xh[u], t2);
+        }
+        const float m1_ = half_sum(t1) * (1.0f / RH);
+        const float m2_ = half_sum(t2) * (1.0f / RH);
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+            const int c = sub + 16 * u;
+            const float dh = rstd * (dx[u] - m1_ - xh[u] * m2_);
+            const float dn = dh * (1.0f - zg[u]);
+            const float dz = dh * (h0v[u] - ng[u]);
             const float dan = dn * (1.0f - ng[u] * ng[u]);
             const float dr = dan * ghn[u];
             const float daz = dz * zg[u] * (1.0f - zg[u]);
             const float dar = dr * rg[u] * (1.0f - rg[u]);
-            gi[c] = dar; gi[RH + c] = daz; gi[2 * RH + c] = dan;
-            gh[c] = dar; gh[RH + c] = daz; gh[2 * RH + c] = dan * rg[u];
-            dbi[3 * u + 0] += dar; dbi[3 * u + 1] += daz; dbi[3 * u + 2] += dan;
-            dbh[3 * u + 0] += dar; dbh[3 * u + 1] += daz; dbh[3 * u + 2] += dan * rg[u];
+            if (valid) {
+                gi[c] = dar; gi[RH + c] = daz; gi[2 * RH + c] = dan;
+                gh[c] = dar; gh[RH + c] = daz; gh[2 * RH + c] = dan * rg[u];
+            }
+            dbi[0][u] += dar; dbi[1][u] += daz; dbi[2][u] += dan;
+            dbh[0][u] += dar; dbh[1][u] += daz; dbh[2][u] += dan * rg[u];
         }
     }
     if (!h.train) return;
 
-    // ---- block reduction of lane-local accumulators -> global gradient buffers ---------
-    __shared__ float red[8][32];
-    float* g = h.G.net(a, type);
-    auto flush = [&](float v, float* dst) {        // dst: address for this lane's value
-        red[w][lane] = v;
-        __syncthreads();
-        if (w == 0) {
-            float t = 0.0f;
-            for (int i = 0; i < nw; ++i) t += red[i][lane];
-            atomicAdd(dst, t);
+    // ---- one-barrier block reduction of the lane-local accumulators -> global gradient buffers ---------
+    {
+        int k = 0;
+#pragma unroll
+        for (int l = 0; l < NOUT; ++l)
+#pragma unroll
+            for (int u = 0; u < HU; ++u) red_v[w][k++][lane] = dW[l][u];
+#pragma unroll
+        for (int u = 0; u < HU; ++u) red_v[w][k++][lane] = dg3[u];
+#pragma unroll
+        for (int u = 0; u < HU; ++u) red_v[w][k++][lane] = db3[u];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int u = 0; u < HU; ++u) red_v[w][k++][lane] = dbi[q][u];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int u = 0; u < HU; ++u) red_v[w][k++][lane] = dbh[q][u];
+        if (sub == 0) {
+#pragma unroll
+            for (int l = 0; l < NOUT; ++l) red_s[w][half][l] = dB[l];
+            red_s[w][half][NOUT] = st_loss; red_s[w][half][NOUT + 1] = st_ent; red_s[w][half][NOUT + 2] = st_ratio;
         }
-        __syncthreads();
-    };
-    for (int l = 0; l < n_out; ++l) {
-        flush(dW0[l], &g[L.head_w + l * RH + lane]);
-        flush(dW1[l], &g[L.head_w + l * RH + lane + 32]);
-    }
-    flush(dg3_0, &g[L.ln3_w + lane]); flush(dg3_1, &g[L.ln3_w + lane + 32]);
-    flush(db3_0, &g[L.ln3_b + lane]); flush(db3_1, &g[L.ln3_b + lane + 32]);
-    for (int u = 0; u < 2; ++u)
-        for (int q = 0; q < 3; ++q) {
-            flush(dbi[3 * u + q], &g[L.bih + q * RH + lane + 32 * u]);
-            flush(dbh[3 * u + q], &g[L.bhh + q * RH + lane + 32 * u]);
-        }
-    // scalars: every lane of a warp holds the same dB / stats value (they derive from
-    // warp-uniform quantities), so take lane 0 of each warp
-    __shared__ float sred[8][IPLAN_MAX_ACT + 3];
-    if (lane == 0) {
-        for (int l = 0; l < IPLAN_MAX_ACT; ++l) sred[w][l] = dB[l];
-        sred[w][IPLAN_MAX_ACT] = st_loss; sred[w][IPLAN_MAX_ACT + 1] = st_ent; sred[w][IPLAN_MAX_ACT + 2] = st_ratio;
     }
     __syncthreads();
-    if (threadIdx.x < IPLAN_MAX_ACT + 3) {
+    float* g = h.G.net(a, type);
+    for (int idx = threadIdx.x; idx < HEAD_NV * 16; idx += HEAD_THREADS) {
+        const int k = idx >> 4, s16 = idx & 15;
         float t = 0.0f;
-        for (int i = 0; i < nw; ++i) t += sred[i][threadIdx.x];
+#pragma unroll
+        for (int i = 0; i < HEAD_WARPS; ++i) t += red_v[i][k][s16] + red_v[i][k][s16 + 16];
+        const int u = k % HU, grp = k / HU;                 // grp: 0..7 head rows | 8 dg3 | 9 db3 | 10..12 dbi | 13..15 dbh
+        const int c = s16 + 16 * u;
+        if (grp < NOUT) { if (grp < n_out) atomicAdd(&g[L.head_w + grp * RH + c], t); }
+        else if (grp == NOUT) atomicAdd(&g[L.ln3_w + c], t);
+        else if (grp == NOUT + 1) atomicAdd(&g[L.ln3_b + c], t);
+        else if (grp < NOUT + 5) atomicAdd(&g[L.bih + (grp - NOUT - 2) * RH + c], t);
+        else atomicAdd(&g[L.bhh + (grp - NOUT - 5) * RH + c], t);
+    }
+    if (threadIdx.x < HEAD_NS) {
         const int q = threadIdx.x;
-        if (q < n_out) atomicAdd(&g[L.head_b + q], t);
-        else if (q == IPLAN_MAX_ACT) atomicAdd(&h.stats[a * 8 + (type == 0 ? 0 : 1)], t);   // policy | value loss
-        else if (q == IPLAN_MAX_ACT + 1 && type == 0) atomicAdd(&h.stats[a * 8 + 2], t);      // entropy
-        else if (q == IPLAN_MAX_ACT + 2 && type == 0) atomicAdd(&h.stats[a * 8 + 3], t);      // ratio
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < HEAD_WARPS; ++i) t += red_s[i][0][q] + red_s[i][1][q];
+        if (q < NOUT) { if (q < n_out) atomicAdd(&g[L.head_b + q], t); }
+        else if (q == NOUT) atomicAdd(&h.stats[a * 8 + (type == 0 ? 0 : 1)], t);   // policy | value loss
+        else if (q == NOUT + 1 && type == 0) atomicAdd(&h.stats[a * 8 + 2], t);      // entropy
+        else if (q == NOUT + 2 && type == 0) atomicAdd(&h.stats[a * 8 + 3], t);      // ratio
     }
 }
 
@@ -597,7 +672,13 @@ extern "C" int iplan_learner_tail(const iplan_learner_ctx* c, int train, void* s
     h.stats = c->stats; h.train = train;
     if (train) IPLAN_REQUIRE(c->g_actor && c->g_critic && c->old_logp && c->old_value && c->returns && c->adv_raw && c->alive && c->norm && c->stats && c->SM && c->stat,
                              "learner_tail: train mode needs gradient/loss buffers");
-    gru_head_kernel<<<dim3((unsigned)std::min<int64_t>((rows + 3) / 4, 148 * 12), 2 * A), 128, 0, st>>>(h); ++launches;
+    {
+        const dim3 hgrid((unsigned)std::min<int64_t>((rows + 7) / 8, 148 * 6), A);
+        if (c->n_actions <= 5) gru_head_kernel<0, 5><<<hgrid, HEAD_THREADS, 0, st>>>(h);
+        else gru_head_kernel<0, IPLAN_MAX_ACT><<<hgrid, HEAD_THREADS, 0, st>>>(h);
+        gru_head_kernel<1, 1><<<hgrid, HEAD_THREADS, 0, st>>>(h);
+        launches += 2;
+    }
     if (train) {
         const int64_t n_tiles64 = (rows + 63) / 64;
         const unsigned dw_ctas = (unsigned)std::min<int64_t>(n_tiles64, 32);
