@@ -149,8 +149,9 @@ def test_rollout_modules_vs_reference_golden(golden_dir):
             batch.update({"actions": st["actions"]}, ts=t, mark_filled=False)
 
 
-def test_gat_highway_shape_vs_oracle():
-    """B=6 envs x 5 agent-nets x 55 slots (Highway), seeded inputs, explicit noise:
+@pytest.mark.parametrize("B", [6, 3])
+def test_gat_highway_shape_vs_oracle(B):
+    """B envs (even / odd: the recurrence kernel packs two environments per CTA) x 5 agent-nets x 55 slots (Highway), seeded inputs, explicit noise:
     CUDA vs the CPU oracle.  Reports ill-conditioned edges (hard weight strictly inside
     (0.01, 0.99)) separately, as SURVEY §7 asks."""
     _need_gpu()
@@ -158,7 +159,7 @@ def test_gat_highway_shape_vs_oracle():
     from iplan_b200.nova.prediction_policy import Prediction_policy
     from oracle import iplan_oracle as O
     args = make_args("highway")
-    B, A, N, o, L, D = 6, args.n_agents, args.max_vehicle_num, args.obs_shape_single, args.latent_dim, args.attention_dim
+    A, N, o, L, D = args.n_agents, args.max_vehicle_num, args.obs_shape_single, args.latent_dim, args.attention_dim
     torch.manual_seed(5)
     pred = Prediction_policy(args, None)
     params = [{k: v.detach().cpu().clone() for k, v in net.state_dict().items()} for net in pred.pred_GAT]
