@@ -254,3 +254,32 @@ def test_argument_checks_fail_loudly():
     assert rc != 0 and b"n_slots" in _lib.lib.iplan_last_error()
     with pytest.raises(RuntimeError):
         _lib.check(rc, "gat_step")
+
+
+def test_device_resident_runner_equals_reference_api_path():
+    """BASELINE configs[1] (Hetero-Highway mild, 5 agents, 64 envs, T = 90): the device-resident runner (kernels read
+    and write the packed EpisodeBatch in place) and the reference's call pattern (numpy in / numpy out through
+    GAT_latent_update / latent_update / EpisodeBatch.update / select_actions_ippo every timestep) are two hosts of the
+    same kernels with the same Philox streams, so a whole greedy episode must agree: same actions, same stored
+    latents / hidden states / one-hot columns."""
+    _need_gpu()
+    from iplan_b200.runners.synthetic_runner import build_system
+    sa = build_system(n_envs=64, env="highway", hazard=0.002, seed=7)
+    sb = build_system(n_envs=64, env="highway", hazard=0.002, seed=7)
+    for x, y in ((sa.mac.actor_stack, sb.mac.actor_stack), (sa.prediction.stack, sb.prediction.stack),
+                 (sa.behavior.stack, sb.behavior.stack)):
+        assert torch.equal(x.flat, y.flat)
+    ba, *_ = sa.runner.run(test_mode=True)
+    bb, *_ = sb.runner.run_reference_api(test_mode=True)
+    torch.cuda.synchronize()
+    T = sa.args.episode_limit
+    assert torch.equal(ba["actions"][:, :T], bb["actions"][:, :T])
+    for key in ("attention_latent", "behavior_latent", "history", "rnn_states_actors", "rnn_states_critics"):
+        d = maxdiff(ba[key], bb[key])
+        print(f"[runner vs api] {key}: {d:.3e}")
+        assert d <= 1e-6, (key, d)
+    F = sa.mac.input_shape
+    d = maxdiff(ba.packed[:, :, :T + 1, :F], bb.packed[:, :, :T + 1, :F])
+    print(f"[runner vs api] packed controller rows: {d:.3e}")
+    assert d <= 1e-6
+    assert torch.equal(ba["terminated"][:, :T], bb["terminated"][:, :T]) and maxdiff(ba["reward"][:, :T], bb["reward"][:, :T]) == 0.0
