@@ -479,3 +479,70 @@ def train_agent(actor_p, critic_p, batch, agent_id, args, opt_a=None, opt_c=None
         t.requires_grad_(False)
     pre = dict(values_all=v_all, returns=returns, advantages=adv, old_logp=old_lp.view(Bf, T))
     return stats, pre, opt_a, opt_c
+
+
+# ----------------------------------------------------------------------------------
+# f2  Prediction_policy.learn  (nova/prediction_policy.py:120-253), the "next" row of SURVEY §8f rank 2
+# ----------------------------------------------------------------------------------
+DECODER_KEYS = ["decoder.linear.weight", "decoder.linear.bias", "decoder.rnn.weight_ih_l0", "decoder.rnn.weight_hh_l0",
+                "decoder.rnn.bias_ih_l0", "decoder.rnn.bias_hh_l0", "decoder.out.weight", "decoder.out.bias"]
+
+
+def prediction_batch(history, attention, behavior, flag, select_idx, pred_length):
+    """prediction_batch_wrapper (nova/prediction_policy.py:123-164) for one agent-net, with the sampled
+    flat indices given: idx -> (episode idx // avail_len, time idx % avail_len), avail_len = T - pred_length - 1.
+    history [B,T,N,o], attention [B,T,N,D], behavior [B,T,N,L], flag [B,T] (the batch's ``terminated`` column, which
+    the reference multiplies the error with, :196 / :163).  Returns x0 [P,N,o], att0 [P,N,D], lat0 [P,N,L],
+    target [P,N,pred_length,o], mask [P,N,pred_length,o]."""
+    B, T = history.shape[:2]
+    avail_len = T - pred_length - 1
+    b = torch.div(select_idx, avail_len, rounding_mode="floor")
+    t = select_idx % avail_len
+    x0, att0, lat0 = history[b, t], attention[b, t], behavior[b, t]
+    target = torch.stack([history[b, t + 1 + k] for k in range(pred_length)], dim=2)          # [P,N,pl,o]
+    mask = flag[b, t].to(history.dtype).view(-1, 1, 1, 1).expand_as(target)
+    return x0, att0, lat0, target, mask
+
+
+def prediction_decoder(dp, last_state, hidden, pred_length, keep, p_drop):
+    """Prediction_Decoder.forward with teacher_forcing_ratio = 0 (nova/prediction_net.py:37-63) around
+    DecoderRNN.forward (:19-27): ReLU(linear) -> 1-step GRU -> tanh -> dropout -> out, fed back on itself.
+    last_state [P,N,o]; hidden [P*N,D]; keep [pred_length, P*N, D] booleans (the dropout draw)."""
+    P, N, o = last_state.shape
+    h = hidden
+    x = last_state.reshape(P * N, o)
+    outs = []
+    for t in range(pred_length):
+        u = F.relu(x @ dp["decoder.linear.weight"].t() + dp["decoder.linear.bias"])
+        gi = u @ dp["decoder.rnn.weight_ih_l0"].t() + dp["decoder.rnn.bias_ih_l0"]
+        h = gru_cell(gi, h, dp["decoder.rnn.weight_hh_l0"], dp["decoder.rnn.bias_hh_l0"])
+        y = torch.tanh(h) * keep[t].to(h.dtype) / (1.0 - p_drop)
+        x = y @ dp["decoder.out.weight"].t() + dp["decoder.out.bias"]
+        outs.append(x)
+    return torch.stack(outs, dim=1).view(P, N, pred_length, o)
+
+
+def prediction_learn_agent(gat_p, dec_p, history, attention, behavior, flag, select_idx, gumbel, keep, args, opt=None):
+    """One agent-net's share of Prediction_policy.learn (:183-244): GAT forward on the sampled transitions,
+    pred_length-step decoder roll-out, masked L1 loss (:228-230), separate clip_grad_norm_ of the GAT and the decoder
+    gradients (:236-243), ONE Adam over both parameter lists (:84-90).  Updates the dicts in place."""
+    pl, o = args.pred_length, history.shape[-1]
+    x0, att0, lat0, target, mask = prediction_batch(history, attention, behavior, flag, select_idx, pl)
+    P, N = x0.shape[:2]
+    gat_keys = list(gat_p.keys())
+    g_tr = [gat_p[k].requires_grad_(True) for k in gat_keys]
+    d_tr = [dec_p[k].requires_grad_(True) for k in DECODER_KEYS]
+    hidden = gat_forward(gat_p, torch.cat([x0, lat0], dim=-1), att0.reshape(P * N, -1), gumbel)
+    pred = prediction_decoder(dec_p, x0, hidden, pl, keep.reshape(pl, P * N, -1), args.decoder_dropout)
+    loss = ((target - pred).abs() * mask).sum() / (mask.sum() + 1e-10) * o * pl
+    grads = torch.autograd.grad(loss, g_tr + d_tr)
+    g_g, n_g = clip_grads(list(grads[:len(g_tr)]), args.max_grad_norm)
+    g_d, n_d = clip_grads(list(grads[len(g_tr):]), args.max_grad_norm)
+    opt = opt or AdamState(g_tr + d_tr, args.lr_predict, args.optim_eps)
+    with torch.no_grad():
+        opt.step(g_g + g_d)
+    for t in g_tr + d_tr:
+        t.requires_grad_(False)
+    return dict(loss=float(loss.detach()), gat_grad_norm=float(n_g), dec_grad_norm=float(n_d),
+                grads=dict(zip(gat_keys + DECODER_KEYS, [g.detach() for g in grads])),
+                clipped=dict(zip(gat_keys + DECODER_KEYS, [g.detach() for g in g_g + g_d]))), opt

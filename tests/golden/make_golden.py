@@ -329,12 +329,100 @@ def golden_learner():
     torch.save(cases, os.path.join(HERE, "learner.pt"))
 
 
+def golden_prediction_learn():
+    """Prediction_policy.learn (nova/prediction_policy.py:168-253) — one call on a seeded EpisodeBatch.
+    The random draws of the call are recorded while the reference runs: the sampled (episode, time) indices
+    (np.random.choice, :147), the Gumbel noise of GAT_Net.forward (F.gumbel_softmax, GAT_Net.py:93 — wrapped by a
+    recorder that does the same arithmetic as torch's implementation) and the decoder's dropout masks
+    (nn.Dropout in train mode, prediction_net.py:18,27 — read off a forward hook).
+    Case "mpe": A=3, N=6, 4 episodes x T=12, pred_batch 8.  Case "highway": one agent, N=55, 3 episodes x T=12, pred_batch 6."""
+    import torch.nn.functional as Fn
+    from nova.prediction_policy import Prediction_policy
+    from components.episode_buffer import EpisodeBatch
+
+    cases = {}
+    for name, env, over in (
+            ("mpe", "MPE", dict(episode_length=12, batch_size_run=4, pred_batch_size=8)),
+            ("highway", "highway", dict(n_agents=1, n_other_vehicles=54, episode_limit=12, batch_size_run=3, pred_batch_size=6))):
+        args = ref_args(env, **over)
+        A, N, o = args.n_agents, args.max_vehicle_num, args.obs_shape_single
+        L, D, T, B = args.latent_dim, args.attention_dim, args.episode_limit, args.batch_size_run
+        torch.manual_seed(99 + N)
+        logger = NullLogger()
+        pol = Prediction_policy(args, logger)
+        scheme, groups, preprocess = make_scheme(args)
+        batch = EpisodeBatch(scheme, groups, B, T + 1, preprocess=preprocess, device="cpu")
+        rng = np.random.default_rng(2024 + N)
+        data = dict(
+            history=np.stack([synth_history(rng, B, A, N, o, min(N, 3 + 2 * t)) for t in range(T + 1)], axis=1),
+            attention_latent=rng.uniform(-1, 1, size=(B, T + 1, A, N, D)).astype(np.float32),
+            behavior_latent=rng.dirichlet(np.ones(L), size=(B, T + 1, A, N)).astype(np.float32),
+        )
+        term = np.ones((B, T + 1, A, 1), dtype=np.uint8)       # the reference multiplies the error by this flag (:196, :163)
+        term[0, 3:6, 0] = 0
+        term[B - 1, :2, A - 1] = 0
+        data["terminated"] = term
+        batch.update(data, bs=slice(None), ts=slice(None))
+
+        rec = dict(args={k: v for k, v in vars(args).items() if isinstance(v, (int, float, str, bool))},
+                   data={k: torch.as_tensor(v) for k, v in data.items()},
+                   gat_before=[sd_clone(m) for m in pol.pred_GAT], dec_before=[sd_clone(m) for m in pol.pred_decoder])
+
+        gumbels, drop_masks = [], [[] for _ in range(A)]
+        orig_gs = Fn.gumbel_softmax
+
+        def recording_gumbel_softmax(logits, tau=1, hard=False, eps=1e-10, dim=-1):
+            assert not hard
+            g = -torch.empty_like(logits).exponential_().log()       # torch/nn/functional.py gumbel_softmax
+            gumbels.append(g.detach().clone())
+            return ((logits + g) / tau).softmax(dim)
+
+        hooks = []
+        for i in range(A):
+            def hook(mod, inp, out, i=i):
+                x = inp[0].detach()
+                assert bool((x != 0).all())
+                drop_masks[i].append((out.detach() != 0).clone())
+            hooks.append(pol.pred_decoder[i].decoder.dropout.register_forward_hook(hook))
+
+        seed = 1618
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        Fn.gumbel_softmax = recording_gumbel_softmax
+        try:
+            losses = pol.learn(batch, t_env=0)
+        finally:
+            Fn.gumbel_softmax = orig_gs
+            for h in hooks:
+                h.remove()
+        # replay the numpy stream: per agent one choice(...) then pred_length x random() (prediction_net.py:55)
+        np.random.seed(seed)
+        avail_len = T - args.pred_length - 1
+        idx = []
+        for i in range(A):
+            idx.append(torch.as_tensor(np.random.choice(B * avail_len, size=args.pred_batch_size, replace=False)))
+            for _ in range(args.pred_length):
+                np.random.random()
+        assert len(gumbels) == A and all(len(m) == args.pred_length for m in drop_masks)
+        rec.update(select_idx=idx, gumbel=[g.view(args.pred_batch_size, N, N - 1, 2) for g in gumbels],
+                   dropout_keep=[torch.stack(m) for m in drop_masks],
+                   losses=[float(x) for x in losses], stats=dict(logger.stats),
+                   gat_after=[sd_clone(m) for m in pol.pred_GAT], dec_after=[sd_clone(m) for m in pol.pred_decoder],
+                   # .grad after learn() = the gradients as clipped in place by clip_grad_norm_ (:236-243)
+                   gat_grads=[{k: v.grad.detach().clone() for k, v in m.named_parameters()} for m in pol.pred_GAT],
+                   dec_grads=[{k: v.grad.detach().clone() for k, v in m.named_parameters()} for m in pol.pred_decoder])
+        cases[name] = rec
+        print("prediction.learn", name, [round(float(x), 6) for x in losses])
+    torch.save(cases, os.path.join(HERE, "prediction_learn.pt"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_config()
     golden_gat()
     golden_rollout_modules()
     golden_learner()
+    golden_prediction_learn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

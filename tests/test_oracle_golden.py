@@ -110,3 +110,38 @@ def test_learner_matches_reference(golden_dir, case):
 def test_one_sided_huber():
     e = torch.tensor([-20.0, -5.0, 0.0, 5.0, 20.0])
     assert O.huber_one_sided(e, 10.0).tolist() == [0.0, 12.5, 0.0, 12.5, 150.0]
+
+
+@pytest.mark.parametrize("case", ["mpe", "highway"])
+def test_prediction_learn_matches_reference(golden_dir, case):
+    """SURVEY §8f rank 2 — Prediction_policy.learn: the oracle (autograd through the oracle's own GAT forward, the
+    restated decoder, the masked L1 loss, two-group gradient clipping, one Adam) against one call of the reference's
+    ``learn`` with its random draws recorded (tests/golden/make_golden.py::golden_prediction_learn)."""
+    from types import SimpleNamespace
+    g = torch.load(os.path.join(golden_dir, "prediction_learn.pt"), weights_only=False)[case]
+    args = SimpleNamespace(**g["args"])
+    d = g["data"]
+    A = args.n_agents
+    hist, att, beh = d["history"][:, :-1], d["attention_latent"][:, :-1], d["behavior_latent"][:, :-1]
+    flag = d["terminated"][:, :-1, :, 0]
+    for a in range(A):
+        gp = {k: v.clone() for k, v in g["gat_before"][a].items()}
+        dp = {k: v.clone() for k, v in g["dec_before"][a].items()}
+        out, _ = O.prediction_learn_agent(gp, dp, hist[:, :, a], att[:, :, a], beh[:, :, a], flag[:, :, a],
+                                          g["select_idx"][a], g["gumbel"][a], g["dropout_keep"][a], args)
+        assert abs(out["loss"] - g["losses"][a]) < 1e-5 * max(1.0, abs(g["losses"][a])), (a, out["loss"], g["losses"][a])
+        worst = max(float((gp[k] - g["gat_after"][a][k]).abs().max()) for k in gp)
+        worst = max(worst, max(float((dp[k] - g["dec_after"][a][k]).abs().max()) for k in dp))
+        moved = max(float((g["gat_after"][a][k] - g["gat_before"][a][k]).abs().max()) for k in gp)
+        print(f"[prediction.learn {case} a={a}] loss {out['loss']:.6f} (reference {g['losses'][a]:.6f}); "
+              f"max |param - reference| after the step {worst:.2e} (the step moved them by {moved:.2e})")
+        assert worst < 2e-7 and moved > 1e-6
+        # Adam's first step is ~lr * sign(g): compare the gradients themselves (as clipped by the reference)
+        ref_g = {**g["gat_grads"][a], **g["dec_grads"][a]}
+        rel = max(float((out["clipped"][k] - ref_g[k]).abs().max() / (ref_g[k].abs().max() + 1e-12)) for k in ref_g)
+        print(f"[prediction.learn {case} a={a}] worst relative gradient difference {rel:.2e}; "
+              f"norms GAT {out['gat_grad_norm']:.4f} decoder {out['dec_grad_norm']:.4f}")
+        assert rel < 2e-4
+    stats = g["stats"]
+    key = [k for k in stats if k.endswith("prediction_loss")][0]
+    assert abs(stats[key] - sum(g["losses"])) < 1e-4 * abs(stats[key])
