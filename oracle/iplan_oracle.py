@@ -546,3 +546,79 @@ def prediction_learn_agent(gat_p, dec_p, history, attention, behavior, flag, sel
     return dict(loss=float(loss.detach()), gat_grad_norm=float(n_g), dec_grad_norm=float(n_d),
                 grads=dict(zip(gat_keys + DECODER_KEYS, [g.detach() for g in grads])),
                 clipped=dict(zip(gat_keys + DECODER_KEYS, [g.detach() for g in g_g + g_d]))), opt
+
+
+# ----------------------------------------------------------------------------------
+# f3  Behavior_policy.learn  (nova/stable_behavior_policy.py:124-279), SURVEY §8f rank 3
+# ----------------------------------------------------------------------------------
+BEH_ENCODER_KEYS = ["linear.weight", "linear.bias", "rnn.weight_ih_l0", "rnn.weight_hh_l0", "rnn.bias_ih_l0",
+                    "rnn.bias_hh_l0", "out.weight", "out.bias"]
+
+
+def behavior_windows(history, step, W):
+    """behavior_traj_wrapper (:127-157): the W-step window ending at ``step`` (zero padded in front) and the W steps
+    that follow it.  history [B,T,N,o] -> curr, next [B,N,W,o]."""
+    B, T, N, o = history.shape
+    start = max(0, step - W + 1)
+    plug = max(0, W - step - 1)
+    curr = torch.zeros(B, N, W, o, dtype=history.dtype)
+    curr[:, :, plug:] = history[:, start:step + 1].permute(0, 2, 1, 3)
+    nxt = history[:, step + 1:step + W + 1].permute(0, 2, 1, 3)
+    return curr, nxt
+
+
+def behavior_decoder(dp, curr, latent, hidden, keep, p_drop):
+    """Behavior_Latent_Decoder.forward (nova/behavior_net.py:57-72) + DecoderRNN.forward (:40-47): the window with the
+    latent tiled on every step -> ReLU(linear) -> GRU over the W steps from the carried hidden -> tanh -> dropout -> out.
+    curr [B,N,W,o], latent [B,N,L], hidden [B*N,Hd], keep [B*N,W,Hd] -> (pred [B,N,W,o], new hidden)."""
+    B, N, W, o = curr.shape
+    x = torch.cat([curr, latent.unsqueeze(2).expand(B, N, W, latent.shape[-1])], dim=-1).reshape(B * N, W, -1)
+    u = F.relu(x @ dp["decoder.linear.weight"].t() + dp["decoder.linear.bias"])
+    h, outs = hidden, []
+    for t in range(W):
+        gi = u[:, t] @ dp["decoder.rnn.weight_ih_l0"].t() + dp["decoder.rnn.bias_ih_l0"]
+        h = gru_cell(gi, h, dp["decoder.rnn.weight_hh_l0"], dp["decoder.rnn.bias_hh_l0"])
+        outs.append(h)
+    y = torch.tanh(torch.stack(outs, dim=1)) * keep.to(u.dtype) / (1.0 - p_drop)
+    pred = y @ dp["decoder.out.weight"].t() + dp["decoder.out.bias"]
+    return pred.view(B, N, W, o), h
+
+
+def behavior_learn_agent(enc_p, dec_p, history, mask, keep, args, opt=None):
+    """One agent-net's share of Behavior_policy.learn (:183-262).  history [B,T,N,o] (the batch without its last
+    step), mask [B,T] (``terminated`` on Highway, ``1 - terminated`` on MPE, :186-189), keep [T-1-W, B*N, W, Hd].
+    The encoder / decoder hidden states and the soft-updated latent are carried — with their graph — across all
+    window positions, so the backward is one BPTT over (T-1-W) x W steps.  Updates the dicts in place."""
+    B, T, N, o = history.shape
+    W, L = args.max_history_len, args.latent_dim
+    e_tr = [enc_p[k].requires_grad_(True) for k in BEH_ENCODER_KEYS]
+    d_tr = [dec_p[k].requires_grad_(True) for k in DECODER_KEYS]
+    latent = torch.zeros(B, N, L)
+    eh = torch.zeros(B * N, args.encoder_rnn_dim)
+    dh = torch.zeros(B * N, args.decoder_rnn_dim)
+    n_pos = T - 1 - W
+    b_err, s_err = 0.0, 0.0
+    for j in range(n_pos):
+        curr, nxt = behavior_windows(history, j, W)
+        m_next = mask[:, j + 1:j + 1 + W].to(history.dtype).view(B, 1, W, 1).expand(B, N, W, o)
+        pred, dh = behavior_decoder(dec_p, curr, latent, dh, keep[j], args.decoder_dropout)
+        eh, new_latent = behavior_encoder(enc_p, curr.reshape(B * N, W, o), eh)
+        stab = torch.linalg.norm(curr - pred, dim=-1).reshape(-1)
+        latent = (1 - args.soft_update_coef) * latent + new_latent.view(B, N, L) * args.soft_update_coef
+        err = (nxt - pred).abs() * m_next
+        b_err = b_err + err.sum() / (m_next.sum() + 1e-10) * o * N
+        s_err = s_err + torch.clamp(stab - args.thres_small_variation, min=0).sum() / B / W
+    b_err, s_err = b_err / n_pos, s_err / n_pos
+    loss = b_err + args.behavior_variation_penalty * s_err
+    grads = torch.autograd.grad(loss, e_tr + d_tr)
+    g_e, n_e = clip_grads(list(grads[:len(e_tr)]), args.max_grad_norm)
+    g_d, n_d = clip_grads(list(grads[len(e_tr):]), args.max_grad_norm)
+    opt = opt or AdamState(e_tr + d_tr, args.lr_behavior, args.optim_eps)
+    with torch.no_grad():
+        opt.step(g_e + g_d)
+    for t in e_tr + d_tr:
+        t.requires_grad_(False)
+    return dict(behavior_loss=float(b_err.detach()), stability_loss=float(s_err.detach()), loss=float(loss.detach()),
+                enc_grad_norm=float(n_e), dec_grad_norm=float(n_d),
+                clipped=dict(zip(["enc:" + k for k in BEH_ENCODER_KEYS] + ["dec:" + k for k in DECODER_KEYS],
+                                 [g.detach() for g in g_e + g_d]))), opt

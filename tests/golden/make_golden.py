@@ -416,6 +416,64 @@ def golden_prediction_learn():
     torch.save(cases, os.path.join(HERE, "prediction_learn.pt"))
 
 
+def golden_behavior_learn():
+    """Behavior_policy.learn (nova/stable_behavior_policy.py:161-279) — one call on a seeded EpisodeBatch.  The only
+    random draw is the decoder's dropout (behavior_net.py:37,46; train mode), read off a forward hook.
+    Case "mpe": A=3, N=6, 3 episodes x T=15 (4 window positions).  Case "highway": one agent, N=55, 2 episodes x T=13."""
+    from nova.stable_behavior_policy import Behavior_policy
+    from components.episode_buffer import EpisodeBatch
+
+    cases = {}
+    for name, env, over in (
+            ("mpe", "MPE", dict(episode_length=15, batch_size_run=3)),
+            ("highway", "highway", dict(n_agents=1, n_other_vehicles=54, episode_limit=13, batch_size_run=2))):
+        args = ref_args(env, **over)
+        A, N, o = args.n_agents, args.max_vehicle_num, args.obs_shape_single
+        L, D, T, B = args.latent_dim, args.attention_dim, args.episode_limit, args.batch_size_run
+        torch.manual_seed(555 + N)
+        logger = NullLogger()
+        pol = Behavior_policy(args, logger)
+        scheme, groups, preprocess = make_scheme(args)
+        batch = EpisodeBatch(scheme, groups, B, T + 1, preprocess=preprocess, device="cpu")
+        rng = np.random.default_rng(4048 + N)
+        data = dict(
+            history=np.stack([synth_history(rng, B, A, N, o, min(N, 3 + 2 * t)) for t in range(T + 1)], axis=1),
+            behavior_latent=rng.dirichlet(np.ones(L), size=(B, T + 1, A, N)).astype(np.float32),
+        )
+        term = np.zeros((B, T + 1, A, 1), dtype=np.uint8)
+        term[0, 11:, 0] = 1
+        term[B - 1, 12:, A - 1] = 1
+        if env != "MPE":
+            term = 1 - term        # highway: the flag is used as the mask directly (:186-189)
+        data["terminated"] = term.astype(np.uint8)
+        batch.update(data, bs=slice(None), ts=slice(None))
+        rec = dict(args={k: v for k, v in vars(args).items() if isinstance(v, (int, float, str, bool))},
+                   data={k: torch.as_tensor(v) for k, v in data.items()},
+                   enc_before=[sd_clone(m) for m in pol.behavior_encoder], dec_before=[sd_clone(m) for m in pol.behavior_decoder])
+        drop = [[] for _ in range(A)]
+        hooks = []
+        for i in range(A):
+            def hook(mod, inp, out, i=i):
+                assert bool((inp[0].detach() != 0).all())
+                drop[i].append((out.detach() != 0).clone())
+            hooks.append(pol.behavior_decoder[i].decoder.dropout.register_forward_hook(hook))
+        torch.manual_seed(2236)
+        try:
+            b_loss, s_loss, t_loss = pol.learn(batch, t_env=0)
+        finally:
+            for h in hooks:
+                h.remove()
+        rec.update(dropout_keep=[torch.stack(m) for m in drop],
+                   behavior_loss=[float(x) for x in b_loss], stability_loss=[float(x) for x in s_loss],
+                   total_loss=[float(x) for x in t_loss], stats=dict(logger.stats),
+                   enc_after=[sd_clone(m) for m in pol.behavior_encoder], dec_after=[sd_clone(m) for m in pol.behavior_decoder],
+                   enc_grads=[{k: v.grad.detach().clone() for k, v in m.named_parameters()} for m in pol.behavior_encoder],
+                   dec_grads=[{k: v.grad.detach().clone() for k, v in m.named_parameters()} for m in pol.behavior_decoder])
+        cases[name] = rec
+        print("behavior.learn", name, [round(float(x), 6) for x in b_loss], [round(float(x), 6) for x in s_loss])
+    torch.save(cases, os.path.join(HERE, "behavior_learn.pt"))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_config()
@@ -423,6 +481,7 @@ if __name__ == "__main__":
     golden_rollout_modules()
     golden_learner()
     golden_prediction_learn()
+    golden_behavior_learn()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

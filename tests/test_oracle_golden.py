@@ -145,3 +145,29 @@ def test_prediction_learn_matches_reference(golden_dir, case):
     stats = g["stats"]
     key = [k for k in stats if k.endswith("prediction_loss")][0]
     assert abs(stats[key] - sum(g["losses"])) < 1e-4 * abs(stats[key])
+
+
+@pytest.mark.parametrize("case", ["mpe", "highway"])
+def test_behavior_learn_matches_reference(golden_dir, case):
+    """SURVEY §8f rank 3 — Behavior_policy.learn against one call of the reference's ``learn`` with its dropout draws
+    recorded: losses, the gradients as clipped by the reference (BPTT across every window position), post-step weights."""
+    from types import SimpleNamespace
+    g = torch.load(os.path.join(golden_dir, "behavior_learn.pt"), weights_only=False)[case]
+    args = SimpleNamespace(**g["args"])
+    d = g["data"]
+    hist = d["history"][:, :-1]
+    term = d["terminated"][:, :-1, :, 0].float()
+    for a in range(args.n_agents):
+        mask = 1 - term[:, :, a] if args.env == "MPE" else term[:, :, a]
+        ep = {k: v.clone() for k, v in g["enc_before"][a].items()}
+        dp = {k: v.clone() for k, v in g["dec_before"][a].items()}
+        out, _ = O.behavior_learn_agent(ep, dp, hist[:, :, a], mask, g["dropout_keep"][a], args)
+        assert abs(out["behavior_loss"] - g["behavior_loss"][a]) < 2e-5 * abs(g["behavior_loss"][a])
+        assert abs(out["stability_loss"] - g["stability_loss"][a]) < 2e-5 * abs(g["stability_loss"][a])
+        ref_g = {**{"enc:" + k: v for k, v in g["enc_grads"][a].items()}, **{"dec:" + k: v for k, v in g["dec_grads"][a].items()}}
+        rel = max(float((out["clipped"][k] - ref_g[k]).abs().max() / (ref_g[k].abs().max() + 1e-12)) for k in ref_g)
+        worst = max(max(float((ep[k] - g["enc_after"][a][k]).abs().max()) for k in ep),
+                    max(float((dp[k] - g["dec_after"][a][k]).abs().max()) for k in dp))
+        print(f"[behavior.learn {case} a={a}] loss {out['behavior_loss']:.6f} (reference {g['behavior_loss'][a]:.6f}); "
+              f"worst relative gradient difference {rel:.2e}; max |param - reference| after the step {worst:.2e}")
+        assert rel < 5e-4 and worst < 1e-6
