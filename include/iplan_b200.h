@@ -131,6 +131,18 @@ int iplan_controller_step(const float* actor_params, int64_t actor_stride,
                           int n_envs, int n_agents, int feat_dim, int n_actions,
                           void* stream);
 
+/* ---- observation-history wrapper step ------------------------------
+ * replaces observersation_state_history_wrapper.obs_history_create + obs_history_output +
+ * obs_single_history_output (observation_wrapper.py:68-141) for one timestep:
+ *   obs        [B][A][n_obs][obs_dim] raw observation rows, column 0 = vehicle id, all-zero rows = nothing observed
+ *   slot_ids   [B][A][n_slots] int32 state: ids in first-seen order (slot = position); slot_count [B][A] (zero both to reset)
+ *   window     [B][A][n_slots][hist_len][obs_dim-1] state and output: the last hist_len history rows of every slot
+ *   single     [B][A][n_slots][obs_dim-1] output: the row appended this step (zeros for unobserved slots)
+ *   overflow   [1] set to 1 if an agent met more than n_slots distinct ids (the reference raises IndexError) */
+int iplan_obs_history_step(const float* obs, int n_envs, int n_agents, int n_obs, int obs_dim,
+                           int32_t* slot_ids, int32_t* slot_count, float* window, float* single,
+                           int32_t* overflow, int n_slots, int hist_len, void* stream);
+
 /* ==== IPPO learner (IPPOLearner.train, learners/ippo_learner.py:227-317) ===============
  * All agents are processed together.  Agent a's input matrix is X_a[rows][ldx] with
  * rows = n_eps*(T+1), row (b,t) at index b*(T+1)+t — the packed EpisodeBatch layout.

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "iplan_controller_step": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64,
                                    _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p,
                                    _i, _i, _i, _i, _p]),
+    "iplan_obs_history_step": (_i, [_p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p]),
     "iplan_learner_row_stats": (_i, [_p, _i64, _i, _i, _i64, _i, _p, _p]),
     "iplan_learner_x_split": (_i, [_p, _i64, _p, _p, _p]),
     "iplan_learner_fc1_forward": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p, _p]),

@@ -622,3 +622,36 @@ def behavior_learn_agent(enc_p, dec_p, history, mask, keep, args, opt=None):
                 enc_grad_norm=float(n_e), dec_grad_norm=float(n_d),
                 clipped=dict(zip(["enc:" + k for k in BEH_ENCODER_KEYS] + ["dec:" + k for k in DECODER_KEYS],
                                  [g.detach() for g in g_e + g_d]))), opt
+
+
+# ----------------------------------------------------------------------------------
+# f4  observation-history wrapper  (observation_wrapper.py:68-141), SURVEY §8f rank 4
+# ----------------------------------------------------------------------------------
+class ObsHistory:
+    """observersation_state_history_wrapper restated without the per-slot deques: ``ids[k][i]`` is the first-seen-order
+    id list (:82-88), ``win`` [B,A,N,W,o] the last W rows of every slot (:101-119), ``single`` the newest row (:124-141).
+    A slot that does not exist yet has an all-zero window, so appending a zero row to it is a no-op and the update is
+    one shift-and-append over all N slots."""
+
+    def __init__(self, B, A, N, W, o):
+        import numpy as np
+        self.ids = [[[] for _ in range(A)] for _ in range(B)]
+        self.win = np.zeros((B, A, N, W, o), dtype=np.float32)
+        self.single = np.zeros((B, A, N, o), dtype=np.float32)
+
+    def step(self, obs):
+        import numpy as np
+        B, A, M, od = obs.shape
+        new = np.zeros_like(self.single)
+        for k in range(B):
+            for i in range(A):
+                ids = self.ids[k][i]
+                for j in range(M):
+                    if np.any(obs[k, i, j, :]):                       # :80
+                        vid = int(obs[k, i, j, 0])                    # :81
+                        if vid not in ids:
+                            ids.append(vid)                           # :84
+                        new[k, i, ids.index(vid)] = obs[k, i, j, 1:]  # :90
+        self.win = np.concatenate([self.win[:, :, :, 1:], new[:, :, :, None]], axis=3)
+        self.single = new
+        return self.win, self.single

@@ -474,6 +474,40 @@ def golden_behavior_learn():
     torch.save(cases, os.path.join(HERE, "behavior_learn.pt"))
 
 
+def golden_obs_wrapper():
+    """observersation_state_history_wrapper (observation_wrapper.py): 14 timesteps of synthetic raw observations in
+    which vehicles enter, leave and re-enter the agents' view; records every step's obs_history_output and
+    obs_single_history_output."""
+    from observation_wrapper import observersation_state_history_wrapper as RefWrapper
+    args = ref_args("highway", batch_size_run=3)
+    B, A, N, W, o = 3, args.n_agents, args.max_vehicle_num, args.max_history_len, args.obs_shape_single
+    M = 15                                                   # n_obs_vehicles (config/envs/highway.yaml:8)
+    wr = RefWrapper(args, A, N, args.episode_limit, W)
+    rng = np.random.default_rng(31)
+    steps = []
+    pool = np.arange(1000, 1000 + 40)                        # vehicle ids an agent may meet (< N distinct)
+    for t in range(14):
+        obs = np.zeros((B, A, M, o + 1))
+        for k in range(B):
+            for i in range(A):
+                n_seen = rng.integers(3, M + 1)
+                seen = rng.choice(pool[:20 + t], size=n_seen - 1, replace=False)
+                obs[k, i, 0, 0] = 7 + i                      # ego first (:73)
+                obs[k, i, 0, 1:] = rng.uniform(-1, 1, size=o)
+                obs[k, i, 1:n_seen, 0] = seen
+                obs[k, i, 1:n_seen, 1:] = rng.uniform(-1, 1, size=(n_seen - 1, o))
+        if t == 0:
+            wr.agent_obs_profile_init(obs)
+        wr.obs_history_create(obs)
+        single = wr.obs_single_history_output().copy()
+        window = wr.obs_history_output().copy()
+        steps.append(dict(obs=torch.tensor(obs, dtype=torch.float32), single=torch.tensor(single, dtype=torch.float32),
+                          window=torch.tensor(window, dtype=torch.float32)))
+    ids = [[list(wr.obs_vehicle_id[k][i]) for i in range(A)] for k in range(B)]
+    torch.save(dict(dims=dict(B=B, A=A, N=N, W=W, o=o, M=M), steps=steps, ids=ids), os.path.join(HERE, "obs_wrapper.pt"))
+    print("obs_wrapper: slots used", max(len(x) for r in ids for x in r))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     golden_config()
@@ -482,6 +516,7 @@ if __name__ == "__main__":
     golden_learner()
     golden_prediction_learn()
     golden_behavior_learn()
+    golden_obs_wrapper()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")

@@ -283,3 +283,34 @@ def test_device_resident_runner_equals_reference_api_path():
     print(f"[runner vs api] packed controller rows: {d:.3e}")
     assert d <= 1e-6
     assert torch.equal(ba["terminated"][:, :T], bb["terminated"][:, :T]) and maxdiff(ba["reward"][:, :T], bb["reward"][:, :T]) == 0.0
+
+
+def test_obs_history_kernel_vs_reference_golden(golden_dir):
+    """iplan_obs_history_step through the reference-named wrapper class: slot assignment in first-seen order, windows and
+    newest rows bit-equal to the reference's wrapper over 14 recorded timesteps; the device window feeds K1b's layout."""
+    _need_gpu()
+    from iplan_b200.config import make_args
+    from iplan_b200.observation_wrapper import observersation_state_history_wrapper as Wrapper
+    g = load(golden_dir, "obs_wrapper.pt")
+    d = g["dims"]
+    args = make_args("highway", batch_size_run=d["B"], use_cuda=True, device="cuda")
+    wr = Wrapper(args, d["A"], d["N"], args.episode_limit, d["W"])
+    for t, st in enumerate(g["steps"]):
+        obs = st["obs"].numpy()
+        if t == 0:
+            wr.agent_obs_profile_init(obs)
+        wr.obs_history_create(obs)
+        single, window = wr.obs_single_history_output(), wr.obs_history_output()
+        assert single.dtype == np.float32 and window.shape == tuple(st["window"].shape)
+        assert (single == st["single"].numpy()).all(), t
+        assert (window == st["window"].numpy()).all(), t
+    ids = wr.slot_ids.cpu()
+    for k in range(d["B"]):
+        for i in range(d["A"]):
+            ref = g["ids"][k][i]
+            assert ids[k, i, :len(ref)].tolist() == ref and int(wr.slot_count[k, i]) == len(ref)
+    assert wr.window.view(d["B"], d["A"], d["N"], -1).permute(1, 0, 2, 3).stride(3) == 1      # K1b's [A,B,N,W*o] view
+    # a second episode starts from a clean table
+    wr.agent_obs_profile_init(g["steps"][0]["obs"].numpy())
+    wr.obs_history_create(g["steps"][0]["obs"].numpy())
+    assert (wr.obs_history_output() == g["steps"][0]["window"].numpy()).all()

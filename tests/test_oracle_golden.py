@@ -171,3 +171,16 @@ def test_behavior_learn_matches_reference(golden_dir, case):
         print(f"[behavior.learn {case} a={a}] loss {out['behavior_loss']:.6f} (reference {g['behavior_loss'][a]:.6f}); "
               f"worst relative gradient difference {rel:.2e}; max |param - reference| after the step {worst:.2e}")
         assert rel < 5e-4 and worst < 1e-6
+
+
+def test_obs_history_matches_reference(golden_dir):
+    """SURVEY §8f rank 4 — the observation-history wrapper restated as one shift-and-append over the slots, against
+    14 timesteps recorded from the reference's own wrapper (vehicles enter, leave and re-enter the view)."""
+    g = torch.load(os.path.join(golden_dir, "obs_wrapper.pt"), weights_only=False)
+    d = g["dims"]
+    oh = O.ObsHistory(d["B"], d["A"], d["N"], d["W"], d["o"])
+    for t, st in enumerate(g["steps"]):
+        win, single = oh.step(st["obs"].numpy())
+        assert (win == st["window"].numpy()).all(), t
+        assert (single == st["single"].numpy()).all(), t
+    assert oh.ids == g["ids"]
