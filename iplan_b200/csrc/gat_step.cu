@@ -26,9 +26,11 @@
 //   gat_recur_kernel   grid (B, A, 2 directions), 4 warps: encode, P/Q projections of its
 //                      direction, the N chains of that direction; writes the per-edge logit
 //                      difference dl[dir][s][i] to a scratch buffer (L2 resident, 27 KB per (b,a)).
-//                      ~66 KB smem, <= 168 registers -> 3 CTAs (12 warps) per SM, and CTAs in
-//                      different phases overlap on an SM.
-//   gat_attend_kernel  grid (B, A), 8 warps: encode, q/k/v, hard x soft attention, GRUCell.
+//                      56 KB smem, 126 registers -> 4 CTAs (16 warps) per SM, and CTAs in
+//                      different phases overlap on an SM.  Gate math on packed fp32 pairs
+//                      (FADD2 / FMUL2 / FFMA2), four sigmoid denominators per rcp.approx.
+//   gat_attend_kernel  grid (B, A), 8 warps: encode, q|k|v, scores and aggregation as MMA
+//                      products around a warp-per-ego soft-max x gumbel gate, GRUCell.
 //
 // HBM traffic per (b,a): read N*(o+L+32) floats, write N*32 floats; weights (28.8k floats)
 // and the dl scratch come from L2.
