@@ -655,3 +655,116 @@ class ObsHistory:
         self.win = np.concatenate([self.win[:, :, :, 1:], new[:, :, :, None]], axis=3)
         self.single = new
         return self.win, self.single
+
+
+# ----------------------------------------------------------------------------------
+# f2'  GAT_Net backward written out by hand — the arithmetic the K1 backward kernels will implement
+#      (checked against autograd through gat_forward in tests/test_oracle_golden.py)
+# ----------------------------------------------------------------------------------
+def _gru_cell_backward(gi, h_prev, w_hh, b_hh, d_h):
+    """Backward of gru_cell: returns (d_gi [.,3H], d_gh [.,3H], d_h_prev [.,H]) for upstream d_h.
+    d_h_prev here is only the direct (z * d_h) path plus d_gh W_hh; weight gradients are formed by the caller."""
+    hd = h_prev.shape[-1]
+    gh = h_prev @ w_hh.t() + b_hh
+    r = torch.sigmoid(gi[..., :hd] + gh[..., :hd])
+    z = torch.sigmoid(gi[..., hd:2 * hd] + gh[..., hd:2 * hd])
+    n = torch.tanh(gi[..., 2 * hd:] + r * gh[..., 2 * hd:])
+    d_n = d_h * (1.0 - z)
+    d_z = d_h * (h_prev - n)
+    da_n = d_n * (1.0 - n * n)
+    d_r = da_n * gh[..., 2 * hd:]
+    da_z = d_z * z * (1.0 - z)
+    da_r = d_r * r * (1.0 - r)
+    d_gi = torch.cat([da_r, da_z, da_n], dim=-1)
+    d_gh = torch.cat([da_r, da_z, da_n * r], dim=-1)
+    d_h_prev = d_h * z + d_gh @ w_hh
+    return d_gi, d_gh, d_h_prev
+
+
+def gat_backward_manual(p, obs, h_prev, gumbel, d_out, tau=0.01):
+    """d(loss)/d(parameters of GAT_Net) for upstream gradient ``d_out`` [B*N, D] of gat_forward's output, written
+    as the explicit chain of products / scatters a kernel performs (no autograd).  Returns dict keyed like ``p``."""
+    B, N, _ = obs.shape
+    H = p["encoding.weight"].shape[0]
+    D = p["q.weight"].shape[0]
+    idx = neighbour_index(N)                                                     # [N, N-1]
+    g = {k: torch.zeros_like(v) for k, v in p.items()}
+    # ---- forward, keeping what the backward needs -------------------------------------------------
+    pre = obs @ p["encoding.weight"].t() + p["encoding.bias"]
+    enc = F.relu(pre)
+    dirs = []
+    for sfx, order in (("", list(range(N - 1))), ("_reverse", list(range(N - 2, -1, -1)))):
+        w_ih, w_hh = p["hard_bi_GRU.weight_ih_l0" + sfx], p["hard_bi_GRU.weight_hh_l0" + sfx]
+        b_ih, b_hh = p["hard_bi_GRU.bias_ih_l0" + sfx], p["hard_bi_GRU.bias_hh_l0" + sfx]
+        ego = enc @ w_ih[:, :H].t() + b_ih
+        nbr = enc @ w_ih[:, H:].t()
+        h = torch.zeros(B, N, H)
+        hs = torch.empty(B, N, N - 1, H)                                         # hidden AFTER each position
+        for s in order:
+            h = gru_cell(ego + nbr[:, idx[:, s], :], h, w_hh, b_hh)
+            hs[:, :, s] = h
+        dirs.append(dict(sfx=sfx, order=order, ego=ego, nbr=nbr, hs=hs))
+    hh = torch.cat([dirs[0]["hs"], dirs[1]["hs"]], dim=-1)
+    logits = hh @ p["hard_encoding.weight"].t() + p["hard_encoding.bias"]
+    hard = torch.sigmoid(((logits[..., 1] - logits[..., 0]) + (gumbel[..., 1] - gumbel[..., 0])) / tau)
+    e2 = enc.reshape(-1, H)
+    q = (e2 @ p["q.weight"].t()).view(B, N, D)
+    k = (e2 @ p["k.weight"].t()).view(B, N, D)
+    v_pre = (e2 @ p["v.weight"].t() + p["v.bias"]).view(B, N, D)
+    v = F.relu(v_pre)
+    inv = 1.0 / float(math.sqrt(D))
+    kj, vj = k[:, idx, :], v[:, idx, :]                                          # [B,N,N-1,D]
+    soft = torch.softmax(torch.einsum("bid,bisd->bis", q, kj) * inv, dim=-1)
+    w = soft * hard
+    x = torch.einsum("bis,bisd->bid", w, vj).reshape(-1, D)
+    gi_c = x @ p["rnn.weight_ih"].t() + p["rnn.bias_ih"]
+    # ---- backward -----------------------------------------------------------------------------------
+    d_gi, d_gh, _ = _gru_cell_backward(gi_c, h_prev, p["rnn.weight_hh"], p["rnn.bias_hh"], d_out)
+    g["rnn.weight_ih"] = d_gi.t() @ x; g["rnn.bias_ih"] = d_gi.sum(0)
+    g["rnn.weight_hh"] = d_gh.t() @ h_prev; g["rnn.bias_hh"] = d_gh.sum(0)
+    d_x = (d_gi @ p["rnn.weight_ih"]).view(B, N, D)
+    d_w = torch.einsum("bid,bisd->bis", d_x, vj)                                 # [B,N,N-1]
+    d_v = torch.zeros(B, N, D)
+    d_v.index_add_(1, idx.reshape(-1), (w.unsqueeze(-1) * d_x.unsqueeze(2)).reshape(B, N * (N - 1), D))
+    d_soft, d_hard = d_w * hard, d_w * soft
+    d_score = soft * (d_soft - (soft * d_soft).sum(-1, keepdim=True)) * inv
+    d_q = torch.einsum("bis,bisd->bid", d_score, kj)
+    d_k = torch.zeros(B, N, D)
+    d_k.index_add_(1, idx.reshape(-1), (d_score.unsqueeze(-1) * q.unsqueeze(2)).reshape(B, N * (N - 1), D))
+    d_delta = d_hard * hard * (1.0 - hard) / tau                                 # d / d(l1 - l0)
+    d_logits = torch.stack([-d_delta, d_delta], dim=-1)
+    g["hard_encoding.weight"] = torch.einsum("bisc,bish->ch", d_logits, hh)
+    g["hard_encoding.bias"] = d_logits.sum((0, 1, 2))
+    d_hh = d_logits @ p["hard_encoding.weight"]                                  # [B,N,N-1,2H]
+    d_enc = torch.zeros(B, N, H)
+    for di, dd in enumerate(dirs):
+        sfx = dd["sfx"]
+        w_ih, w_hh = p["hard_bi_GRU.weight_ih_l0" + sfx], p["hard_bi_GRU.weight_hh_l0" + sfx]
+        b_hh = p["hard_bi_GRU.bias_hh_l0" + sfx]
+        d_hs = d_hh[..., di * H:(di + 1) * H]
+        d_ego, d_nbr = torch.zeros(B, N, 3 * H), torch.zeros(B, N, 3 * H)
+        gw_hh, gb_hh = torch.zeros_like(w_hh), torch.zeros_like(b_hh)
+        d_h = torch.zeros(B, N, H)
+        order = dd["order"]
+        for pos in range(len(order) - 1, -1, -1):                                # BPTT, last position first
+            s = order[pos]
+            h_before = dd["hs"][:, :, order[pos - 1]] if pos > 0 else torch.zeros(B, N, H)
+            d_h = d_h + d_hs[:, :, s]
+            gi = dd["ego"] + dd["nbr"][:, idx[:, s], :]
+            dgi, dgh, d_h = _gru_cell_backward(gi, h_before, w_hh, b_hh, d_h)
+            gw_hh += torch.einsum("bng,bnh->gh", dgh, h_before); gb_hh += dgh.sum((0, 1))
+            d_ego += dgi
+            d_nbr.index_add_(1, idx[:, s], dgi)                                  # the neighbour part scatters to node j(i, s)
+        g["hard_bi_GRU.weight_hh_l0" + sfx], g["hard_bi_GRU.bias_hh_l0" + sfx] = gw_hh, gb_hh
+        g["hard_bi_GRU.weight_ih_l0" + sfx] = torch.cat([torch.einsum("bng,bnh->gh", d_ego, enc),
+                                                          torch.einsum("bng,bnh->gh", d_nbr, enc)], dim=1)
+        g["hard_bi_GRU.bias_ih_l0" + sfx] = d_ego.sum((0, 1))
+        d_enc += d_ego @ w_ih[:, :H] + d_nbr @ w_ih[:, H:]
+    d_vpre = d_v * (v_pre > 0).to(d_v.dtype)
+    g["q.weight"] = d_q.reshape(-1, D).t() @ e2
+    g["k.weight"] = d_k.reshape(-1, D).t() @ e2
+    g["v.weight"] = d_vpre.reshape(-1, D).t() @ e2; g["v.bias"] = d_vpre.sum((0, 1))
+    d_enc += d_q @ p["q.weight"] + d_k @ p["k.weight"] + d_vpre @ p["v.weight"]
+    d_pre = d_enc * (pre > 0).to(d_enc.dtype)
+    g["encoding.weight"] = torch.einsum("bnh,bni->hi", d_pre, obs); g["encoding.bias"] = d_pre.sum((0, 1))
+    return g

@@ -184,3 +184,20 @@ def test_obs_history_matches_reference(golden_dir):
         assert (win == st["window"].numpy()).all(), t
         assert (single == st["single"].numpy()).all(), t
     assert oh.ids == g["ids"]
+
+
+@pytest.mark.parametrize("case", ["mpe", "highway"])
+def test_gat_backward_by_hand_matches_autograd(golden_dir, case):
+    """The hand-written backward of GAT_Net (explicit BPTT over the bidirectional hard-attention GRU, the gumbel-sigmoid
+    gate, soft attention, GRUCell) — the arithmetic specification of the K1 backward kernels — against autograd through
+    the oracle's forward, which the prediction-learn fixture pins to the reference."""
+    g = torch.load(os.path.join(golden_dir, "gat_net.pt"), weights_only=False)[case]
+    p = {k: v.clone().requires_grad_(True) for k, v in g["params"].items()}
+    torch.manual_seed(3)
+    d_out = torch.randn_like(g["out"])
+    out = O.gat_forward(p, g["obs"], g["h_prev"], g["gumbel"])
+    auto = torch.autograd.grad((out * d_out).sum(), list(p.values()))
+    hand = O.gat_backward_manual({k: v.detach() for k, v in p.items()}, g["obs"], g["h_prev"], g["gumbel"], d_out)
+    for (k, _), ga in zip(p.items(), auto):
+        rel = float((hand[k] - ga).abs().max() / (ga.abs().max() + 1e-12))
+        assert rel < 5e-4, (k, rel)
