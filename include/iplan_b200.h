@@ -143,6 +143,25 @@ int iplan_obs_history_step(const float* obs, int n_envs, int n_agents, int n_obs
                            int32_t* slot_ids, int32_t* slot_count, float* window, float* single,
                            int32_t* overflow, int n_slots, int hist_len, void* stream);
 
+/* ---- Prediction_policy.learn (nova/prediction_policy.py:168-253) ------------------------------
+ * Arithmetic specified line by line by oracle/iplan_oracle.py (prediction_learn_agent, gat_backward_manual).
+ * One launch = forward, masked-L1 loss and backward of the GAT + trajectory decoder over P sampled transitions per
+ * agent-net; gradients are ADDED into g_gat / g_dec (zero them first; parameter-buffer layout, iplan_gat_layout /
+ * iplan_pdec_layout), the un-normalised loss sum |err| * mask into loss_sum[a].  Clip + Adam: iplan_learner_adam on the
+ * two gradient buffers.
+ *   x0 [A][P][N][o], lat0 [A][P][N][L], att0 [A][P][N][32], target [A][P][N][pred_len][o], mask [A][P] (0/1)
+ *   gumbel NULL (Philox) or [A][P][N][N-1][2]; keep NULL (Philox) or uint8 [A][P][pred_len][N][32] dropout keep flags
+ *   scale [A] = o * pred_len / (number of unmasked target elements + 1e-10)  (:230) */
+#define IPLAN_PDEC_NTENSORS 8     /* nova/prediction_net.py:7-16 (DecoderRNN inside Prediction_Decoder) */
+int64_t iplan_pdec_layout(int obs_dim, int64_t* offsets);
+int64_t iplan_pred_learn_scratch_floats(int n_agents, int n_samples, int n_slots, int obs_dim, int pred_len);
+int iplan_pred_learn(const float* gat_params, int64_t gat_stride, const float* dec_params, int64_t dec_stride,
+                     float* g_gat, float* g_dec,
+                     const float* x0, const float* lat0, const float* att0, const float* target, const float* mask,
+                     const float* gumbel, const uint8_t* keep, const float* scale, float* loss_sum,
+                     float* scratch, int64_t scratch_floats, uint64_t seed, uint64_t counter, float tau, float p_drop,
+                     int n_agents, int n_samples, int n_slots, int obs_dim, int latent_dim, int pred_len, void* stream);
+
 /* ==== IPPO learner (IPPOLearner.train, learners/ippo_learner.py:227-317) ===============
  * All agents are processed together.  Agent a's input matrix is X_a[rows][ldx] with
  * rows = n_eps*(T+1), row (b,t) at index b*(T+1)+t — the packed EpisodeBatch layout.

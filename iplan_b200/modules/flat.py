@@ -41,6 +41,14 @@ def beh_spec(obs_dim, latent_dim):
             ("out.weight", (latent_dim, H)), ("out.bias", (latent_dim,))]
 
 
+def pdec_spec(obs_dim):
+    """Prediction_Decoder -> DecoderRNN (nova/prediction_net.py:7-16, :29-35): hidden = attention_dim = H."""
+    return [("decoder.linear.weight", (H, obs_dim)), ("decoder.linear.bias", (H,)),
+            ("decoder.rnn.weight_ih_l0", (3 * H, H)), ("decoder.rnn.weight_hh_l0", (3 * H, H)),
+            ("decoder.rnn.bias_ih_l0", (3 * H,)), ("decoder.rnn.bias_hh_l0", (3 * H,)),
+            ("decoder.out.weight", (obs_dim, H)), ("decoder.out.bias", (obs_dim,))]
+
+
 def trunk_spec(feat_dim):
     """MLPBase + RNNLayer (utils/mappo_utils/mlp.py:17-22,44-48; rnn.py:13-22)."""
     return [("base.feature_norm.weight", (feat_dim,)), ("base.feature_norm.bias", (feat_dim,)),
@@ -110,11 +118,11 @@ class AgentNet(nn.Module):
 
 
 class ParamStack:
-    """[A, total] fp32 buffer + per-agent AgentNet views; `kind` in gat|beh|actor|critic."""
+    """[A, total] fp32 buffer + per-agent AgentNet views; `kind` in gat|beh|actor|critic|pdec."""
 
     def __init__(self, kind, n_agents, dims, device="cpu"):
         self.kind, self.n_agents, self.dims = kind, n_agents, tuple(dims)
-        self.spec = {"gat": gat_spec, "beh": beh_spec, "actor": actor_spec, "critic": critic_spec}[kind](*dims)
+        self.spec = {"gat": gat_spec, "beh": beh_spec, "actor": actor_spec, "critic": critic_spec, "pdec": pdec_spec}[kind](*dims)
         self.total, self.offsets = _lib.layout(kind, *dims)
         assert len(self.offsets) == len(self.spec)
         # initialise on the host (orthogonal init = QR: dozens of tiny launches on a GPU), then move
@@ -163,9 +171,9 @@ class ParamStack:
 
     def _init_tensor(self, name, p):
         k = self.kind
-        if k in ("gat", "beh"):
+        if k in ("gat", "beh", "pdec"):
             # torch defaults: Linear U(+-1/sqrt(fan_in)); GRU/GRUCell U(+-1/sqrt(hidden))
-            if "GRU" in name or name.startswith("rnn."):
+            if "GRU" in name or name.startswith("rnn.") or ".rnn." in name:
                 bound = 1.0 / math.sqrt(H)
             else:
                 fan_in = dict(self.spec)[name.rsplit(".", 1)[0] + ".weight"][1]

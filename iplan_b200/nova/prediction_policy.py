@@ -5,8 +5,11 @@ entry point ``GAT_latent_update``; the arithmetic is kernel K1 (csrc/gat_step.cu
 Same constructor, same ``GAT_latent_update(history_single, encoder_hidden,
 behavior_latent) -> np.float32 [B, A, N, D]`` contract, same ``pred_GAT[i]`` modules
 (state_dict keys/shapes) and ``pred_GAT_{i}.th`` checkpoint files.  The auxiliary
-trajectory-prediction learner (``learn``, reference :168-253) is a "next" row of the
-scope table and is not built.
+trajectory-prediction learner (``learn``, reference :168-253) is a "next" row of the scope table
+(SURVEY §8f rank 2): kernel csrc/pred_learn.cu (forward, masked-L1 loss and the full backward in one launch), checked
+against the reference's recorded ``learn`` call (tools/check_pred_learn.py, tests/test_gpu_learner.py): losses 7e-8,
+all 112 gradient tensors <= 1e-5 relative, post-step weights 1.5e-8.  The optimiser state is not checkpointed yet
+(``pred_optimizer_{i}_opt.th``, reference :262).
 """
 import copy
 import os
@@ -41,6 +44,15 @@ class Prediction_policy:
         self.capture_hard = False   # keep the hard-attention weights of the last call in .last_hard
         self.last_hard = None
         self._scratch = None      # kernel-to-kernel hand-off buffer of K1 (iplan_gat_scratch_floats)
+        # ---- auxiliary trajectory-prediction learner (reference :63-90): decoder nets, one Adam over GAT + decoder
+        self.dec_stack = ParamStack("pdec", self.n_agents, (args.obs_shape_single,), device=self.device)
+        self.pred_decoder = self.dec_stack.nets
+        self.prediction_batch_size = args.pred_batch_size
+        self.pred_length = args.pred_length
+        self._learn = None          # lazily allocated optimiser state / work buffers of learn()
+        self.log_prefix = getattr(args, "log_prefix", "")
+        self.log_stats_t = -getattr(args, "learner_log_interval", 0) - 1
+        self.debug_learn = None     # dict(select_idx=[A][P], gumbel=[A,P,N,N-1,2], keep=[A,P,pl,N,32] uint8) for parity runs
         self._stage = None        # device staging buffers of the pipelined numpy entry point
 
     # ---- device path: tensors laid out [A, B, N, *] (any strides) ------------------
@@ -101,13 +113,86 @@ class Prediction_policy:
         return _lib.to_host(out)
 
     def learn(self, batch, t_env):
-        raise NotImplementedError("Prediction_policy.learn (aux trajectory-prediction loss, reference "
-                                  "nova/prediction_policy.py:168-253) is outside the built hot path (SURVEY §8f)")
+        """Reference :168-253: per agent-net sample ``pred_batch_size`` (episode, time) transitions (:147), run the GAT
+        and roll the decoder ``pred_length`` steps, masked L1 loss (:228-230), clip the GAT and the decoder gradients
+        separately (:236-243), one Adam step over both (:84-90).  Returns the list of per-agent losses."""
+        args, dev = self.args, self.device
+        A, N, o, L, D = self.n_agents, self.max_vehicle_num, self.obs_shape, args.latent_dim, args.attention_dim
+        P, pl = self.prediction_batch_size, self.pred_length
+        hist = batch["history"][:, :-1]                       # [B, T, A, N, o]
+        att = batch["attention_latent"][:, :-1]
+        beh = batch["behavior_latent"][:, :-1]
+        flag = batch["terminated"][:, :-1, :, 0].to(torch.float32)   # the reference multiplies the error by this flag (:196, :163)
+        B, T = hist.shape[0], hist.shape[1]
+        avail_len = T - pl - 1
+        dbg = self.debug_learn or {}
+        idx_rows = []
+        for i in range(A):
+            if "select_idx" in dbg:
+                idx_rows.append(torch.as_tensor(dbg["select_idx"][i]).to(torch.int64))
+            else:
+                idx_rows.append(torch.as_tensor(np.random.choice(B * avail_len, size=P, replace=False)))   # :147
+                for _ in range(pl):
+                    np.random.random()                       # the decoder's teacher-forcing draws (prediction_net.py:55)
+        sel = torch.stack(idx_rows).to(dev)                   # [A, P]
+        b_i, t_i = torch.div(sel, avail_len, rounding_mode="floor"), sel % avail_len
+        a_i = torch.arange(A, device=dev).view(A, 1).expand(A, P)
+        x0 = hist[b_i, t_i, a_i].contiguous()                 # [A, P, N, o]
+        att0 = att[b_i, t_i, a_i].contiguous()
+        lat0 = beh[b_i, t_i, a_i].contiguous()
+        target = torch.stack([hist[b_i, t_i + 1 + k, a_i] for k in range(pl)], dim=3).contiguous()    # [A, P, N, pl, o]
+        mask = flag[b_i, t_i, a_i].contiguous()               # [A, P]
+        scale = (o * pl) / (mask.sum(dim=1) * (N * pl * o) + 1e-10)
+        if self._learn is None:
+            z = lambda t: torch.zeros_like(t)
+            self._learn = dict(g_gat=z(self.stack.flat), g_dec=z(self.dec_stack.flat),
+                               m_gat=z(self.stack.flat), v_gat=z(self.stack.flat), m_dec=z(self.dec_stack.flat), v_dec=z(self.dec_stack.flat),
+                               ones_gat=torch.ones(self.stack.total, device=dev), ones_dec=torch.ones(self.dec_stack.total, device=dev),
+                               sq=torch.zeros(A, device=dev), stats=torch.zeros(A, 8, device=dev), step=0, scratch=None)
+        w = self._learn
+        need = _lib.lib.iplan_pred_learn_scratch_floats(A, P, N, o, pl)
+        if w["scratch"] is None or w["scratch"].numel() < need:
+            w["scratch"] = torch.empty(need, device=dev)
+        w["g_gat"].zero_(); w["g_dec"].zero_(); w["stats"].zero_()
+        loss_sum = torch.zeros(A, device=dev)
+        gum = dbg.get("gumbel")
+        keep = dbg.get("keep")
+        if gum is not None:
+            gum = gum.to(dev, torch.float32).contiguous()
+            assert tuple(gum.shape) == (A, P, N, N - 1, 2)
+        if keep is not None:
+            keep = keep.to(dev, torch.uint8).contiguous()
+            assert tuple(keep.shape) == (A, P, pl, N, D)
+        lib, st, ptr = _lib.lib, _lib.stream(), _lib.ptr
+        _lib.check(lib.iplan_pred_learn(
+            ptr(self.stack.flat), self.stack.stride(), ptr(self.dec_stack.flat), self.dec_stack.stride(),
+            ptr(w["g_gat"]), ptr(w["g_dec"]), ptr(x0), ptr(lat0), ptr(att0), ptr(target), ptr(mask),
+            ptr(gum), ptr(keep), ptr(scale.contiguous()), ptr(loss_sum), ptr(w["scratch"]), w["scratch"].numel(),
+            self.seed, self.calls, self.tau, float(args.decoder_dropout), A, P, N, o, L, pl, st), "pred_learn")
+        self.calls += 1
+        self.last_grads = dict(gat=w["g_gat"].clone(), dec=w["g_dec"].clone())       # raw (unclipped) gradients, for parity checks
+        w["step"] += 1
+        for stack, g, m, v, ones, col in ((self.stack, w["g_gat"], w["m_gat"], w["v_gat"], w["ones_gat"], 0),
+                                          (self.dec_stack, w["g_dec"], w["m_dec"], w["v_dec"], w["ones_dec"], 1)):
+            _lib.check(lib.iplan_learner_adam(ptr(stack.flat), ptr(g), ptr(m), ptr(v), ptr(ones), ptr(w["sq"]), stack.stride(),
+                                              stack.total, A, float(args.lr_predict), 0.9, 0.999, float(args.optim_eps), w["step"],
+                                              float(args.max_grad_norm), 1.0, ptr(w["stats"]), col, st), "adam")
+        losses = (loss_sum * scale).cpu()
+        norms = w["stats"].cpu()
+        out = [np.asarray(float(losses[i]), dtype=np.float32) for i in range(A)]
+        self.train_info = dict(prediction_loss=float(losses.sum()), pred_encoder_grad_norm=float(norms[:, 0].sum()),
+                               pred_decoder_grad_norm=float(norms[:, 1].sum()))
+        if self.logger is not None and t_env - self.log_stats_t >= getattr(args, "learner_log_interval", 0):
+            for k, v in self.train_info.items():
+                self.logger.log_stat(self.log_prefix + k, v, t_env)
+        return out
 
     # ---- checkpoints (reference :256-285) ----------------------------------------
     def save_models(self, path):
         for i, net in enumerate(self.pred_GAT):
             torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/pred_GAT_{i}.th")
+        for i, net in enumerate(self.pred_decoder):
+            torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/pred_decoder_{i}.th")
 
     def load_models(self, paths, load_optimisers=False):
         if len(paths) == 1:
@@ -115,3 +200,7 @@ class Prediction_policy:
         for i, net in enumerate(self.pred_GAT):
             net.load_state_dict(torch.load(os.path.join(paths[i], f"pred_GAT_{i}.th"),
                                            map_location="cpu", weights_only=False))
+        for i, net in enumerate(self.pred_decoder):
+            f = os.path.join(paths[i], f"pred_decoder_{i}.th")
+            if os.path.exists(f):
+                net.load_state_dict(torch.load(f, map_location="cpu", weights_only=False))

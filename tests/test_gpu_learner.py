@@ -187,3 +187,18 @@ def test_fc1_tcgen05_matches_mma_sync_and_fp64(shape):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(*shape, reps=1) < 1e-5
+
+
+@pytest.mark.parametrize("case", ["mpe", "highway"])
+def test_prediction_learn_vs_reference_golden(case):
+    """SURVEY §8f rank 2 — Prediction_policy.learn (csrc/pred_learn.cu: GAT + decoder forward, masked L1, full backward,
+    clip, Adam) against one recorded call of the reference's ``learn`` (same sampled transitions, Gumbel noise and
+    dropout masks): loss, every gradient tensor vs the oracle's autograd, post-step weights vs the reference."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "check_pred_learn", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_pred_learn.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.run(case)
