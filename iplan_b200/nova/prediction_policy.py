@@ -8,8 +8,8 @@ behavior_latent) -> np.float32 [B, A, N, D]`` contract, same ``pred_GAT[i]`` mod
 trajectory-prediction learner (``learn``, reference :168-253) is a "next" row of the scope table
 (SURVEY §8f rank 2): kernel csrc/pred_learn.cu (forward, masked-L1 loss and the full backward in one launch), checked
 against the reference's recorded ``learn`` call (tools/check_pred_learn.py, tests/test_gpu_learner.py): losses 7e-8,
-all 112 gradient tensors <= 1e-5 relative, post-step weights 1.5e-8.  The optimiser state is not checkpointed yet
-(``pred_optimizer_{i}_opt.th``, reference :262).
+all 112 gradient tensors <= 1e-5 relative, post-step weights 1.5e-8.  ``pred_optimizer_{i}_opt.th`` holds the Adam
+state in torch.optim.Adam's state_dict format (reference :262).
 """
 import copy
 import os
@@ -19,6 +19,51 @@ import torch
 
 from .. import _lib
 from ..modules.flat import ParamStack
+
+
+class _PredAdam:
+    """torch.optim.Adam-compatible ``state_dict`` of one agent's (GAT + decoder) optimiser (reference :84-90,
+    files ``pred_optimizer_{i}_opt.th`` :262): parameter ids run over the GAT tensors, then the decoder tensors."""
+
+    def __init__(self, owner, index):
+        self.owner, self.index = owner, index
+
+    def _entries(self):
+        o, out, pid = self.owner, [], 0
+        for kind, stack in (("gat", o.stack), ("dec", o.dec_stack)):
+            for (name, shape), off in zip(stack.spec, stack.offsets):
+                n = 1
+                for d in shape:
+                    n *= d
+                out.append((pid, kind, shape, off, n))
+                pid += 1
+        return out
+
+    def state_dict(self):
+        o = self.owner
+        o._learn_state()
+        w, st = o._learn, {}
+        for pid, kind, shape, off, n in self._entries():
+            if w["step"] == 0:
+                continue
+            st[pid] = {"step": torch.tensor(float(w["step"])),
+                       "exp_avg": w["m_" + kind][self.index, off:off + n].view(shape).detach().cpu().clone(),
+                       "exp_avg_sq": w["v_" + kind][self.index, off:off + n].view(shape).detach().cpu().clone()}
+        group = {"lr": float(o.args.lr_predict), "betas": (0.9, 0.999), "eps": float(o.args.optim_eps),
+                 "weight_decay": float(getattr(o.args, "weight_decay", 0)), "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None, "params": [e[0] for e in self._entries()]}
+        return {"state": st, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        o = self.owner
+        o._learn_state()
+        w = o._learn
+        for pid, kind, shape, off, n in self._entries():
+            if pid in sd["state"]:
+                s_ = sd["state"][pid]
+                w["m_" + kind][self.index, off:off + n] = s_["exp_avg"].reshape(-1).to(o.device)
+                w["v_" + kind][self.index, off:off + n] = s_["exp_avg_sq"].reshape(-1).to(o.device)
+                w["step"] = int(s_["step"])
 
 
 class Prediction_policy:
@@ -52,6 +97,7 @@ class Prediction_policy:
         self._learn = None          # lazily allocated optimiser state / work buffers of learn()
         self.log_prefix = getattr(args, "log_prefix", "")
         self.log_stats_t = -getattr(args, "learner_log_interval", 0) - 1
+        self.pred_optimizer = [_PredAdam(self, i) for i in range(self.n_agents)]
         self.debug_learn = None     # dict(select_idx=[A][P], gumbel=[A,P,N,N-1,2], keep=[A,P,pl,N,32] uint8) for parity runs
         self._stage = None        # device staging buffers of the pipelined numpy entry point
 
@@ -112,6 +158,17 @@ class Prediction_policy:
         self.gat_step(hs.permute(perm), bl.permute(perm), eh.permute(perm), out.permute(perm), gum, dbg)
         return _lib.to_host(out)
 
+    def _learn_state(self):
+        """Optimiser state (Adam moments with the parameter buffers' layout) and work buffers of ``learn``."""
+        if self._learn is None:
+            dev, A = self.device, self.n_agents
+            z = lambda t: torch.zeros_like(t)
+            self._learn = dict(g_gat=z(self.stack.flat), g_dec=z(self.dec_stack.flat),
+                               m_gat=z(self.stack.flat), v_gat=z(self.stack.flat), m_dec=z(self.dec_stack.flat), v_dec=z(self.dec_stack.flat),
+                               ones_gat=torch.ones(self.stack.total, device=dev), ones_dec=torch.ones(self.dec_stack.total, device=dev),
+                               sq=torch.zeros(A, device=dev), stats=torch.zeros(A, 8, device=dev), step=0, scratch=None)
+        return self._learn
+
     def learn(self, batch, t_env):
         """Reference :168-253: per agent-net sample ``pred_batch_size`` (episode, time) transitions (:147), run the GAT
         and roll the decoder ``pred_length`` steps, masked L1 loss (:228-230), clip the GAT and the decoder gradients
@@ -143,13 +200,7 @@ class Prediction_policy:
         target = torch.stack([hist[b_i, t_i + 1 + k, a_i] for k in range(pl)], dim=3).contiguous()    # [A, P, N, pl, o]
         mask = flag[b_i, t_i, a_i].contiguous()               # [A, P]
         scale = (o * pl) / (mask.sum(dim=1) * (N * pl * o) + 1e-10)
-        if self._learn is None:
-            z = lambda t: torch.zeros_like(t)
-            self._learn = dict(g_gat=z(self.stack.flat), g_dec=z(self.dec_stack.flat),
-                               m_gat=z(self.stack.flat), v_gat=z(self.stack.flat), m_dec=z(self.dec_stack.flat), v_dec=z(self.dec_stack.flat),
-                               ones_gat=torch.ones(self.stack.total, device=dev), ones_dec=torch.ones(self.dec_stack.total, device=dev),
-                               sq=torch.zeros(A, device=dev), stats=torch.zeros(A, 8, device=dev), step=0, scratch=None)
-        w = self._learn
+        w = self._learn_state()
         need = _lib.lib.iplan_pred_learn_scratch_floats(A, P, N, o, pl)
         if w["scratch"] is None or w["scratch"].numel() < need:
             w["scratch"] = torch.empty(need, device=dev)
@@ -193,6 +244,8 @@ class Prediction_policy:
             torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/pred_GAT_{i}.th")
         for i, net in enumerate(self.pred_decoder):
             torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/pred_decoder_{i}.th")
+        for i in range(self.n_agents):
+            torch.save(self.pred_optimizer[i].state_dict(), "{}/pred_optimizer_{}_opt.th".format(path, i))
 
     def load_models(self, paths, load_optimisers=False):
         if len(paths) == 1:
@@ -204,3 +257,7 @@ class Prediction_policy:
             f = os.path.join(paths[i], f"pred_decoder_{i}.th")
             if os.path.exists(f):
                 net.load_state_dict(torch.load(f, map_location="cpu", weights_only=False))
+        if load_optimisers:
+            for i in range(self.n_agents):
+                self.pred_optimizer[i].load_state_dict(torch.load("{}/pred_optimizer_{}_opt.th".format(paths[i], i),
+                                                                  map_location="cpu", weights_only=False))

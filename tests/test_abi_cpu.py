@@ -77,3 +77,33 @@ def test_episode_batch_cpu_semantics():
         assert False
     except KeyError:
         pass
+
+
+def test_prediction_optimizer_state_dict_is_torch_adam_compatible():
+    """``pred_optimizer_{i}_opt.th`` (reference nova/prediction_policy.py:262): the flat Adam moments of the GAT + decoder
+    stacks export / import in torch.optim.Adam's state_dict format (parameter ids: GAT tensors, then decoder tensors)."""
+    from types import SimpleNamespace
+    from iplan_b200.modules.flat import ParamStack
+    from iplan_b200.nova.prediction_policy import _PredAdam
+    gat, dec = ParamStack("gat", 2, (13,)), ParamStack("pdec", 2, (5,))
+    z = lambda t: torch.zeros_like(t)
+    state = dict(m_gat=torch.randn_like(gat.flat), v_gat=torch.rand_like(gat.flat), m_dec=torch.randn_like(dec.flat),
+                 v_dec=torch.rand_like(dec.flat), step=3)
+    owner = SimpleNamespace(stack=gat, dec_stack=dec, device=torch.device("cpu"), _learn=state, _learn_state=lambda: state,
+                            args=SimpleNamespace(lr_predict=2e-5, optim_eps=1e-5, weight_decay=0))
+    sd = _PredAdam(owner, 1).state_dict()
+    params = [torch.nn.Parameter(torch.zeros(shape)) for _, shape in gat.spec + dec.spec]
+    opt = torch.optim.Adam(params, lr=2e-5, eps=1e-5)
+    opt.load_state_dict(sd)                                    # torch accepts the format
+    assert len(sd["state"]) == len(params) == 28
+    off, shape = gat.named_offsets()["q.weight"]
+    pid = [n for n, _ in gat.spec].index("q.weight")
+    assert torch.equal(opt.state[params[pid]]["exp_avg"], state["m_gat"][1, off:off + 1024].view(shape))
+    # round trip into a fresh owner
+    state2 = dict(m_gat=z(gat.flat), v_gat=z(gat.flat), m_dec=z(dec.flat), v_dec=z(dec.flat), step=0)
+    owner2 = SimpleNamespace(stack=gat, dec_stack=dec, device=torch.device("cpu"), _learn=state2, _learn_state=lambda: state2, args=owner.args)
+    _PredAdam(owner2, 1).load_state_dict(opt.state_dict())
+    assert state2["step"] == 3
+    for (name, shape), off in zip(dec.spec, dec.offsets):
+        n = int(torch.tensor(shape).prod()) if len(shape) else 1
+        assert torch.equal(state2["v_dec"][1, off:off + n], state["v_dec"][1, off:off + n]), name
