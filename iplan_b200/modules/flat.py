@@ -49,6 +49,14 @@ def pdec_spec(obs_dim):
             ("decoder.out.weight", (obs_dim, H)), ("decoder.out.bias", (obs_dim,))]
 
 
+def bdec_spec(obs_dim, latent_dim, hidden=64):
+    """Behavior_Latent_Decoder -> DecoderRNN (nova/behavior_net.py:25-47, :50-55): input = obs + latent, hidden = decoder_rnn_dim."""
+    return [("decoder.linear.weight", (hidden, obs_dim + latent_dim)), ("decoder.linear.bias", (hidden,)),
+            ("decoder.rnn.weight_ih_l0", (3 * hidden, hidden)), ("decoder.rnn.weight_hh_l0", (3 * hidden, hidden)),
+            ("decoder.rnn.bias_ih_l0", (3 * hidden,)), ("decoder.rnn.bias_hh_l0", (3 * hidden,)),
+            ("decoder.out.weight", (obs_dim, hidden)), ("decoder.out.bias", (obs_dim,))]
+
+
 def trunk_spec(feat_dim):
     """MLPBase + RNNLayer (utils/mappo_utils/mlp.py:17-22,44-48; rnn.py:13-22)."""
     return [("base.feature_norm.weight", (feat_dim,)), ("base.feature_norm.bias", (feat_dim,)),
@@ -78,6 +86,15 @@ def critic_spec(feat_dim):
 
 FROZEN = ("v_out.stddev", "v_out.mean", "v_out.mean_sq", "v_out.debiasing_term")
 DEAD = ("base.mlp.fc_h.",)       # cloned into fc2 then never called (mlp.py:20-27): grad stays None
+
+
+def _host_layout(spec):
+    offsets, off = [], 0
+    for _, shape in spec:
+        offsets.append(off)
+        n = int(math.prod(shape)) if len(shape) else 1
+        off = (off + n + 3) // 4 * 4
+    return off, offsets
 
 
 class AgentNet(nn.Module):
@@ -122,8 +139,12 @@ class ParamStack:
 
     def __init__(self, kind, n_agents, dims, device="cpu"):
         self.kind, self.n_agents, self.dims = kind, n_agents, tuple(dims)
-        self.spec = {"gat": gat_spec, "beh": beh_spec, "actor": actor_spec, "critic": critic_spec, "pdec": pdec_spec}[kind](*dims)
-        self.total, self.offsets = _lib.layout(kind, *dims)
+        self.spec = {"gat": gat_spec, "beh": beh_spec, "actor": actor_spec, "critic": critic_spec, "pdec": pdec_spec,
+                     "bdec": bdec_spec}[kind](*dims)
+        if kind == "bdec":          # no kernel reads this stack yet: host-side layout, same rule (tensor starts padded to 4 floats)
+            self.total, self.offsets = _host_layout(self.spec)
+        else:
+            self.total, self.offsets = _lib.layout(kind, *dims)
         assert len(self.offsets) == len(self.spec)
         # initialise on the host (orthogonal init = QR: dozens of tiny launches on a GPU), then move
         self.flat = torch.zeros(n_agents, self.total, dtype=torch.float32)
@@ -171,10 +192,11 @@ class ParamStack:
 
     def _init_tensor(self, name, p):
         k = self.kind
-        if k in ("gat", "beh", "pdec"):
+        if k in ("gat", "beh", "pdec", "bdec"):
             # torch defaults: Linear U(+-1/sqrt(fan_in)); GRU/GRUCell U(+-1/sqrt(hidden))
             if "GRU" in name or name.startswith("rnn.") or ".rnn." in name:
-                bound = 1.0 / math.sqrt(H)
+                hidden = dict(self.spec)["decoder.rnn.weight_hh_l0"][1] if k in ("pdec", "bdec") else H
+                bound = 1.0 / math.sqrt(hidden)
             else:
                 fan_in = dict(self.spec)[name.rsplit(".", 1)[0] + ".weight"][1]
                 bound = 1.0 / math.sqrt(fan_in)

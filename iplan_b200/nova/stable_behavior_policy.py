@@ -35,6 +35,9 @@ class Behavior_policy:
         assert args.encoder_rnn_dim == 32 and args.num_encoder_layer == 1, "kernel K1b is built for E = 32, one layer"
         self.stack = ParamStack("beh", self.n_agents, (args.obs_shape_single, args.latent_dim), device=self.device)
         self.behavior_encoder = self.stack.nets
+        # the reconstruction decoder of the auxiliary learner (reference :48-53): parameters and checkpoints only — ``learn`` is not built
+        self.dec_stack = ParamStack("bdec", self.n_agents, (args.obs_shape_single, args.latent_dim, args.decoder_rnn_dim), device=self.device)
+        self.behavior_decoder = self.dec_stack.nets
         self._stage = None        # device staging buffers of the pipelined numpy entry point
 
     # ---- device path: tensors laid out [A, B, N, *] ----------------------------------
@@ -90,6 +93,8 @@ class Behavior_policy:
     def save_models(self, path):
         for i, net in enumerate(self.behavior_encoder):
             torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/behavior_encoder_{i}.th")
+        for i, net in enumerate(self.behavior_decoder):
+            torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/behavior_decoder_{i}.th")
 
     def load_models(self, paths, load_optimisers=False):
         if len(paths) == 1:
@@ -97,3 +102,7 @@ class Behavior_policy:
         for i, net in enumerate(self.behavior_encoder):
             net.load_state_dict(torch.load(os.path.join(paths[i], f"behavior_encoder_{i}.th"),
                                            map_location="cpu", weights_only=False))
+        for i, net in enumerate(self.behavior_decoder):
+            f = os.path.join(paths[i], f"behavior_decoder_{i}.th")
+            if os.path.exists(f):
+                net.load_state_dict(torch.load(f, map_location="cpu", weights_only=False))
