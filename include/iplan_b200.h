@@ -162,6 +162,24 @@ int iplan_pred_learn(const float* gat_params, int64_t gat_stride, const float* d
                      float* scratch, int64_t scratch_floats, uint64_t seed, uint64_t counter, float tau, float p_drop,
                      int n_agents, int n_samples, int n_slots, int obs_dim, int latent_dim, int pred_len, void* stream);
 
+/* ---- Behavior_policy.learn (nova/stable_behavior_policy.py:161-279) -----------------------------
+ * DRAFT: specified line by line by oracle/iplan_oracle.py::behavior_learn_agent, compiled, not yet validated on
+ * hardware; the host class raises NotImplementedError unless its `enable_learn` flag is set (tools/check_beh_learn.py).
+ * One launch = the reconstruction loss over every window position of every episode and its gradients (one BPTT through
+ * the encoder GRU, the decoder GRU and the latent recursion), ADDED into g_enc / g_dec (zero them first; layouts
+ * iplan_beh_layout / iplan_bdec_layout).  behavior_variation_penalty = 0 only (the stability term is reported, not
+ * differentiated).
+ *   hist [A][B][T][N][o] (the batch without its last step), mask [A][B][T], scale [A][T-1-W] = o N / (unmasked elements
+ *   of the next-window + 1e-10) / (T-1-W); keep NULL (Philox) or uint8 [A][B][T-1-W][N][W][64]; b_loss, s_loss [A] += */
+#define IPLAN_BDEC_NTENSORS 8     /* nova/behavior_net.py:25-38 (DecoderRNN inside Behavior_Latent_Decoder), hidden = IPLAN_RNN */
+int64_t iplan_bdec_layout(int obs_dim, int latent_dim, int64_t* offsets);
+int64_t iplan_beh_learn_scratch_floats(int n_agents, int n_eps, int n_pos, int n_slots, int obs_dim, int latent_dim, int hist_len);
+int iplan_beh_learn(const float* enc_params, int64_t enc_stride, const float* dec_params, int64_t dec_stride,
+                    float* g_enc, float* g_dec, const float* hist, const float* mask, const float* scale, const uint8_t* keep,
+                    float* b_loss, float* s_loss, float* scratch, int64_t scratch_floats,
+                    uint64_t seed, uint64_t counter, float p_drop, float soft_coef, float thres_small_variation,
+                    int n_agents, int n_eps, int n_steps, int n_slots, int obs_dim, int latent_dim, int hist_len, void* stream);
+
 /* ==== IPPO learner (IPPOLearner.train, learners/ippo_learner.py:227-317) ===============
  * All agents are processed together.  Agent a's input matrix is X_a[rows][ldx] with
  * rows = n_eps*(T+1), row (b,t) at index b*(T+1)+t — the packed EpisodeBatch layout.

@@ -50,6 +50,10 @@ _SIGNATURES = {
     "iplan_pred_learn_scratch_floats": (_i64, [_i, _i, _i, _i, _i]),
     "iplan_pred_learn": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _u64, _u64, _f, _f,
                               _i, _i, _i, _i, _i, _i, _p]),
+    "iplan_bdec_layout": (_i64, [_i, _i, _p]),
+    "iplan_beh_learn_scratch_floats": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
+    "iplan_beh_learn": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _u64, _u64, _f, _f, _f,
+                             _i, _i, _i, _i, _i, _i, _i, _p]),
     "iplan_learner_row_stats": (_i, [_p, _i64, _i, _i, _i64, _i, _p, _p]),
     "iplan_learner_x_split": (_i, [_p, _i64, _p, _p, _p]),
     "iplan_learner_fc1_forward": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _i, _i, _i64, _i, _p, _p, _p, _p, _p, _p, _p]),
@@ -227,7 +231,7 @@ def run_pipelined(host_in, dev_in, host_out, dev_out, launch, n_chunks=None):
 
 def layout(kind, *dims):
     """(total floats per agent, [offsets]) of a flat parameter buffer."""
-    n = {"gat": 20, "beh": 8, "actor": 22, "critic": 26, "pdec": 8}[kind]
+    n = {"gat": 20, "beh": 8, "actor": 22, "critic": 26, "pdec": 8, "bdec": 8}[kind]
     arr = (C.c_int64 * n)()
     fn = getattr(lib, f"iplan_{kind}_layout")
     total = fn(*dims, C.cast(arr, C.c_void_p))

@@ -88,15 +88,6 @@ FROZEN = ("v_out.stddev", "v_out.mean", "v_out.mean_sq", "v_out.debiasing_term")
 DEAD = ("base.mlp.fc_h.",)       # cloned into fc2 then never called (mlp.py:20-27): grad stays None
 
 
-def _host_layout(spec):
-    offsets, off = [], 0
-    for _, shape in spec:
-        offsets.append(off)
-        n = int(math.prod(shape)) if len(shape) else 1
-        off = (off + n + 3) // 4 * 4
-    return off, offsets
-
-
 class AgentNet(nn.Module):
     """One agent's network: a module tree whose leaves are views into the stack."""
 
@@ -141,10 +132,7 @@ class ParamStack:
         self.kind, self.n_agents, self.dims = kind, n_agents, tuple(dims)
         self.spec = {"gat": gat_spec, "beh": beh_spec, "actor": actor_spec, "critic": critic_spec, "pdec": pdec_spec,
                      "bdec": bdec_spec}[kind](*dims)
-        if kind == "bdec":          # no kernel reads this stack yet: host-side layout, same rule (tensor starts padded to 4 floats)
-            self.total, self.offsets = _host_layout(self.spec)
-        else:
-            self.total, self.offsets = _lib.layout(kind, *dims)
+        self.total, self.offsets = _lib.layout(kind, *(dims[:2] if kind == "bdec" else dims))
         assert len(self.offsets) == len(self.spec)
         # initialise on the host (orthogonal init = QR: dozens of tiny launches on a GPU), then move
         self.flat = torch.zeros(n_agents, self.total, dtype=torch.float32)

@@ -7,8 +7,11 @@ Same constructor, same ``latent_update(history, encoder_hidden, prev_latent) ->
 (np latent [B,A,N,L], torch hidden [B,1,A,N,E])`` contract (the reference returns the
 hidden state as a torch tensor and accepts numpy on the first call / a tensor
 afterwards, :101-121), same ``behavior_encoder[i]`` state_dict keys and
-``behavior_encoder_{i}.th`` files.  The auxiliary reconstruction learner (``learn``,
-reference :161-279) is a "next" row of the scope table and is not built.
+``behavior_encoder_{i}.th`` files.  The auxiliary reconstruction learner (``learn``, reference :161-279, SURVEY §8f
+rank 3) is DRAFTED: kernel csrc/beh_learn.cu and the host code below follow the pinned oracle
+(oracle/iplan_oracle.py::behavior_learn_agent) line by line and compile, but have not run on hardware yet, so ``learn``
+raises ``NotImplementedError`` unless ``enable_learn`` is set (tools/check_beh_learn.py sets it to compare with the
+reference's recorded ``learn`` call).  It is a plain-FFMA first version (seconds per call at 512 envs).
 """
 import copy
 import os
@@ -39,6 +42,13 @@ class Behavior_policy:
         self.dec_stack = ParamStack("bdec", self.n_agents, (args.obs_shape_single, args.latent_dim, args.decoder_rnn_dim), device=self.device)
         self.behavior_decoder = self.dec_stack.nets
         self._stage = None        # device staging buffers of the pipelined numpy entry point
+        self.enable_learn = False   # see the module docstring
+        self._learn = None          # Adam moments / work buffers of learn()
+        self.learn_calls = 0
+        self.seed = int(getattr(args, "seed", 112358))
+        self.log_prefix = getattr(args, "log_prefix", "")
+        self.log_stats_t = -getattr(args, "learner_log_interval", 0) - 1
+        self.debug_keep = None      # uint8 [A, B, n_pos, N, W, 64] explicit dropout draw for the next learn() (parity runs)
 
     # ---- device path: tensors laid out [A, B, N, *] ----------------------------------
     def behavior_step(self, window, hid_io, lat_prev, lat_out):
@@ -86,8 +96,69 @@ class Behavior_policy:
         return _lib.to_host(new), hid
 
     def learn(self, batch, t_env):
-        raise NotImplementedError("Behavior_policy.learn (aux reconstruction loss, reference "
-                                  "nova/stable_behavior_policy.py:161-279) is outside the built hot path (SURVEY §8f)")
+        """Reference :161-279: for every agent-net, walk the T-1-W window positions of every episode with the decoder and
+        the encoder (hidden states and the soft-updated latent carried across positions), masked L1 reconstruction of the
+        next window (:226-233), one backward through everything, separate gradient clipping of encoder and decoder
+        (:248-256), one Adam step (:258).  Returns (behavior_loss, stability_loss, total_loss) lists of per-agent values."""
+        if not self.enable_learn:
+            raise NotImplementedError("Behavior_policy.learn: kernel drafted (csrc/beh_learn.cu) but not yet validated on hardware; "
+                                      "set enable_learn = True to run it (tools/check_beh_learn.py)")
+        args, dev = self.args, self.device
+        if float(getattr(args, "behavior_variation_penalty", 0)) != 0.0:
+            raise NotImplementedError("only behavior_variation_penalty = 0 (the iPLAN setting) is built: the stability term is reported, not differentiated")
+        A, N, o, L, W = self.n_agents, self.max_vehicle_num, args.obs_shape_single, self.latent_dim, self.max_history_len
+        hist = batch["history"][:, :-1]                                  # [B, T, A, N, o]
+        term = batch["terminated"][:, :-1, :, 0].to(torch.float32)      # [B, T, A]
+        mask = (1.0 - term) if args.env == "MPE" else term               # :186-189
+        B, T = hist.shape[0], hist.shape[1]
+        n_pos = T - 1 - W
+        hist_a = hist.permute(2, 0, 1, 3, 4).contiguous()
+        mask_a = mask.permute(2, 0, 1).contiguous()                      # [A, B, T]
+        cs = torch.cumsum(mask_a.sum(dim=1), dim=1)                      # [A, T]
+        j = torch.arange(n_pos, device=dev)
+        msum = (cs[:, j + W] - cs[:, j]) * (N * o)                       # unmasked elements of the next-window at position j
+        scale = ((o * N) / (msum + 1e-10) / n_pos).contiguous()
+        if self._learn is None:
+            z = lambda t: torch.zeros_like(t)
+            self._learn = dict(g_enc=z(self.stack.flat), g_dec=z(self.dec_stack.flat), m_enc=z(self.stack.flat), v_enc=z(self.stack.flat),
+                               m_dec=z(self.dec_stack.flat), v_dec=z(self.dec_stack.flat),
+                               ones_enc=torch.ones(self.stack.total, device=dev), ones_dec=torch.ones(self.dec_stack.total, device=dev),
+                               sq=torch.zeros(A, device=dev), stats=torch.zeros(A, 8, device=dev), step=0, scratch=None)
+        w = self._learn
+        need = _lib.lib.iplan_beh_learn_scratch_floats(A, B, n_pos, N, o, L, W)
+        if w["scratch"] is None or w["scratch"].numel() < need:
+            w["scratch"] = torch.empty(need, device=dev)
+        w["g_enc"].zero_(); w["g_dec"].zero_(); w["stats"].zero_()
+        b_loss, s_loss = torch.zeros(A, device=dev), torch.zeros(A, device=dev)
+        keep = self.debug_keep
+        self.debug_keep = None
+        if keep is not None:
+            keep = keep.to(dev, torch.uint8).contiguous()
+            assert tuple(keep.shape) == (A, B, n_pos, N, W, args.decoder_rnn_dim), keep.shape
+        lib, st, ptr = _lib.lib, _lib.stream(), _lib.ptr
+        _lib.check(lib.iplan_beh_learn(
+            ptr(self.stack.flat), self.stack.stride(), ptr(self.dec_stack.flat), self.dec_stack.stride(), ptr(w["g_enc"]), ptr(w["g_dec"]),
+            ptr(hist_a), ptr(mask_a), ptr(scale), ptr(keep), ptr(b_loss), ptr(s_loss), ptr(w["scratch"]), w["scratch"].numel(),
+            self.seed, self.learn_calls, float(args.decoder_dropout), float(self.soft_update_coef), float(args.thres_small_variation),
+            A, B, T, N, o, L, W, st), "beh_learn")
+        self.learn_calls += 1
+        self.last_grads = dict(enc=w["g_enc"].clone(), dec=w["g_dec"].clone())       # raw (unclipped) gradients, for parity checks
+        w["step"] += 1
+        for stack, g, m, v, ones, col in ((self.stack, w["g_enc"], w["m_enc"], w["v_enc"], w["ones_enc"], 0),
+                                          (self.dec_stack, w["g_dec"], w["m_dec"], w["v_dec"], w["ones_dec"], 1)):
+            _lib.check(lib.iplan_learner_adam(ptr(stack.flat), ptr(g), ptr(m), ptr(v), ptr(ones), ptr(w["sq"]), stack.stride(),
+                                              stack.total, A, float(args.lr_behavior), 0.9, 0.999, float(args.optim_eps), w["step"],
+                                              float(args.max_grad_norm), 1.0, ptr(w["stats"]), col, st), "adam")
+        bl, sl, norms = b_loss.cpu(), s_loss.cpu(), w["stats"].cpu()
+        behavior_loss = [np.asarray(float(bl[i]), dtype=np.float32) for i in range(A)]
+        stability_loss = [np.asarray(float(sl[i]), dtype=np.float32) for i in range(A)]
+        total_loss = [np.asarray(float(bl[i]), dtype=np.float32) for i in range(A)]          # penalty = 0
+        self.train_info = dict(behavior_loss=float(bl.sum()), stability_loss=float(sl.sum()), behavior_total=float(bl.sum()),
+                               behavior_encoder_grad_norm=float(norms[:, 0].sum()), behavior_decoder_grad_norm=float(norms[:, 1].sum()))
+        if self.logger is not None and t_env - self.log_stats_t >= getattr(args, "learner_log_interval", 0):
+            for k, v in self.train_info.items():
+                self.logger.log_stat(self.log_prefix + k, v, t_env)
+        return behavior_loss, stability_loss, total_loss
 
     # ---- checkpoints (reference :282-312) -------------------------------------------
     def save_models(self, path):
