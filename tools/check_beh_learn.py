@@ -1,4 +1,4 @@
-"""Behavior_policy.learn on the GPU (DRAFT kernel csrc/beh_learn.cu) against the reference's recorded ``learn`` call
+"""Behavior_policy.learn on the GPU (kernel csrc/beh_learn.cu) against the reference's recorded ``learn`` call
 (tests/golden/behavior_learn.pt, dropout masks replayed):
 
     timeout 200 python tools/check_beh_learn.py
@@ -38,7 +38,6 @@ def run(case):
         pol.behavior_encoder[a].load_state_dict(g["enc_before"][a])
         pol.behavior_decoder[a].load_state_dict(g["dec_before"][a])
     pol.debug_keep = torch.stack([k.view(n_pos, B, N, W, -1).permute(1, 0, 2, 3, 4) for k in g["dropout_keep"]]).to(torch.uint8)
-    pol.enable_learn = True
     b_loss, s_loss, _ = pol.learn(batch, t_env=0)
     torch.cuda.synchronize()
     ok = True
