@@ -11,7 +11,8 @@ afterwards, :101-121), same ``behavior_encoder[i]`` state_dict keys and
 rank 3): kernel csrc/beh_learn.cu (the pinned oracle oracle/iplan_oracle.py::behavior_learn_agent line by line), checked
 against the reference's recorded ``learn`` call (tools/check_beh_learn.py, tests/test_gpu_learner.py): losses 2e-7,
 every gradient tensor <= 1e-5 relative, post-step weights 1.5e-8.  It is a plain-FFMA first version (estimated seconds
-per call at 512 envs; the tensor-core version is future work); ``behavior_optimizer_{i}_opt.th`` is not written yet.
+per call at 512 envs; the tensor-core version is future work); ``behavior_optimizer_{i}_opt.th`` holds the Adam state in
+torch.optim.Adam's state_dict format.
 """
 import copy
 import os
@@ -21,6 +22,49 @@ import torch
 
 from .. import _lib
 from ..modules.flat import ParamStack
+
+
+class _BehAdam:
+    """torch.optim.Adam-compatible ``state_dict`` of one agent's (encoder + decoder) optimiser (reference :59-62, files
+    ``behavior_optimizer_{i}_opt.th`` :288): parameter ids run over the encoder tensors, then the decoder tensors."""
+
+    def __init__(self, owner, index):
+        self.owner, self.index = owner, index
+
+    def _entries(self):
+        o, out, pid = self.owner, [], 0
+        for kind, stack in (("enc", o.stack), ("dec", o.dec_stack)):
+            for (name, shape), off in zip(stack.spec, stack.offsets):
+                n = 1
+                for d in shape:
+                    n *= d
+                out.append((pid, kind, shape, off, n))
+                pid += 1
+        return out
+
+    def state_dict(self):
+        o = self.owner
+        w, st = o._learn_state(), {}
+        for pid, kind, shape, off, n in self._entries():
+            if w["step"] == 0:
+                continue
+            st[pid] = {"step": torch.tensor(float(w["step"])),
+                       "exp_avg": w["m_" + kind][self.index, off:off + n].view(shape).detach().cpu().clone(),
+                       "exp_avg_sq": w["v_" + kind][self.index, off:off + n].view(shape).detach().cpu().clone()}
+        group = {"lr": float(o.args.lr_behavior), "betas": (0.9, 0.999), "eps": float(o.args.optim_eps),
+                 "weight_decay": float(getattr(o.args, "weight_decay", 0)), "amsgrad": False, "maximize": False, "foreach": None,
+                 "capturable": False, "differentiable": False, "fused": None, "params": [e[0] for e in self._entries()]}
+        return {"state": st, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        o = self.owner
+        w = o._learn_state()
+        for pid, kind, shape, off, n in self._entries():
+            if pid in sd["state"]:
+                s_ = sd["state"][pid]
+                w["m_" + kind][self.index, off:off + n] = s_["exp_avg"].reshape(-1).to(o.device)
+                w["v_" + kind][self.index, off:off + n] = s_["exp_avg_sq"].reshape(-1).to(o.device)
+                w["step"] = int(s_["step"])
 
 
 class Behavior_policy:
@@ -47,6 +91,7 @@ class Behavior_policy:
         self.seed = int(getattr(args, "seed", 112358))
         self.log_prefix = getattr(args, "log_prefix", "")
         self.log_stats_t = -getattr(args, "learner_log_interval", 0) - 1
+        self.behavior_optimizer = [_BehAdam(self, i) for i in range(self.n_agents)]
         self.debug_keep = None      # uint8 [A, B, n_pos, N, W, 64] explicit dropout draw for the next learn() (parity runs)
 
     # ---- device path: tensors laid out [A, B, N, *] ----------------------------------
@@ -94,6 +139,17 @@ class Behavior_policy:
                            prev.permute(perm), new.permute(perm))
         return _lib.to_host(new), hid
 
+    def _learn_state(self):
+        """Optimiser state (Adam moments with the parameter buffers' layout) and work buffers of ``learn``."""
+        if self._learn is None:
+            dev, A = self.device, self.n_agents
+            z = lambda t: torch.zeros_like(t)
+            self._learn = dict(g_enc=z(self.stack.flat), g_dec=z(self.dec_stack.flat), m_enc=z(self.stack.flat), v_enc=z(self.stack.flat),
+                               m_dec=z(self.dec_stack.flat), v_dec=z(self.dec_stack.flat),
+                               ones_enc=torch.ones(self.stack.total, device=dev), ones_dec=torch.ones(self.dec_stack.total, device=dev),
+                               sq=torch.zeros(A, device=dev), stats=torch.zeros(A, 8, device=dev), step=0, scratch=None)
+        return self._learn
+
     def learn(self, batch, t_env):
         """Reference :161-279: for every agent-net, walk the T-1-W window positions of every episode with the decoder and
         the encoder (hidden states and the soft-updated latent carried across positions), masked L1 reconstruction of the
@@ -114,13 +170,7 @@ class Behavior_policy:
         j = torch.arange(n_pos, device=dev)
         msum = (cs[:, j + W] - cs[:, j]) * (N * o)                       # unmasked elements of the next-window at position j
         scale = ((o * N) / (msum + 1e-10) / n_pos).contiguous()
-        if self._learn is None:
-            z = lambda t: torch.zeros_like(t)
-            self._learn = dict(g_enc=z(self.stack.flat), g_dec=z(self.dec_stack.flat), m_enc=z(self.stack.flat), v_enc=z(self.stack.flat),
-                               m_dec=z(self.dec_stack.flat), v_dec=z(self.dec_stack.flat),
-                               ones_enc=torch.ones(self.stack.total, device=dev), ones_dec=torch.ones(self.dec_stack.total, device=dev),
-                               sq=torch.zeros(A, device=dev), stats=torch.zeros(A, 8, device=dev), step=0, scratch=None)
-        w = self._learn
+        w = self._learn_state()
         need = _lib.lib.iplan_beh_learn_scratch_floats(A, B, n_pos, N, o, L, W)
         if w["scratch"] is None or w["scratch"].numel() < need:
             w["scratch"] = torch.empty(need, device=dev)
@@ -162,6 +212,8 @@ class Behavior_policy:
             torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/behavior_encoder_{i}.th")
         for i, net in enumerate(self.behavior_decoder):
             torch.save({k: v.detach().cpu() for k, v in net.state_dict().items()}, f"{path}/behavior_decoder_{i}.th")
+        for i in range(self.n_agents):
+            torch.save(self.behavior_optimizer[i].state_dict(), "{}/behavior_optimizer_{}_opt.th".format(path, i))
 
     def load_models(self, paths, load_optimisers=False):
         if len(paths) == 1:
@@ -173,3 +225,7 @@ class Behavior_policy:
             f = os.path.join(paths[i], f"behavior_decoder_{i}.th")
             if os.path.exists(f):
                 net.load_state_dict(torch.load(f, map_location="cpu", weights_only=False))
+        if load_optimisers:
+            for i in range(self.n_agents):
+                self.behavior_optimizer[i].load_state_dict(torch.load("{}/behavior_optimizer_{}_opt.th".format(paths[i], i),
+                                                                      map_location="cpu", weights_only=False))
