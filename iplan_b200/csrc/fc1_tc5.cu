@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "tc5.cuh"
 
 namespace iplan {
 
@@ -32,90 +33,7 @@ constexpr int T5_STAGE_BYTES = 4 * T5_TILE_BYTES;              // Xh, Xl, Wh, Wl
 constexpr size_t T5_SMEM = (size_t)T5_STAGES * T5_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 constexpr int T5_TMEM_COLS = 256;                              // two 128-column fp32 accumulators
 
-// ---- raw PTX wrappers --------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// D[tmem] (+)= A[smem] . B[smem]^T, f16 inputs, f32 accumulate; issued by ONE thread for the CTA
-__device__ __forceinline__ void tc5_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// the mbarrier is signalled when every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void tc5_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread = TMEM lane (row), v[j] = column j
-__device__ __forceinline__ void tc5_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-}
-
-// K-major operand tile, 128B swizzle (what TMA SWIZZLE_128B writes for a 64 x f16 box row): rows of 128 B,
-// 8-row groups 1024 B apart (SBO), descriptor version 1 (sm_100), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t tc5_smem_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address, 16-byte units          bits [0,14)
-    d |= (uint64_t)0 << 16;                                 // leading byte offset (unused: K fits one swizzle atom)
-    d |= (uint64_t)(1024 >> 4) << 32;                       // stride byte offset: 8 rows x 128 B    bits [32,46)
-    d |= (uint64_t)1 << 46;                                 // descriptor version                    bits [46,48)
-    d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B                          bits [61,64)
-    return d;
-}
-// kind::f16: D = F32 (bit 4), A = B = F16 (0), both K-major (0), N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t T5_IDESC = (1u << 4) | ((uint32_t)(T5_BN >> 3) << 17) | ((uint32_t)(T5_BM >> 4) << 24);
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
-}
-// MN-major operand tile (the reduction index k is the slow one: element (k, mn) at row k, column mn), 128B swizzle:
-// a TMA box of 64 mn x 64 k lands as 64 rows of 128 B; 8-row groups along k are 1024 B apart (SBO); the next 64 mn
-// columns are the next box, `mn_group_bytes` further (LBO).
-__device__ __forceinline__ uint64_t tc5_smem_desc_mn(uint32_t smem_addr, uint32_t mn_group_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(mn_group_bytes >> 4) << 16;             // leading byte offset: next 64-element group along M / N
-    d |= (uint64_t)(1024 >> 4) << 32;                       // stride byte offset: next 8 rows along K
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
-    return d;
-}
+constexpr uint32_t T5_IDESC = tc5_idesc(T5_BM, T5_BN);
 // as T5_IDESC with A and B MN-major (bits 15, 16)
 constexpr uint32_t T5_IDESC_MN = T5_IDESC | (1u << 15) | (1u << 16);
 

@@ -35,33 +35,14 @@
 // HBM traffic per (b,a): read N*(o+L+32) floats, write N*32 floats; weights (28.8k floats)
 // and the dl scratch come from L2.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include <type_traits>
 
 #include "common.cuh"
+#include "gat_common.cuh"
 
 namespace iplan {
-
-constexpr int H = IPLAN_HID;   // 32 == GAT_hidden_dim == attention_dim
-constexpr int G3 = 3 * H;      // gate rows r|z|n
-constexpr int GAT_THREADS = 256;           // attend kernel
-constexpr int GAT_WARPS = GAT_THREADS / 32;
-constexpr int REC_THREADS = 128;           // recurrence kernel: 4 warps = 4 m-tiles of 16 egos
-constexpr int REC_WARPS = REC_THREADS / 32;
-constexpr int DLP = IPLAN_MAX_SLOTS;       // row pitch of the dl scratch: dl[dir][s][DLP]
-constexpr int IN_MAX = 16;     // obs_dim + latent_dim upper bound
-constexpr int NT_G = G3 / 8;   // 12 n-tiles of 8 gate columns
-constexpr int PP = G3 + 8;     // row pitch of the ego projections P: rows of different chains fall in different banks
-constexpr int KB_H = H / 16;   // 2 k-blocks of 16 hidden units
-
-struct GatArgs {
-    const float* params; int64_t param_stride;
-    iplan_view hist, beh, hprev, out;
-    const float* gumbel; float* dbg_hard; float* dl;
-    uint64_t seed, counter;
-    float inv_tau;
-    int n_envs, n_slots, obs_dim, latent_dim;
-};
 
 __host__ __device__ inline size_t rec_smem_floats(int N) {
     // s_P | s_Q | union { s_x, s_enc  (prologue) ; W_hh fragments, b_hn, logit weights (recurrence) }
@@ -78,65 +59,6 @@ __host__ __device__ inline size_t att_smem_floats(int N) {
     return (size_t)H * WP + 3 * (size_t)N * H + (size_t)N * G3 + (region > gru ? region : gru);
 }
 
-// fast, fp32-accurate-enough gates (abs error ~1e-7): ex2.approx + rcp.approx
-// The recurrence keeps its r|z pre-activations scaled by -log2(e) and its n pre-activation by
-// 2 log2(e) (the scale is folded into W_hh, b_hh, P and Q once per CTA), so that
-//   sigmoid(x) = 1 / (1 + 2^(x'))   and   tanh(x) = 1 - 2 / (1 + 2^(x'))
-// cost one ex2.approx + one add + one rcp.approx each (abs error ~1e-7).
-constexpr float K_RZ = -1.4426950408889634f;      // -log2(e)
-constexpr float K_N = 2.8853900817779268f;        //  2 log2(e)
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-// Packed fp32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): the gate math of the recurrence is issue-slot
-// bound, and an accumulator fragment is two (col, col+1) pairs, so every elementwise op is done on
-// pairs.  A pair lives in a 64-bit register (lo = first element).
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 lds64(const float* p) {
-    f32x2 v;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
-    return v;
-}
-
-// Four sigmoid denominators with ONE rcp.approx (the XU pipe is the recurrence's busiest unit):
-// given ea = 2^xa (pair) and eb = 2^xb (pair), returns ia = 1/(1+ea), ib = 1/(1+eb) from
-//   p = (1+ea)(1+eb) per pair,  inv = 1/(p0 p1),  q = (inv p1, inv p0) = 1/p,
-//   ia = (1+eb) q,  ib = (1+ea) q.
-// Inputs are clamped to x <= 30 so that p0 p1 <= 2^121 stays finite; the clamp moves a sigmoid by
-// < 1e-9 (the gate is saturated: pre-activation beyond 20.8).
-__device__ __forceinline__ void sigmoid4_den(f32x2 x01, f32x2 x23, f32x2& ia, f32x2& ib) {
-    float x0, x1, x2, x3;
-    upk2(x01, x0, x1); upk2(x23, x2, x3);
-    const f32x2 ea = pk2(ex2_approx(fminf(x0, 30.0f)), ex2_approx(fminf(x1, 30.0f)));
-    const f32x2 eb = pk2(ex2_approx(fminf(x2, 30.0f)), ex2_approx(fminf(x3, 30.0f)));
-    const f32x2 b = add2(eb, pk2(1.0f, 1.0f));
-    const f32x2 p = fma2(ea, b, b);
-    float p0, p1;
-    upk2(p, p0, p1);
-    const float inv = rcp_approx(p0 * p1);
-    const f32x2 q = pk2(inv * p1, inv * p0);
-    ia = mul2(b, q);
-    ib = fma2(ea, q, q);
-}
-// pair -> packed f16 hi pair and f16 lo (residual) pair
-__device__ __forceinline__ void split_f16p(f32x2 v, uint32_t& hi, uint32_t& lo) {
-    float x, y;
-    upk2(v, x, y);
-    const __half2 h = __floats2half2_rn(x, y);
-    const float2 hf = __half22float2(h);
-    float rx, ry;
-    upk2(sub2(v, pk2(hf.x, hf.y)), rx, ry);
-    const __half2 l = __floats2half2_rn(rx, ry);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 // volatile: the W_hh fragments are loop-invariant, and hoisting them out of the step loop would cost
 // 96 registers per thread
 __device__ __forceinline__ uint4 lds128(const uint4* p) {
@@ -144,15 +66,6 @@ __device__ __forceinline__ uint4 lds128(const uint4* p) {
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "r"((uint32_t)__cvta_generic_to_shared(p)));
     return v;
-}
-
-// (x, y) -> packed f16 hi pair and f16 lo (residual) pair
-__device__ __forceinline__ void split_f16(float x, float y, uint32_t& hi, uint32_t& lo) {
-    const __half2 h = __floats2half2_rn(x, y);
-    const float2 hf = __half22float2(h);
-    const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h);
-    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 // D = A(16x16, row) * B(16x8, col) + C, f16 x f16 -> f32
@@ -545,6 +458,25 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
 
 }  // namespace iplan
 
+namespace iplan {
+// 0 = tcgen05 recurrence (gat_tc5.cu, default), 1 = mma.sync recurrence (gat_recur_kernel: kept as the cross-check)
+static int g_gat_impl = -1;
+static int gat_impl() {
+    if (g_gat_impl < 0) {
+        const char* e = getenv("IPLAN_GAT_IMPL");
+        g_gat_impl = (e && (e[0] == '1' || e[0] == 'm')) ? 1 : 0;
+    }
+    return g_gat_impl;
+}
+}  // namespace iplan
+
+extern "C" int iplan_gat_set_impl(int impl) {
+    IPLAN_REQUIRE(impl == 0 || impl == 1, "gat_set_impl: %d not in {0 (tcgen05), 1 (mma.sync)}", impl);
+    iplan::g_gat_impl = impl;
+    return 0;
+}
+extern "C" int iplan_gat_get_impl(void) { return iplan::gat_impl(); }
+
 extern "C" int64_t iplan_gat_scratch_floats(int n_envs, int n_agents, int n_slots) {
     return (int64_t)n_envs * n_agents * 2 * (n_slots - 1) * iplan::DLP;
 }
@@ -583,9 +515,14 @@ extern "C" int iplan_gat_step_ex(const float* gat_params, int64_t param_stride,
         conf_a = smem_a;
     }
     if (ev_begin) cudaEventRecord((cudaEvent_t)ev_begin, (cudaStream_t)stream);
-    gat_recur_kernel<<<dim3(n_envs, n_agents, 2), REC_THREADS, smem_r, (cudaStream_t)stream>>>(a);
-    count_launch();
-    int rc = check_launch("gat_step(recur)");
+    int rc;
+    if (gat_impl() == 0) {
+        rc = launch_gat_recur_tc5(a, n_agents, (cudaStream_t)stream);
+    } else {
+        gat_recur_kernel<<<dim3(n_envs, n_agents, 2), REC_THREADS, smem_r, (cudaStream_t)stream>>>(a);
+        count_launch();
+        rc = check_launch("gat_step(recur)");
+    }
     if (rc) return rc;
     if (ev_mid) cudaEventRecord((cudaEvent_t)ev_mid, (cudaStream_t)stream);
     gat_attend_kernel<<<dim3(n_envs, n_agents), GAT_THREADS, smem_a, (cudaStream_t)stream>>>(a);
