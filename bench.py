@@ -130,48 +130,65 @@ def ncu_traffic(kernel):
 
 
 def run_reference(args):
-    """--impl reference: the oracle port of the reference's CPU path on the host cores."""
+    """--impl reference: the reference's OWN CPU implementation of the path (oracle/_ref, staged unmodified by
+    oracle/make_ref.py) on the host cores; every step is the same FIXED sample (one full rollout timestep at 512 envs
+    inside the reference's ParallelRunner.run + one IPPOLearner.train at Bf=64), extrapolated to the step.  Falls back
+    to the oracle port (kind "port") only if oracle/_ref was not staged."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
-    from iplan_b200.config import make_args
-    from oracle import cpu_baseline as cb
-    a = make_args("highway", use_cuda=False, device="cpu")
-    cores = cb.usable_cpus()
-    torch.set_num_threads(cores)
+    from oracle import ref_driver as R
     Bl = args.envs_per_gpu
-    B, T = Bl * args.gpus, a.episode_limit
-    params = cb.random_params(a)
-    # size each step's sample from a probe so that K+W steps end within a few minutes
-    probe = cb.time_rollout_steps(a, params, 16, 1, warmup=0)
-    per_step_budget = max(4.0, min(20.0, 150.0 / (args.warmup + args.steps)))
-    Bs = Bl
-    while Bs > 16 and probe * (Bs / 16) > 0.6 * per_step_budget:
-        Bs //= 2
-    train_eps = 8
-    cb._log(f"{cores} threads, probe {probe:.2f} s at 16 envs -> each step: 1 timestep at {Bs} envs + update at {train_eps} episodes")
-    times = []
-    for it in range(args.warmup + args.steps):
-        t_step = cb.time_rollout_steps(a, params, Bs, 1, warmup=0, seed=it) * (Bl / Bs)
-        t_train = cb.time_train(a, params, train_eps, seed=it) * (Bl / train_eps)
-        cb._log(f"step {it}: timestep {t_step:.2f} s (scaled to {Bl} envs), update {t_train:.2f} s (scaled)")
-        if it >= args.warmup:
-            times.append((t_step, t_train))
-    t_step = sum(t[0] for t in times) / len(times)
-    t_train = sum(t[1] for t in times) / len(times)
+    T = 90
+    if R.available():
+        cores = R.usable_cpus()
+        torch.set_num_threads(cores)
+        runs = []
+        for it in range(args.warmup + args.steps):
+            m = R.measure(B=Bl, T=T, threads=cores, seed=it)
+            if it >= args.warmup:
+                runs.append(m)
+        t_step = sum(m["t_step"] for m in runs) / len(runs)
+        t_train = sum(m["t_train"] for m in runs) / len(runs)
+        kind, sample, sample_s = "reference", runs[-1]["sample"], sum(m["sample_s"] for m in runs) / len(runs)
+        n_agents, slots = 5, 55
+    else:
+        from iplan_b200.config import make_args
+        from oracle import cpu_baseline as cb
+        a = make_args("highway", use_cuda=False, device="cpu")
+        cores = cb.usable_cpus()
+        torch.set_num_threads(cores)
+        params = cb.random_params(a)
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            ts = cb.time_rollout_steps(a, params, 128, 1, warmup=0, seed=it) * (Bl / 128)
+            tt = cb.time_train(a, params, 8, seed=it) * (Bl / 8)
+            if it >= args.warmup:
+                times.append((ts, tt, time.perf_counter() - t0))
+        t_step = sum(t[0] for t in times) / len(times)
+        t_train = sum(t[1] for t in times) / len(times)
+        kind, sample_s = "port", sum(t[2] for t in times) / len(times)
+        sample = "oracle port (oracle/_ref not staged): 1 timestep at 128 envs x4, update at Bf=8 x64 in rows"
+        n_agents, slots = a.n_agents, a.max_vehicle_num
+    B = Bl * args.gpus
     # the CPU path does not shard: N x 512 envs cost N x the 512-env time
     step_s = (T * t_step + t_train) * args.gpus
     value = B * T / step_s
-    sample = (f"each step: 1 rollout timestep at {Bs} envs (scaled x{Bl / Bs:g}, x{T} timesteps) + one update at Bf={train_eps} "
-              f"episodes scaled x{Bl / train_eps:g} in rows; x{args.gpus} for the {B}-env job (no sharding on CPU); {cores} torch threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Hetero-Highway chaotic, 5 agents, 512 envs/GPU, T=90, 15 PPO epochs",
-                   "envs": B, "agents": a.n_agents, "slots": a.max_vehicle_num, "feat_dim": 2485},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "Hetero-Highway chaotic, 5 agents, 512 envs/GPU, T=90, 15 PPO epochs (BASELINE configs[2])",
+                   "envs": B, "envs_per_gpu": Bl, "agents": n_agents, "slots": slots, "feat_dim": 2485, "episode_limit": T,
+                   "ppo_epoch": 15},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": kind, "sample": sample,
+                         "t_rollout_step_s": t_step, "t_update_s": t_train},
+        "extrapolation": {"measured_s_per_step": sample_s,
+                          "step_s": f"{T} x t_rollout_step_s + t_update_s" + (f", x{args.gpus} (no sharding on CPU)" if args.gpus > 1 else ""),
+                          "note": "ms_per_step is the extrapolated full step (a full 512-env step of the reference takes ~10 min); "
+                                  "the timed sample per step is fixed, not probe-sized"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -319,10 +336,14 @@ def main():
     }
     log("gpu legs done" + ("; cpu baseline" if world == 1 and not args.no_cpu_baseline else ""))
     if world == 1 and not args.no_cpu_baseline:
-        from oracle import cpu_baseline as cb
-        from iplan_b200.config import make_args
-        cpu = cb.measure(make_args("highway", use_cuda=False, device="cpu"), B=Bl, rollout_steps=2, train_eps=32)
-        out["cpu_baseline"] = {"value": cpu["value"], "unit": "env-steps/s", "cores": cpu["cores"], "kind": "port",
+        from oracle import ref_driver as R
+        if R.available():
+            cpu, kind = R.measure(B=Bl, T=T), "reference"
+        else:
+            from oracle import cpu_baseline as cb
+            from iplan_b200.config import make_args
+            cpu, kind = cb.measure(make_args("highway", use_cuda=False, device="cpu"), B=Bl, rollout_steps=2, train_eps=32), "port"
+        out["cpu_baseline"] = {"value": cpu["value"], "unit": "env-steps/s", "cores": cpu["cores"], "kind": kind,
                                "sample": cpu["sample"], "t_rollout_step_s": cpu["t_step"], "t_update_s": cpu["t_train"]}
     print(json.dumps(out))
     if world > 1:
