@@ -213,15 +213,15 @@ class _Timers:
         setattr(obj, name, timed)
 
 
-def time_rollout_timestep(B, timesteps=1, seed=0, hazard=0.01):
+def time_rollout_timestep(B, timesteps=1, seed=0, hazard=0.01, warm=False):
     """Seconds of hot-path work per rollout timestep at B envs, measured inside the reference's OWN ParallelRunner.run
     (runners/ippo_parallel_runner.py:105-281) driving its own MAC / GAT / behaviour modules and EpisodeBatch on the
     synthetic env: select_actions_ippo + GAT_latent_update + latent_update + EpisodeBatch.update of one loop iteration.
     The runner's Python observation wrapper and the env are out of scope and not counted.
-    `timesteps` loop iterations are timed after one warm-up iteration."""
+    `timesteps` loop iterations are timed (after one untimed iteration if `warm`)."""
     activate()
     from components.episode_buffer import EpisodeBatch
-    args = ref_args("highway", batch_size_run=B, episode_limit=timesteps + 1, buffer_size=B, batch_size=B - 1)
+    args = ref_args("highway", batch_size_run=B, episode_limit=timesteps + (1 if warm else 0), buffer_size=B, batch_size=B - 1)
     sysm = build_reference(args, seed)
     runner = build_runner(sysm, SyntheticHostEnv(args, B, hazard, seed=112358 + seed))
     tm = _Timers()
@@ -249,7 +249,7 @@ def time_rollout_timestep(B, timesteps=1, seed=0, hazard=0.01):
             iters.append(cur)
         if cur is not None:
             cur[name] = cur.get(name, 0.0) + dt
-    timed = iters[1:] if len(iters) > 1 else iters
+    timed = iters[1:] if warm and len(iters) > 1 else iters
     per = {k: float(np.mean([it.get(k, 0.0) for it in timed])) for k in ("select_actions_ippo", "GAT_latent_update", "latent_update", "batch_update")}
     return sum(per.values()), per
 
@@ -306,7 +306,7 @@ def measure(B=512, T=90, threads=None, seed=0, rollout_envs=ROLLOUT_ENVS, update
     t_upd = t_upd_s * (B / update_episodes)
     _log(f"train() at Bf={update_episodes}: {t_upd_s:.2f} s -> {t_upd:.1f} s at Bf={B}")
     value = B * T / (T * t_step + t_upd)
-    sample = (f"the reference's own code (oracle/_ref): ParallelRunner.run loop iteration at {rollout_envs} envs (1 warm-up + 1 timed: "
+    sample = (f"the reference's own code (oracle/_ref): ParallelRunner.run at {rollout_envs} envs, one timed loop iteration ("
               f"select_actions_ippo + GAT_latent_update + latent_update + EpisodeBatch.update) x{T} timesteps"
               f"{'' if rollout_envs == B else f' x{B / rollout_envs:g} envs'}; IPPOLearner.insert_episode_batch + train at Bf={update_episodes} "
               f"(T={T}, 15 epochs, 5 agents) x{B / update_episodes:g} in rows; {threads} torch threads")
