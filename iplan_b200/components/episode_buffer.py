@@ -153,12 +153,15 @@ class EpisodeBatch:
         ts = slices[1]
         t_idx = range(*ts.indices(T1)) if isinstance(ts, slice) else list(ts)
         oh = onehot.reshape(-1, len(t_idx), d.A, d.n_actions).permute(2, 0, 1, 3)      # [A,b,t,n_act]
-        dst = self.packed[:, slices[0]]
+        bsel = slices[0]           # write THROUGH an index expression: a list / tensor `bs` would make `packed[:, bs]` a copy
+        if not isinstance(bsel, slice):
+            bsel = th.as_tensor(bsel, device=self.packed.device).long()
+        c0, c1 = d.col_act, d.col_act + d.n_actions
         for i, t in enumerate(t_idx):
             if t + 1 < T1:
-                dst[:, :, t + 1, d.col_act:d.col_act + d.n_actions] = oh[:, :, i]
+                self.packed[:, bsel, t + 1, c0:c1] = oh[:, :, i]
             if t == 0:
-                dst[:, :, 0, d.col_act:d.col_act + d.n_actions] = oh[:, :, i]
+                self.packed[:, bsel, 0, c0:c1] = oh[:, :, i]
 
     @staticmethod
     def _check_safe_view(v, dest):

@@ -164,8 +164,10 @@ class DcntrlMAC:
     def save_models(self, path):
         for i, agent in enumerate(self.agents):
             th.save({k: v.detach().cpu() for k, v in agent.state_dict().items()}, f"{path}/agent_{i}.th")
+        quirk = bool(getattr(self.args, "popart_cuda_quirk", False))      # CUDA reference: no v_out.* keys (modules/flat.py)
         for i, critic in enumerate(self.critics):
-            th.save({k: v.detach().cpu() for k, v in critic.state_dict().items()}, f"{path}/critic_{i}.th")
+            th.save({k: v.detach().cpu() for k, v in critic.state_dict().items() if not (quirk and k.startswith("v_out."))},
+                    f"{path}/critic_{i}.th")
 
     def load_models(self, paths):
         if len(paths) == 1:

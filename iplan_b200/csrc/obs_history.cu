@@ -10,8 +10,11 @@
 // newest row (:124-141).  Appending a zero row to a slot that does not exist yet changes nothing (its window is
 // zero), so the update is uniform over the N slots: shift the window left by one row, append the new row.
 //
-// One CTA per (env, agent): thread 0 walks the observed rows in order (first-seen order is sequential by
-// definition), the whole CTA then shifts the N x W x o window in place.
+// One CTA per (env, agent).  Slot assignment is done by warp 0, 32 observed rows at a time: every lane looks its id up
+// in the agent's slot table; rows with an unknown id find the first row of the same id among themselves
+// (__match_any_sync) and the leaders take consecutive new slots in row order (ballot + popc) = first-seen order.  Of
+// several rows with the same id the LAST one provides the values (a deque's last append), decided by the same match
+// mask, so there is no write race.  The whole CTA then shifts the N x W x o window in place.
 #include "common.cuh"
 
 namespace iplan {
@@ -24,35 +27,53 @@ __global__ void __launch_bounds__(OBS_THREADS) obs_history_step_kernel(
     const float* __restrict__ obs, int n_obs, int obs_dim, int32_t* __restrict__ slot_ids, int32_t* __restrict__ slot_count,
     float* __restrict__ window, float* __restrict__ single, int32_t* __restrict__ overflow, int N, int W) {
     extern __shared__ float s_new[];                   // [N][o] the rows appended this step
-    __shared__ int s_slot[OBS_MAX_ROWS];
     const int ka = blockIdx.x, tid = threadIdx.x;
     const int o = obs_dim - 1;
     const float* ob = obs + (int64_t)ka * n_obs * obs_dim;
     int32_t* ids = slot_ids + (int64_t)ka * N;
 
     for (int idx = tid; idx < N * o; idx += OBS_THREADS) s_new[idx] = 0.0f;
-    if (tid == 0) {
-        int count = slot_count[ka];
-        for (int j = 0; j < n_obs; ++j) {
-            bool any = false;                          // np.any(obs[k, i, j, :]) — the id column included (:80)
-            for (int c = 0; c < obs_dim; ++c) any |= ob[j * obs_dim + c] != 0.0f;
-            int slot = -1;
-            if (any) {
-                const int id = (int)ob[j * obs_dim];   // int(...) truncation, as :81
-                for (int q = 0; q < count; ++q) if (ids[q] == id) { slot = q; break; }
-                if (slot < 0) {
-                    if (count < N) { slot = count; ids[count++] = id; }
-                    else atomicExch(overflow, 1);      // the reference would raise IndexError at :116
-                }
-            }
-            s_slot[j] = slot;
-        }
-        slot_count[ka] = count;
-    }
     __syncthreads();
-    for (int idx = tid; idx < n_obs * o; idx += OBS_THREADS) {
-        const int j = idx / o, c = idx - j * o;
-        if (s_slot[j] >= 0) s_new[s_slot[j] * o + c] = ob[j * obs_dim + 1 + c];     // a later row of the same id wins, as a deque's last append
+    if (tid < 32) {
+        const int lane = tid;
+        int count = slot_count[ka];                                    // warp-uniform
+        for (int j0 = 0; j0 < n_obs; j0 += 32) {                       // chunks in row order: later rows see earlier chunks' slots
+            const int j = j0 + lane;
+            bool any = false;                                          // np.any(obs[k, i, j, :]) — the id column included (:80)
+            int id = 0;
+            if (j < n_obs) {
+                for (int c = 0; c < obs_dim; ++c) any |= ob[j * obs_dim + c] != 0.0f;
+                id = (int)ob[j * obs_dim];                             // int(...) truncation, as :81
+            }
+            int slot = -1;
+            if (any)
+                for (int q = 0; q < count; ++q) if (ids[q] == id) { slot = q; break; }
+            // rows whose id is not in the table yet: group by id, the first row of a group opens the slot
+            const bool fresh = any && slot < 0;
+            const unsigned fresh_mask = __ballot_sync(0xffffffffu, fresh);
+            unsigned same = 0u;
+            if (fresh) same = __match_any_sync(fresh_mask, id);
+            const bool leader = fresh && (__ffs(same) - 1) == lane;
+            const unsigned leaders = __ballot_sync(0xffffffffu, leader);
+            int new_slot = -1;
+            if (leader) {
+                new_slot = count + __popc(leaders & ((1u << lane) - 1u));
+                if (new_slot < N) ids[new_slot] = id;
+                else { new_slot = -1; atomicExch(overflow, 1); }       // the reference would raise IndexError at :116
+            }
+            const int lead_lane = fresh ? __ffs(same) - 1 : 0;
+            const int got = __shfl_sync(0xffffffffu, new_slot, lead_lane);
+            if (fresh) slot = got;
+            count = min(N, count + __popc(leaders));
+            // values: of the rows that share a slot in this chunk the last one writes (later chunks overwrite in order)
+            const unsigned valid = __ballot_sync(0xffffffffu, slot >= 0);
+            unsigned grp = 0u;
+            if (slot >= 0) grp = __match_any_sync(valid, slot);
+            if (slot >= 0 && (31 - __clz(grp)) == lane)
+                for (int c = 0; c < o; ++c) s_new[slot * o + c] = ob[j * obs_dim + 1 + c];
+            __syncwarp();
+        }
+        if (lane == 0) slot_count[ka] = count;
     }
     __syncthreads();
     // shift left by one row and append: element (slot, w, c) <- (slot, w + 1, c); read everything, barrier, write

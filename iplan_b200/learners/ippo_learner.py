@@ -21,7 +21,7 @@ import math
 import torch as th
 
 from .. import _lib, parallel
-from ..modules.flat import DEAD, FROZEN
+from ..modules.flat import DEAD, FROZEN, POPART_KEYS
 
 
 class _AdamSlot:
@@ -32,12 +32,19 @@ class _AdamSlot:
     def __init__(self, owner, kind, index):
         self.owner, self.kind, self.index = owner, kind, index
 
-    def _entries(self):
+    def _entries(self, cuda_format=None):
+        """(param id, name, shape, offset, numel) in torch's parameter order.  In the CUDA reference's format the
+        critic has no v_out.* parameters (modules/flat.py POPART_KEYS): ids run over the 20 trunk tensors only."""
         stack = self.owner.stacks[self.kind]
-        out = []
-        for pi, ((name, shape), off) in enumerate(zip(stack.spec, stack.offsets)):
+        if cuda_format is None:
+            cuda_format = self.owner.popart_cuda_quirk
+        out, pi = [], 0
+        for (name, shape), off in zip(stack.spec, stack.offsets):
+            if cuda_format and self.kind == "critic" and name in POPART_KEYS:
+                continue
             n = int(math.prod(shape)) if len(shape) else 1
             out.append((pi, name, shape, off, n))
+            pi += 1
         return out
 
     def state_dict(self):
@@ -45,6 +52,8 @@ class _AdamSlot:
         st = {}
         for pi, name, shape, off, n in self._entries():
             if name in FROZEN or name.startswith(DEAD[0]) or o.steps[self.kind] == 0:
+                continue
+            if o.popart_cuda_quirk and name in POPART_KEYS:
                 continue
             st[pi] = {"step": th.tensor(float(o.steps[self.kind])),
                       "exp_avg": o.exp_avg[self.kind][self.index, off:off + n].view(shape).detach().cpu().clone(),
@@ -56,7 +65,12 @@ class _AdamSlot:
 
     def load_state_dict(self, sd):
         o = self.owner
-        for pi, name, shape, off, n in self._entries():
+        # parameter ids are positional: pick the format (26 critic params = CPU reference, 20 = CUDA reference) by count
+        n_params = len(sd["param_groups"][0]["params"])
+        fmt = None
+        if self.kind == "critic":
+            fmt = n_params == len(self._entries(cuda_format=True))
+        for pi, name, shape, off, n in self._entries(cuda_format=fmt):
             if pi in sd["state"]:
                 s = sd["state"][pi]
                 o.exp_avg[self.kind][self.index, off:off + n] = s["exp_avg"].reshape(-1).to(o.device)
@@ -98,7 +112,10 @@ class IPPOLearner:
         self.stacks = {"actor": mac.actor_stack, "critic": mac.critic_stack}
         self.exp_avg = {k: th.zeros_like(s.flat) for k, s in self.stacks.items()}
         self.exp_avg_sq = {k: th.zeros_like(s.flat) for k, s in self.stacks.items()}
-        self.masks = {k: s.trainable_mask().to(self.device) for k, s in self.stacks.items()}
+        # True: behave like a CUDA run of the reference (PopArt value head never registered: frozen, absent from checkpoints)
+        self.popart_cuda_quirk = bool(getattr(args, "popart_cuda_quirk", False))
+        frozen = {"actor": (), "critic": ("v_out.weight", "v_out.bias") if self.popart_cuda_quirk else ()}
+        self.masks = {k: s.trainable_mask(frozen[k]).to(self.device) for k, s in self.stacks.items()}
         self.steps = {"actor": 0, "critic": 0}
         self.lrs = {"actor": self.lr, "critic": self.critic_lr}
         self.actor_optimizers = [_AdamSlot(self, "actor", i) for i in range(self.n_agents)]
@@ -153,23 +170,26 @@ class IPPOLearner:
         if self.store is None or self.store["X"].shape[-1] != Fp:
             self._alloc_store(Fp)
         Bf = self.buffer_size
-        over = self.count + B - Bf
-        if over > 0:                 # deque(maxlen): the oldest episodes fall out
+        first = max(0, B - Bf)       # deque(maxlen): of a batch longer than the buffer only the last Bf episodes survive
+        nb = B - first
+        over = self.count + nb - Bf
+        if over > 0:                 # the oldest episodes fall out
             keep = self.count - over
-            for v in self.store.values():
-                v[:, :keep] = v[:, over:self.count].clone()
+            if keep > 0:
+                for v in self.store.values():
+                    v[:, :keep] = v[:, over:self.count].clone()
             self.count = keep
-        sl = slice(self.count, self.count + B)
+        sl = slice(self.count, self.count + nb)
         dev = self.device
         s = self.store
-        s["X"][:, sl] = X
-        s["rnn_a"][:, sl] = ep_batch["rnn_states_actors"].to(dev).permute(2, 0, 1, 3)
-        s["rnn_c"][:, sl] = ep_batch["rnn_states_critics"].to(dev).permute(2, 0, 1, 3)
-        s["actions"][:, sl] = ep_batch["actions"].to(dev)[..., 0].permute(2, 0, 1).to(th.int32)
-        s["avail"][:, sl] = (ep_batch["avail_actions"].to(dev) != 0).permute(2, 0, 1, 3).to(th.uint8)
-        s["reward"][:, sl] = ep_batch["reward"].to(dev)[..., 0].permute(2, 0, 1)
-        s["alive"][:, sl] = 1.0 - ep_batch["terminated"].to(dev)[..., 0].permute(2, 0, 1).float()
-        self.count += B
+        s["X"][:, sl] = X[:, first:]
+        s["rnn_a"][:, sl] = ep_batch["rnn_states_actors"][first:].to(dev).permute(2, 0, 1, 3)
+        s["rnn_c"][:, sl] = ep_batch["rnn_states_critics"][first:].to(dev).permute(2, 0, 1, 3)
+        s["actions"][:, sl] = ep_batch["actions"][first:].to(dev)[..., 0].permute(2, 0, 1).to(th.int32)
+        s["avail"][:, sl] = (ep_batch["avail_actions"][first:].to(dev) != 0).permute(2, 0, 1, 3).to(th.uint8)
+        s["reward"][:, sl] = ep_batch["reward"][first:].to(dev)[..., 0].permute(2, 0, 1)
+        s["alive"][:, sl] = 1.0 - ep_batch["terminated"][first:].to(dev)[..., 0].permute(2, 0, 1).float()
+        self.count += nb
 
     def can_sample(self):
         return self.count == self.buffer_size

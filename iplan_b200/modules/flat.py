@@ -86,6 +86,12 @@ def critic_spec(feat_dim):
 
 FROZEN = ("v_out.stddev", "v_out.mean", "v_out.mean_sq", "v_out.debiasing_term")
 DEAD = ("base.mlp.fc_h.",)       # cloned into fc2 then never called (mlp.py:20-27): grad stays None
+# PopArt on CUDA (utils/mappo_utils/popart.py:21-27): ``nn.Parameter(...).to(device)`` returns plain tensors, so a
+# reference run with use_cuda=True has NO v_out.* entries in critic.state_dict(), 20 (not 26) optimiser params and a
+# value head frozen at its initial value.  The CPU reference (the oracle, the golden fixtures) registers and trains
+# them.  ``args.popart_cuda_quirk = True`` reproduces the CUDA behaviour (frozen head, 20-key checkpoints); loading
+# accepts either checkpoint format in both modes.
+POPART_KEYS = ("v_out.weight", "v_out.bias") + FROZEN
 
 
 class AgentNet(nn.Module):
@@ -119,6 +125,15 @@ class AgentNet(nn.Module):
 
     def forward(self, *a, **k):
         raise RuntimeError("AgentNet holds parameters only; the arithmetic runs in libiplan_b200.so")
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """As nn.Module.load_state_dict; a critic checkpoint written by a CUDA run of the reference has no ``v_out.*``
+        keys (see POPART_KEYS): those tensors then keep their current (initial) values."""
+        if strict and self._stack.kind == "critic":
+            missing = [k for k in self.state_dict() if k not in state_dict]
+            if missing and all(k in POPART_KEYS for k in missing) and not [k for k in state_dict if k not in self.state_dict()]:
+                return super().load_state_dict(state_dict, strict=False, **kw)
+        return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def _apply(self, fn, recurse=True):       # .cuda()/.to(): move the whole stack, then re-view
         self._stack._move(fn)
@@ -159,12 +174,12 @@ class ParamStack:
     def named_offsets(self):
         return {name: (off, shape) for (name, shape), off in zip(self.spec, self.offsets)}
 
-    def trainable_mask(self):
+    def trainable_mask(self, frozen_extra=()):
         """1.0 where Adam may move a value (excludes padding, PopArt statistics and
         the dead fc_h tensors, which the reference's optimiser never touches)."""
         m = torch.zeros(self.total)
         for (name, shape), off in zip(self.spec, self.offsets):
-            if name in FROZEN or name.startswith(DEAD[0]):
+            if name in FROZEN or name.startswith(DEAD[0]) or name in frozen_extra:
                 continue
             n = int(math.prod(shape)) if len(shape) else 1
             m[off:off + n] = 1.0

@@ -15,7 +15,12 @@ place: ``window.view(B, A, N, W * o).permute(1, 0, 2, 3)`` is K1b's input layout
 Differences from the reference, by design: outputs are float32 (the reference builds float64 arrays that every consumer
 casts to float32); a vehicle id repeated within one observation keeps its last row (the reference's deque would take two
 appends in one timestep); meeting more than ``max_vehicle_num`` distinct ids raises (the reference fails with IndexError at
-output time).  ``obs_history_episode_output`` (used only by the auxiliary learners) is not built.
+output time).
+
+Beyond the reference's surface: ``step(obs_device)`` is the hook a vectorised (device-resident) simulator calls once per
+timestep with its raw observation tensor — it runs the kernel and returns the ``(single, window)`` CUDA tensors, no host
+round trip.  ``obs_history_episode_output(mask)`` (reference :145-173; unused by the reference's own training loop) is
+served from a per-episode log of the appended rows kept on the device (``record_episode=True``).
 """
 import numpy as np
 import torch
@@ -36,6 +41,9 @@ class observersation_state_history_wrapper:
         self.n_threads = args.batch_size_run
         self.device = torch.device("cuda")
         self.slot_ids = self.slot_count = self.window = self.single = self._overflow = None
+        self.record_episode = True        # keep every appended row of the episode (for obs_history_episode_output)
+        self.episode_log = None           # [B, A, N, max_episode_len + 1, o], column t = the rows appended at call t
+        self.calls = 0
 
     def _alloc(self, B, A):
         N, W, o, dev = self.max_vehicle_num, self.max_history_len, self.obs_shape, self.device
@@ -44,6 +52,7 @@ class observersation_state_history_wrapper:
         self.window = torch.zeros(B, A, N, W, o, device=dev)
         self.single = torch.zeros(B, A, N, o, device=dev)
         self._overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.episode_log = torch.zeros(B, A, N, self.max_episode_len + 1, o, device=dev) if self.record_episode else None
 
     def agent_obs_profile_init(self, obs):
         """Reference :25-45.  ``obs`` [B, A, n_obs, obs_dim] (numpy or tensor); only its shape is used here."""
@@ -52,19 +61,53 @@ class observersation_state_history_wrapper:
             self._alloc(B, A)
         else:
             self.slot_ids.fill_(-1); self.slot_count.zero_(); self.window.zero_(); self.single.zero_(); self._overflow.zero_()
+            if self.episode_log is not None:
+                self.episode_log.zero_()
+        self.calls = 0
         return self.slot_ids
+
+    def step(self, obs_device):
+        """Hook for a device-resident simulator: ``obs_device`` [B, A, n_obs, 1 + o] CUDA fp32 (column 0 = vehicle id).
+        Runs the slot assignment + window update on the current stream and returns ``(single [B,A,N,o], window
+        [B,A,N,W,o])`` — the tensors K1 / K1b read in place; nothing crosses PCIe."""
+        x = obs_device
+        assert torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        B, A, M, od = x.shape
+        assert od == self.obs_shape + 1, (od, self.obs_shape)
+        if self.window is None or tuple(self.window.shape[:2]) != (B, A):
+            self.agent_obs_profile_init(x)
+        _lib.check(_lib.lib.iplan_obs_history_step(
+            _lib.ptr(x), B, A, M, od, _lib.ptr(self.slot_ids), _lib.ptr(self.slot_count), _lib.ptr(self.window),
+            _lib.ptr(self.single), _lib.ptr(self._overflow), self.max_vehicle_num, self.max_history_len, _lib.stream()),
+            "obs_history_step")
+        if self.episode_log is not None and self.calls <= self.max_episode_len:
+            self.episode_log[:, :, :, self.calls] = self.single
+        self.calls += 1
+        return self.single, self.window
 
     def obs_history_create(self, obs):
         """Reference :68-97.  Returns (agent ids [B, A] int tensor, slot table [B, A, N] int32, window tensor)."""
         x = obs if torch.is_tensor(obs) and obs.is_cuda else _lib.to_device(np.asarray(obs))
         x = x.to(torch.float32).contiguous()
-        B, A, M, od = x.shape
-        assert od == self.obs_shape + 1, (od, self.obs_shape)
-        _lib.check(_lib.lib.iplan_obs_history_step(
-            _lib.ptr(x), B, A, M, od, _lib.ptr(self.slot_ids), _lib.ptr(self.slot_count), _lib.ptr(self.window),
-            _lib.ptr(self.single), _lib.ptr(self._overflow), self.max_vehicle_num, self.max_history_len, _lib.stream()),
-            "obs_history_step")
+        self.step(x)
         return x[:, :, 0, 0].to(torch.int64), self.slot_ids, self.window
+
+    def obs_history_episode_output(self, mask):
+        """Reference :145-173: the whole episode's rows of every slot, right aligned in ``max_episode_len`` columns and
+        multiplied by ``mask[k, column, agent]``; returns (raw [B,A,N,L,o], the same reshaped [B,A,N,L/W,W,o])."""
+        self._check()
+        if self.episode_log is None:
+            raise RuntimeError("obs_history_episode_output needs record_episode=True")
+        L, W = self.max_episode_len, self.max_history_len
+        B, A, N, _, o = self.episode_log.shape
+        n = min(self.calls, L)                                  # a deque(maxlen=L) keeps the last L rows
+        raw = torch.zeros(B, A, N, L, o, device=self.device)
+        raw[:, :, :, L - n:] = self.episode_log[:, :, :, self.calls - n:self.calls]
+        m = torch.as_tensor(np.asarray(mask), dtype=torch.float32, device=self.device)      # [B, L, A]
+        raw = raw * m.permute(0, 2, 1)[:, :, None, :, None]
+        # rows of a slot that did not exist yet are zero either way: the reference writes only len(history) columns
+        raw_h = _lib.to_host(raw)
+        return raw_h, raw_h.reshape(B, A, N, int(L // W), W, o)
 
     def _check(self):
         if int(self._overflow.item()):

@@ -314,3 +314,56 @@ def test_obs_history_kernel_vs_reference_golden(golden_dir):
     wr.agent_obs_profile_init(g["steps"][0]["obs"].numpy())
     wr.obs_history_create(g["steps"][0]["obs"].numpy())
     assert (wr.obs_history_output() == g["steps"][0]["window"].numpy()).all()
+
+
+def test_obs_wrapper_full_episode_vs_reference_wrapper():
+    """A whole 91-observation episode (vehicles enter, leave and re-enter the agents' view; more observations than the
+    deque's maxlen): every timestep's obs_single_history_output / obs_history_output and the final
+    obs_history_episode_output(mask) bit-equal to the REFERENCE'S OWN wrapper (oracle/_ref/observation_wrapper.py,
+    staged unmodified) run beside it on the CPU; the device `step()` hook returns the same tensors without a host copy."""
+    _need_gpu()
+    from oracle import ref_driver as R
+    if not R.available():
+        pytest.skip("oracle/_ref not staged (python oracle/make_ref.py in the build container)")
+    R.activate()
+    from observation_wrapper import observersation_state_history_wrapper as RefWrapper
+    from iplan_b200.config import make_args
+    from iplan_b200.observation_wrapper import observersation_state_history_wrapper as Wrapper
+    B, M = 4, 15
+    args = make_args("highway", batch_size_run=B, use_cuda=True, device="cuda")
+    A, N, W, o, L = args.n_agents, args.max_vehicle_num, args.max_history_len, args.obs_shape_single, args.episode_limit
+    ref = RefWrapper(R.ref_args("highway", batch_size_run=B), A, N, L, W)
+    own = Wrapper(args, A, N, L, W)
+    own2 = Wrapper(args, A, N, L, W)                    # driven through the device hook
+    rng = np.random.default_rng(99)
+    pool = np.arange(1000, 1000 + N - 1)                # <= N - 1 other vehicles ever: the table never overflows
+    for t in range(L + 1):
+        obs = np.zeros((B, A, M, o + 1))
+        for k in range(B):
+            for i in range(A):
+                n_seen = rng.integers(2, M + 1)
+                hi = min(len(pool), 8 + t)              # the set an agent may meet grows; earlier ones drop out and return
+                seen = rng.choice(pool[:hi], size=min(n_seen - 1, hi), replace=False)
+                obs[k, i, 0, 0] = 7 + i
+                obs[k, i, 0, 1:] = rng.uniform(-1, 1, size=o)
+                obs[k, i, 1:1 + len(seen), 0] = seen
+                obs[k, i, 1:1 + len(seen), 1:] = rng.uniform(-1, 1, size=(len(seen), o))
+        obs32 = obs.astype(np.float32).astype(np.float64)      # both sides see fp32-representable values
+        if t == 0:
+            ref.agent_obs_profile_init(obs32)
+            own.agent_obs_profile_init(obs32)
+        ref.obs_history_create(obs32)
+        own.obs_history_create(obs32)
+        s_dev, w_dev = own2.step(torch.as_tensor(obs32, dtype=torch.float32).cuda().contiguous())
+        rs, rw = ref.obs_single_history_output(), ref.obs_history_output()
+        assert (own.obs_single_history_output() == rs.astype(np.float32)).all(), t
+        assert (own.obs_history_output() == rw.astype(np.float32)).all(), t
+        assert torch.equal(s_dev, own.single) and torch.equal(w_dev, own.window)
+    for k in range(B):
+        for i in range(A):
+            assert own.slot_ids[k, i, :len(ref.obs_vehicle_id[k][i])].tolist() == list(ref.obs_vehicle_id[k][i])
+    mask = (rng.uniform(size=(B, L, A)) < 0.8).astype(np.float64)
+    raw_ref, ep_ref = ref.obs_history_episode_output(mask)
+    raw, ep = own.obs_history_episode_output(mask)
+    assert raw.shape == raw_ref.shape and ep.shape == ep_ref.shape
+    assert (raw == raw_ref.astype(np.float32)).all() and (ep == ep_ref.astype(np.float32)).all()
