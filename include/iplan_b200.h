@@ -111,6 +111,19 @@ int iplan_behavior_step(const float* beh_params, int64_t param_stride,
                         int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int hist_len,
                         void* stream);
 
+/* iplan_behavior_step reading the window rows in place from a time-strided store (no shifted copy of the window):
+ *   win_stride_step == 0   as iplan_behavior_step: `window` is [a][b][n][hist_len*obs_dim], rows contiguous
+ *   win_stride_step != 0   window row w (0 = oldest) of a node is at window.ptr + (w - win_pad) * win_stride_step for
+ *                          w >= win_pad and all-zero for w < win_pad (observation_wrapper.py:101-119 pads in front);
+ *                          e.g. the packed episode store: window.ptr -> history at time max(0, t - hist_len + 1),
+ *                          win_stride_step = the store's time stride, win_pad = max(0, hist_len - 1 - t). */
+int iplan_behavior_step_ex(const float* beh_params, int64_t param_stride,
+                           iplan_view window, int64_t win_stride_step, int win_pad,
+                           iplan_view hid_io, iplan_view lat_prev, iplan_view lat_out,
+                           float soft_coef,
+                           int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int hist_len,
+                           void* stream);
+
 /* ---- K1c: controller step (actor + critic, one timestep) -------------------------
  * replaces DcntrlMAC.select_actions_ippo (controllers/dcntrl_controller.py:27-58):
  * LayerNorm(F) -> fc1 -> ReLU -> LN -> fc2 -> ReLU -> LN -> 1-step GRU -> LN ->

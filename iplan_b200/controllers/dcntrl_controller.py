@@ -45,15 +45,20 @@ class DcntrlMAC:
 
     # ---- K1c on device tensors ------------------------------------------------------
     def controller_step(self, feat, rnn_a_in, rnn_c_in, rnn_a_out, rnn_c_out, avail_u8=None,
-                        test_mode=False, uniforms=None, next_onehot=None, this_onehot=None, logits=None):
+                        test_mode=False, uniforms=None, next_onehot=None, this_onehot=None, logits=None, out=None):
         """feat [A,B,>=F] rows (strided), rnn_* [A,B,64] (strided views).  Returns
-        (actions int32 [A,B], logp [A,B], values [A,B])."""
+        (actions int32 [A,B], logp [A,B], values [A,B]); ``out`` = caller-owned contiguous tensors for the three
+        (a rollout loop passes slices of per-episode buffers: no allocation, no copy per timestep)."""
         A, B = feat.shape[0], feat.shape[1]
         assert feat.stride(2) == 1 and rnn_a_in.stride(2) == 1 and rnn_a_out.stride(2) == 1
         assert rnn_a_in.stride() == rnn_c_in.stride() and rnn_a_out.stride() == rnn_c_out.stride()
-        actions = th.empty(A, B, dtype=th.int32, device=self.device)
-        logp = th.empty(A, B, device=self.device)
-        values = th.empty(A, B, device=self.device)
+        if out is not None:
+            actions, logp, values = out
+            assert actions.is_contiguous() and logp.is_contiguous() and values.is_contiguous() and actions.dtype == th.int32
+        else:
+            actions = th.empty(A, B, dtype=th.int32, device=self.device)
+            logp = th.empty(A, B, device=self.device)
+            values = th.empty(A, B, device=self.device)
         rc = _lib.lib.iplan_controller_step(
             _lib.ptr(self.actor_stack.flat), self.actor_stack.stride(),
             _lib.ptr(self.critic_stack.flat), self.critic_stack.stride(),

@@ -33,6 +33,8 @@ struct BehArgs {
     iplan_view window, hid, lat_prev, lat_out;
     float coef;
     int n_envs, n_slots, obs_dim, latent_dim, hist_len;
+    int64_t win_step;      // 0: window rows are contiguous ([hist_len][obs_dim] per node); else element stride between rows
+    int win_pad;           // (win_step != 0) leading window rows that are zero padding; window.ptr = the first real row
 };
 
 struct BehSmem {
@@ -135,7 +137,14 @@ __global__ void __launch_bounds__(BEH_THREADS, 2) behavior_step_kernel(BehArgs a
         const int nd = min(node_base + r, total_nodes - 1);
         const int bb = nd / N, nn = nd - bb * N;
         const float* src = a.window.ptr + ag * a.window.stride_agent + bb * a.window.stride_env + nn * a.window.stride_slot;
-        for (int q = lane; q < Wn * o; q += 32) S.win[warp][r][q] = src[q];
+        if (a.win_step == 0) {
+            for (int q = lane; q < Wn * o; q += 32) S.win[warp][r][q] = src[q];
+        } else {                                               // rows live `win_step` apart (e.g. the episode store's time axis)
+            for (int q = lane; q < Wn * o; q += 32) {
+                const int w = q / o, c = q - w * o;
+                S.win[warp][r][q] = w >= a.win_pad ? src[(int64_t)(w - a.win_pad) * a.win_step + c] : 0.0f;
+            }
+        }
     }
     float h[4][4];
     {
@@ -277,7 +286,18 @@ extern "C" int iplan_behavior_step(const float* beh_params, int64_t param_stride
                                    float soft_coef,
                                    int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int hist_len,
                                    void* stream) {
+    return iplan_behavior_step_ex(beh_params, param_stride, window, 0, 0, hid_io, lat_prev, lat_out, soft_coef,
+                                  n_envs, n_agents, n_slots, obs_dim, latent_dim, hist_len, stream);
+}
+
+extern "C" int iplan_behavior_step_ex(const float* beh_params, int64_t param_stride,
+                                      iplan_view window, int64_t win_stride_step, int win_pad,
+                                      iplan_view hid_io, iplan_view lat_prev, iplan_view lat_out,
+                                      float soft_coef,
+                                      int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int hist_len,
+                                      void* stream) {
     using namespace iplan;
+    IPLAN_REQUIRE(win_pad >= 0 && win_pad < hist_len, "behavior_step: win_pad %d not in [0,%d)", win_pad, hist_len);
     IPLAN_REQUIRE(obs_dim > 0 && obs_dim <= 7, "behavior_step: obs_dim %d not in [1,7]", obs_dim);
     IPLAN_REQUIRE(hist_len > 0 && hist_len * obs_dim <= WIN_MAX, "behavior_step: hist_len*obs_dim %d > %d", hist_len * obs_dim, WIN_MAX);
     IPLAN_REQUIRE(latent_dim > 0 && latent_dim <= LAT_MAX, "behavior_step: latent_dim %d not in [1,%d]", latent_dim, LAT_MAX);
@@ -290,6 +310,7 @@ extern "C" int iplan_behavior_step(const float* beh_params, int64_t param_stride
     a.window = window; a.hid = hid_io; a.lat_prev = lat_prev; a.lat_out = lat_out;
     a.coef = soft_coef;
     a.n_envs = n_envs; a.n_slots = n_slots; a.obs_dim = obs_dim; a.latent_dim = latent_dim; a.hist_len = hist_len;
+    a.win_step = win_stride_step; a.win_pad = win_stride_step ? win_pad : 0;
     const size_t smem = sizeof(BehSmem);
     static bool configured = false;
     if (!configured) {

@@ -95,12 +95,14 @@ class Behavior_policy:
         self.debug_keep = None      # uint8 [A, B, n_pos, N, W, 64] explicit dropout draw for the next learn() (parity runs)
 
     # ---- device path: tensors laid out [A, B, N, *] ----------------------------------
-    def behavior_step(self, window, hid_io, lat_prev, lat_out):
-        """window [A,B,N,W*o], hid_io [A,B,N,E] (in place), lat_prev/lat_out [A,B,N,L]."""
+    def behavior_step(self, window, hid_io, lat_prev, lat_out, win_stride_step=0, win_pad=0):
+        """window [A,B,N,W*o], hid_io [A,B,N,E] (in place), lat_prev/lat_out [A,B,N,L].
+        With ``win_stride_step`` != 0 the window is read in place from a time-strided store: ``window`` is the [A,B,N,o]
+        view of its oldest real row, later rows ``win_stride_step`` elements apart, ``win_pad`` leading rows are zeros."""
         A, B, N, _ = window.shape
-        rc = _lib.lib.iplan_behavior_step(
+        rc = _lib.lib.iplan_behavior_step_ex(
             _lib.ptr(self.stack.flat), self.stack.stride(),
-            _lib.view(window), _lib.view(hid_io), _lib.view(lat_prev), _lib.view(lat_out),
+            _lib.view(window), int(win_stride_step), int(win_pad), _lib.view(hid_io), _lib.view(lat_prev), _lib.view(lat_out),
             float(self.soft_update_coef), B, A, N, self.args.obs_shape_single, self.latent_dim,
             self.max_history_len, _lib.stream())
         _lib.check(rc, "behavior_step")

@@ -165,17 +165,16 @@ class ParallelRunner:
         enc_hid = th.zeros(A, B, N, E, device=dev)
         zeros_att = th.zeros(A, B, N, d.D, device=dev)
         zeros_beh = th.zeros(A, B, N, d.L, device=dev)
-        window = th.zeros(A, B, N, W * o, device=dev)                   # last W single histories, flattened
-        actions_all = th.empty(A, B, T + 1, dtype=th.int32, device=dev)
-        actions_all[:, :, T] = 0
+        # per-episode output buffers of K1c: [T+1][A][B], one contiguous [A][B] plane per timestep (no alloc / copy per step)
+        actions_steps = th.zeros(T + 1, A, B, dtype=th.int32, device=dev)
+        logp_steps = th.empty(T, A, B, device=dev)
+        value_steps = th.empty(T, A, B, device=dev)
         onehot_cols = packed[..., d.col_act:d.col_act + d.n_actions]    # [A,B,T+1,n_act] view
-
-        def push_history(t):
-            h = env.history[t].permute(1, 0, 2, 3)                      # [A,B,N,o]
-            hist_v[:, :, t] = h
-            if W > 1:
-                window[..., :(W - 1) * o] = window[..., o:].clone()
-            window[..., (W - 1) * o:] = h
+        # The synthetic simulator holds the whole episode's observations in HBM: they enter the episode store in ONE
+        # strided device copy (a live simulator would write row t each step through observation_wrapper.step()).  K1 reads
+        # row t, K1b reads its W-step window in place from rows t-W+1..t of the store: no shifted window copy per step.
+        hist_v.copy_(env.history.permute(2, 1, 0, 3, 4))
+        step_stride = packed.stride(2)
 
         events = getattr(self, "gat_events", None)
 
@@ -202,17 +201,18 @@ class ParallelRunner:
             events.append(("gat", ev[0], ev[2]))
             return out
 
-        push_history(0)
         gat(hist_v[:, :, 0], zeros_beh, zeros_att, att_v[:, :, 0])
         for t in range(T):
-            acts, _, _ = timed("ctrl", self.mac.controller_step,
-                packed[:, :, t], rnn_a[:, :, t], rnn_c[:, :, t], rnn_a[:, :, t + 1], rnn_c[:, :, t + 1],
-                None, test_mode=test_mode, next_onehot=onehot_cols[:, :, t + 1],
-                this_onehot=onehot_cols[:, :, 0] if t == 0 else None)
-            actions_all[:, :, t] = acts
-            push_history(t + 1)
+            timed("ctrl", self.mac.controller_step,
+                  packed[:, :, t], rnn_a[:, :, t], rnn_c[:, :, t], rnn_a[:, :, t + 1], rnn_c[:, :, t + 1],
+                  None, test_mode=test_mode, next_onehot=onehot_cols[:, :, t + 1],
+                  this_onehot=onehot_cols[:, :, 0] if t == 0 else None,
+                  out=(actions_steps[t], logp_steps[t], value_steps[t]))
             gat(hist_v[:, :, t + 1], beh_v[:, :, t], att_v[:, :, t], att_v[:, :, t + 1])
-            timed("beh", self.behavior_learner.behavior_step, window, enc_hid, beh_v[:, :, t], beh_v[:, :, t + 1])
+            first = max(0, t + 2 - W)                                   # oldest time inside the window of time t+1
+            timed("beh", self.behavior_learner.behavior_step, hist_v[:, :, first], enc_hid, beh_v[:, :, t], beh_v[:, :, t + 1],
+                  win_stride_step=step_stride, win_pad=max(0, W - (t + 2)))
+        actions_all = actions_steps.permute(1, 2, 0)                    # [A,B,T+1]
         # episode-level stores in the reference's layout [B,T+1,A,*]
         batch["actions"][..., 0] = actions_all.permute(1, 2, 0).long()
         batch["actions_onehot"].zero_().scatter_(-1, batch["actions"], 1.0)
