@@ -39,7 +39,7 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--envs-per-gpu", type=int, default=512)
-    p.add_argument("--e2e-steps", type=int, default=1)
+    p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     return p.parse_args()
@@ -288,7 +288,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         sysm.run_and_train(api=True)                        # warm-up of the API path
-        _lib.io_bytes["h2d"] = _lib.io_bytes["d2h"] = 0
+        _lib.io_bytes["h2d"] = _lib.io_bytes["d2h"] = _lib.io_bytes["h2d_saved"] = 0
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
@@ -300,6 +300,7 @@ def main():
         e2e = {"value": Bl * world * T / float(dt), "unit": "env-steps/s",
                "h2d_bytes_per_step": _lib.io_bytes["h2d"] // args.e2e_steps,
                "d2h_bytes_per_step": _lib.io_bytes["d2h"] // args.e2e_steps,
+               "h2d_bytes_not_reuploaded_per_step": _lib.io_bytes["h2d_saved"] // args.e2e_steps,
                "ms_per_step": float(dt) * 1e3, "steps": args.e2e_steps,
                "path": "GAT_latent_update/latent_update/EpisodeBatch.update/select_actions_ippo with numpy buffers every timestep"}
 

@@ -123,7 +123,37 @@ def view(t):
     return View(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2))
 
 
-io_bytes = {"h2d": 0, "d2h": 0}      # host<->device traffic of the reference-facing (numpy) API
+io_bytes = {"h2d": 0, "d2h": 0, "h2d_saved": 0}      # host<->device traffic of the reference-facing (numpy) API
+
+# ---- device shadows of arrays this package handed out ------------------------------------------
+# The reference's runner passes several results straight back into the next call (attention_latent, behavior_latent,
+# rnn states: runners/ippo_parallel_runner.py:222-266).  A numpy array returned by ``to_host(t, shadow=True)`` is made
+# READ-ONLY and remembered together with the (immutable) device tensor it was copied from; when the same array object
+# comes back, ``to_device`` returns that tensor instead of re-uploading it.  Identity + read-only means the content
+# cannot have changed; a copy or a modified array is simply uploaded as before.
+SHADOW = True
+_shadow = {}
+
+
+def _register_shadow(arr, dev_t):
+    import weakref
+    key = id(arr)
+    arr.flags.writeable = False
+
+    def _drop(_ref, key=key):
+        _shadow.pop(key, None)
+    _shadow[key] = (weakref.ref(arr, _drop), dev_t)
+
+
+def device_shadow(x):
+    """The device tensor an earlier ``to_host(..., shadow=True)`` produced `x` from, or None."""
+    import numpy as np
+    if not SHADOW or not isinstance(x, np.ndarray):
+        return None
+    e = _shadow.get(id(x))
+    if e is not None and e[0]() is x and not x.flags.writeable:
+        return e[1]
+    return None
 
 
 _copy_stream = None
@@ -137,6 +167,10 @@ def to_device(x, dtype=torch.float32, device="cuda"):
     stream, so the copy does not queue behind kernels already in flight on the compute stream."""
     import numpy as np
     global _copy_stream
+    sh = device_shadow(x)
+    if sh is not None:                       # an array we returned, handed straight back: already on the device
+        io_bytes["h2d_saved"] += sh.numel() * sh.element_size()
+        return sh.to(dtype)
     if torch.is_tensor(x):
         if x.is_cuda:
             return x.to(dtype)
@@ -156,14 +190,27 @@ def to_device(x, dtype=torch.float32, device="cuda"):
     return t.to(device)
 
 
-def to_host(t):
+def to_host(t, shadow=False):
     """CUDA tensor -> fresh numpy array (page-locked, from torch's caching host allocator, so that
-    the copy runs at PCIe speed and a later ``to_device`` of the same array does too)."""
+    the copy runs at PCIe speed and a later ``to_device`` of the same array does too).
+    ``shadow=True``: `t` will not be written again by the caller; the returned array is read-only and ``to_device``
+    of that same array object returns `t` without a copy (see ``device_shadow``)."""
     io_bytes["d2h"] += t.numel() * t.element_size()
     h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     h.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return h.numpy()
+    arr = h.numpy()
+    if shadow and SHADOW:
+        _register_shadow(arr, t)
+    return arr
+
+
+def adopt_host(h, dev_t):
+    """Pinned CPU tensor `h` filled from the immutable device tensor `dev_t` -> read-only numpy array with a shadow."""
+    arr = h.numpy()
+    if SHADOW:
+        _register_shadow(arr, dev_t)
+    return arr
 
 
 def pinned_numpy(t):

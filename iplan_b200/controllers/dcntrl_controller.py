@@ -97,8 +97,8 @@ class DcntrlMAC:
         values_np = _lib.to_host(values.t())                                        # [B,A]
         actions_np = _lib.to_host(actions.t().to(th.int64))
         action_log_probs = [logp[a].view(B, 1) for a in range(A)]                   # list[A] of [B,1]
-        rnn_a_np = _lib.to_host(new_a.permute(1, 0, 2).unsqueeze(0))                # [1,B,A,R]
-        rnn_c_np = _lib.to_host(new_c.permute(1, 0, 2).unsqueeze(0))
+        rnn_a_np = _lib.to_host(new_a.permute(1, 0, 2).unsqueeze(0), shadow=True)   # [1,B,A,R]; handed back via batch.update
+        rnn_c_np = _lib.to_host(new_c.permute(1, 0, 2).unsqueeze(0), shadow=True)
         return values_np, actions_np, action_log_probs, rnn_a_np, rnn_c_np
 
     # ---- learner-facing evaluation helpers (reference :61-85); bound by the learner ----
