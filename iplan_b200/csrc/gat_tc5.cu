@@ -14,7 +14,10 @@
 // (registers) and the neighbour part Q (shared memory, broadcast: a step touches two Q rows), sigmoid / tanh through
 // ex2 + a shared rcp, new h -> f16 hi/lo -> the operand tile, the per-step hard-attention logit difference -> dl.
 // The two tiles (directions) interleave on the SM: while one tile's gates run on the MUFU / FMA pipes the other
-// tile's product runs on the tensor core.  Two single-lane MMA issuers (warps 8, 9), one per tile.
+// tile's product runs on the tensor core.  8 warps = 2 per scheduler, so a thread may use up to 255 registers (a
+// scheduler's register file holds 16 K: a third warp would cap the kernel at 168).  No separate issuer warps: once the
+// four warps of a tile have passed their named barrier (h tile written), lane 0 of the tile's first warp issues the
+// six MMAs and commits them to the tile's mbarrier, which all four warps then wait on.
 //
 // Prologue, also on the tensor core: enc = ReLU(W_e x + b) per row (thread = row, fp32 FMA, K <= 16), then
 // [P | Q] = enc . [W_ih[:, :H] | W_ih[:, H:]]^T as ONE M 128 x N 192 product per direction; P lands in the TMEM lane of
@@ -27,7 +30,7 @@
 
 namespace iplan {
 
-constexpr int G5_THREADS = 320;             // warps 0-3 gate fwd | 4-7 gate rev | 8 MMA fwd (+TMEM owner) | 9 MMA rev
+constexpr int G5_THREADS = 256;             // warps 0-3: tile 0 (forward direction) | warps 4-7: tile 1 (reverse)
 constexpr int G5_TMEM_COLS = 512;
 constexpr int G5_A_BYTES = 128 * 128;       // h operand tile: 128 rows x (32 hi + 32 lo) f16
 constexpr int G5_BHH_BYTES = G3 * 128;      // W_hh operand tile: 96 rows
@@ -60,7 +63,7 @@ __device__ __forceinline__ void tc5_wait_ld8(float (&a)[8]) {
                  : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]) :: "memory");
 }
 
-__global__ void __maxnreg__(200) gat_recur_tc5_kernel(GatArgs a) {
+__global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a) {
     extern __shared__ unsigned char g5_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ag = blockIdx.y, b0 = blockIdx.x * 2;
@@ -77,16 +80,15 @@ __global__ void __maxnreg__(200) gat_recur_tc5_kernel(GatArgs a) {
     float* s_bn = s_pb + 2 * G3;                                    // [2][32] K_N b_hn
     float* s_lw = s_bn + 2 * H;                                     // [2][32] logit-difference weights
     const uint32_t bars = base + G5_OFF_BAR;
-    auto a_ready = [&](int t) { return bars + 8u * t; };            // gate warps -> MMA issuer: h tile of the step written
-    auto d_full = [&](int t) { return bars + 8u * (2 + t); };       // MMA issuer -> gate warps: accumulator complete
+    auto d_full = [&](int t) { return bars + 8u * (2 + t); };       // MMA issuer -> the tile's warps: accumulator complete
     const uint32_t pro_bar = bars + 32u, tmem_slot = bars + 40u;
 
     if (tid == 0) {
-        for (int t = 0; t < 2; ++t) { mbar_init(a_ready(t), 4); mbar_init(d_full(t), 1); }
+        for (int t = 0; t < 2; ++t) mbar_init(d_full(t), 1);
         mbar_init(pro_bar, 1);
         mbar_init_fence();
     }
-    if (warp == 8) tc5_alloc<G5_TMEM_COLS>(tmem_slot);
+    if (warp == 0) tc5_alloc<G5_TMEM_COLS>(tmem_slot);
 
     // ---- inputs of this thread's row (threads 0..127): x = [history | behaviour latent] ----------
     float x[IN_MAX];
@@ -186,7 +188,7 @@ __global__ void __maxnreg__(200) gat_recur_tc5_kernel(GatArgs a) {
 
     constexpr uint32_t IDESC_IH = tc5_idesc(128, 2 * G3), IDESC_HH = tc5_idesc(128, G3);
     constexpr int PQ_COL = 128;                               // [P | Q] fwd at TMEM columns 128..319, rev at 320..511
-    if (warp == 8 && lane == 0) {
+    if (tid == 0) {
         tc5_fence_after();
         const uint64_t da = tc5_smem_desc(base + G5_OFF_A);
 #pragma unroll
@@ -203,8 +205,8 @@ __global__ void __maxnreg__(200) gat_recur_tc5_kernel(GatArgs a) {
         tc5_commit(pro_bar);
     }
 
-    if (warp < 8) {
-        // ================= gate warps: thread = chain `row` of tile (direction) t =================
+    {
+        // ================= thread = chain `row` of tile (direction) t =================
         const int t = warp >> 2, row = (warp & 3) * 32 + lane;
         const int e = row >> 6, i = row & 63, b = b0 + e;
         const bool ok = i < N && b < a.n_envs;
@@ -246,8 +248,21 @@ __global__ void __maxnreg__(200) gat_recur_tc5_kernel(GatArgs a) {
         tc5_fence_before();
         __syncthreads();                                        // Q tables complete, TMEM [P | Q] columns free
         tc5_fence_after();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_ready(t));                 // step 0 may start
+        // the tile's product h . W_hh^T: issued by one lane once the tile's four warps have written h (named barrier)
+        const bool issuer = (warp & 3) == 0 && lane == 0;
+        const uint64_t mma_a = tc5_smem_desc(a_tile), mma_b = tc5_smem_desc(base + G5_OFF_BHH + t * G5_BHH_BYTES);
+        const uint32_t mma_d = tmem_base + (t ? 128u : 0u);
+        auto issue = [&]() {
+            tc5_fence_after();
+            tc5_mma(mma_d, mma_a + 0, mma_b + 0, IDESC_HH, 0);      // hi * hi
+            tc5_mma(mma_d, mma_a + 2, mma_b + 2, IDESC_HH, 1);
+            tc5_mma(mma_d, mma_a + 4, mma_b + 0, IDESC_HH, 1);      // lo * hi
+            tc5_mma(mma_d, mma_a + 6, mma_b + 2, IDESC_HH, 1);
+            tc5_mma(mma_d, mma_a + 0, mma_b + 4, IDESC_HH, 1);      // hi * lo
+            tc5_mma(mma_d, mma_a + 2, mma_b + 6, IDESC_HH, 1);
+            tc5_commit(d_full(t));
+        };
+        if (issuer) issue();                                    // step 0 (h = 0)
 
         f32x2 h2[H / 2];
 #pragma unroll
@@ -314,38 +329,16 @@ __global__ void __maxnreg__(200) gat_recur_tc5_kernel(GatArgs a) {
             }
             fence_proxy_async();                                        // this thread's h stores -> async proxy
             tc5_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_ready(t));
+            asm volatile("barrier.sync %0, 128;" ::"r"(1 + t) : "memory");   // the tile's 4 warps: h tile complete, D consumed
+            if (issuer && step + 1 < NM1) issue();
             float pa, pb;
             upk2(pl, pa, pb);
             if (ok) dlp[(int64_t)s * DLP] = pa + pb;                    // lanes = consecutive egos: coalesced
         }
-    } else {
-        // ================= MMA issuers: warp 8 -> tile 0 (fwd), warp 9 -> tile 1 (rev) =================
-        __syncthreads();                                                // pairs with the gate warps' barrier above
-        tc5_fence_after();
-        if (lane == 0) {
-            const int t = warp - 8;
-            const uint64_t da = tc5_smem_desc(base + G5_OFF_A + t * G5_A_BYTES);
-            const uint64_t db = tc5_smem_desc(base + G5_OFF_BHH + t * G5_BHH_BYTES);
-            const uint32_t dst = tmem_base + (t ? 128u : 0u);
-            for (int step = 0; step < NM1; ++step) {
-                mbar_wait(a_ready(t), step & 1);
-                tc5_fence_after();
-                tc5_mma(dst, da + 0, db + 0, IDESC_HH, 0);              // hi * hi
-                tc5_mma(dst, da + 2, db + 2, IDESC_HH, 1);
-                tc5_mma(dst, da + 4, db + 0, IDESC_HH, 1);              // lo * hi
-                tc5_mma(dst, da + 6, db + 2, IDESC_HH, 1);
-                tc5_mma(dst, da + 0, db + 4, IDESC_HH, 1);              // hi * lo
-                tc5_mma(dst, da + 2, db + 6, IDESC_HH, 1);
-                tc5_commit(d_full(t));
-            }
-        }
-        __syncwarp();
     }
     tc5_fence_before();
     __syncthreads();
-    if (warp == 8) {
+    if (warp == 0) {
         tc5_fence_after();
         tc5_dealloc<G5_TMEM_COLS>(tmem_base);
     }

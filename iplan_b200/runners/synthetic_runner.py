@@ -177,6 +177,7 @@ class ParallelRunner:
         step_stride = packed.stride(2)
 
         events = getattr(self, "gat_events", None)
+        noise = getattr(self, "noise_hook", None)      # parity tests: noise(kind, index) -> explicit noise tensor or None
 
         def timed(tag, fn, *a, **k):
             """Kernel launch, optionally bracketed by CUDA events on the launching stream (bench.py)."""
@@ -189,13 +190,17 @@ class ParallelRunner:
             events.append((tag, e0, e1))
             return out
 
+        gat_calls = [0]
+
         def gat(*a):
+            gum = noise("gumbel", gat_calls[0]) if noise is not None else None      # [A,B,N,N-1,2] or None (Philox)
+            gat_calls[0] += 1
             if events is None:
-                return self.prediction_learner.gat_step(*a)
+                return self.prediction_learner.gat_step(*a, gumbel=gum)
             ev = [th.cuda.Event(enable_timing=True) for _ in range(3)]
             for e in ev:
                 e.record()                   # creates the handles; the library re-records them around its two kernels
-            out = self.prediction_learner.gat_step(*a, events=ev)
+            out = self.prediction_learner.gat_step(*a, gumbel=gum, events=ev)
             events.append(("gat_recur", ev[0], ev[1]))
             events.append(("gat_attend", ev[1], ev[2]))
             events.append(("gat", ev[0], ev[2]))
@@ -205,14 +210,15 @@ class ParallelRunner:
         for t in range(T):
             timed("ctrl", self.mac.controller_step,
                   packed[:, :, t], rnn_a[:, :, t], rnn_c[:, :, t], rnn_a[:, :, t + 1], rnn_c[:, :, t + 1],
-                  None, test_mode=test_mode, next_onehot=onehot_cols[:, :, t + 1],
-                  this_onehot=onehot_cols[:, :, 0] if t == 0 else None,
+                  None, test_mode=test_mode, uniforms=noise("uniforms", t) if noise is not None else None,
+                  next_onehot=onehot_cols[:, :, t + 1], this_onehot=onehot_cols[:, :, 0] if t == 0 else None,
                   out=(actions_steps[t], logp_steps[t], value_steps[t]))
             gat(hist_v[:, :, t + 1], beh_v[:, :, t], att_v[:, :, t], att_v[:, :, t + 1])
             first = max(0, t + 2 - W)                                   # oldest time inside the window of time t+1
             timed("beh", self.behavior_learner.behavior_step, hist_v[:, :, first], enc_hid, beh_v[:, :, t], beh_v[:, :, t + 1],
                   win_stride_step=step_stride, win_pad=max(0, W - (t + 2)))
         actions_all = actions_steps.permute(1, 2, 0)                    # [A,B,T+1]
+        self.last_logp, self.last_values = logp_steps, value_steps      # [T,A,B] of the episode just run (parity tests)
         # episode-level stores in the reference's layout [B,T+1,A,*]
         batch["actions"][..., 0] = actions_all.permute(1, 2, 0).long()
         batch["actions_onehot"].zero_().scatter_(-1, batch["actions"], 1.0)
