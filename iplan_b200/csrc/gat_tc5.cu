@@ -9,15 +9,18 @@
 //
 // with h kept in shared memory as a K-major SWIZZLE_128B operand tile [128 rows][hi(32) | lo(32)] f16 that the gate
 // warps rewrite every step (generic-proxy stores + fence.proxy.async + mbarrier), and W_hh (gate-activation scale
-// folded in) as a [96 rows][hi | lo] tile written once.  Four gate warps per tile (warp = TMEM lane quarter, thread =
-// one chain, all 32 hidden units): tcgen05.ld the r|z|n pre-activations 8 hidden units at a time, add the ego part P
-// (registers) and the neighbour part Q (shared memory, broadcast: a step touches two Q rows), sigmoid / tanh through
-// ex2 + a shared rcp, new h -> f16 hi/lo -> the operand tile, the per-step hard-attention logit difference -> dl.
+// folded in) as a [96 rows][hi | lo] tile written once.  Eight gate warps per tile (warp -> TMEM lane quarter and one
+// half of the hidden units; thread = one chain x 16 units): tcgen05.ld the r|z|n pre-activations AND the chain's ego
+// part P (which the prologue's product left in TMEM) 8 hidden units at a time, add the neighbour part Q (shared memory,
+// broadcast: a step touches two Q rows; the biases are folded into the Q table), sigmoid / tanh through ex2 + a shared
+// rcp, new h -> f16 hi/lo -> the operand tile, the per-step hard-attention logit difference -> dl.
 // The two tiles (directions) interleave on the SM: while one tile's gates run on the MUFU / FMA pipes the other
-// tile's product runs on the tensor core.  8 warps = 2 per scheduler, so a thread may use up to 255 registers (a
-// scheduler's register file holds 16 K: a third warp would cap the kernel at 168).  No separate issuer warps: once the
-// four warps of a tile have passed their named barrier (h tile written), lane 0 of the tile's first warp issues the
-// six MMAs and commits them to the tile's mbarrier, which all four warps then wait on.
+// tile's product runs on the tensor core.  16 warps = 4 per scheduler at <= 128 registers: the step of a warp is a long
+// dependent chain (tcgen05.ld -> ex2 -> rcp -> ...), and the MUFU pipe — the unit this loop is bound by — only stays
+// busy with several warps per scheduler in different phases (2 warps per scheduler measured 1.00 ms per launch at
+// B = 512, half the MUFU bound).  No separate issuer warps: once the eight warps of a tile have passed their named
+// barrier (h tile written), lane 0 of the tile's first warp issues the six MMAs and commits them to the tile's
+// mbarrier, which all eight warps then wait on.
 //
 // Prologue, also on the tensor core: enc = ReLU(W_e x + b) per row (thread = row, fp32 FMA, K <= 16), then
 // [P | Q] = enc . [W_ih[:, :H] | W_ih[:, H:]]^T as ONE M 128 x N 192 product per direction; P lands in the TMEM lane of
@@ -30,7 +33,7 @@
 
 namespace iplan {
 
-constexpr int G5_THREADS = 256;             // warps 0-3: tile 0 (forward direction) | warps 4-7: tile 1 (reverse)
+constexpr int G5_THREADS = 512;             // warp w: tile (direction) (w >> 2) & 1, unit half w >> 3, TMEM lane quarter w & 3
 constexpr int G5_TMEM_COLS = 512;
 constexpr int G5_A_BYTES = 128 * 128;       // h operand tile: 128 rows x (32 hi + 32 lo) f16
 constexpr int G5_BHH_BYTES = G3 * 128;      // W_hh operand tile: 96 rows
@@ -41,7 +44,7 @@ constexpr int G5_OFF_A = 0;
 constexpr int G5_OFF_BHH = G5_OFF_A + 2 * G5_A_BYTES;
 constexpr int G5_OFF_Q = G5_OFF_BHH + 2 * G5_BHH_BYTES;          // the W_ih tiles alias the Q tables (dead before Q is written)
 constexpr int G5_OFF_SMALL = G5_OFF_Q + 2 * G5_Q_BYTES;
-constexpr int G5_SMALL_FLOATS = H * IN_MAX + H + 2 * G3 + 2 * H + 2 * H;   // W_e | b_e | P bias | b_hn | logit weights
+constexpr int G5_SMALL_FLOATS = H * IN_MAX + H + 2 * G3 + 2 * H + 2 * H + 2 * 2 * 128;   // W_e | b_e | P bias | b_hn | logit weights | logit partials
 constexpr int G5_OFF_BAR = G5_OFF_SMALL + G5_SMALL_FLOATS * 4;
 constexpr size_t G5_SMEM = G5_OFF_BAR + 64 + 1024;
 static_assert(2 * G5_BIH_BYTES <= 2 * G5_Q_BYTES, "W_ih tiles must fit under the Q tables");
@@ -79,6 +82,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
     float* s_pb = s_be + H;                                         // [2][96] gate-scaled b_ih (+ b_hh for r|z)
     float* s_bn = s_pb + 2 * G3;                                    // [2][32] K_N b_hn
     float* s_lw = s_bn + 2 * H;                                     // [2][32] logit-difference weights
+    float* s_pl = s_lw + 2 * H;                                     // [2 tiles][2 step parities][128 rows] logit partial of unit half 1
     const uint32_t bars = base + G5_OFF_BAR;
     auto d_full = [&](int t) { return bars + 8u * (2 + t); };       // MMA issuer -> the tile's warps: accumulator complete
     const uint32_t pro_bar = bars + 32u, tmem_slot = bars + 40u;
@@ -206,52 +210,50 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
     }
 
     {
-        // ================= thread = chain `row` of tile (direction) t =================
-        const int t = warp >> 2, row = (warp & 3) * 32 + lane;
+        // ================= thread = chain `row` of tile (direction) t, hidden units 16 hh .. 16 hh + 15 =================
+        const int t = (warp >> 2) & 1, hh = warp >> 3, row = (warp & 3) * 32 + lane;
         const int e = row >> 6, i = row & 63, b = b0 + e;
         const bool ok = i < N && b < a.n_envs;
         const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const uint32_t a_tile = base + G5_OFF_A + t * G5_A_BYTES;
         float* q_tab = reinterpret_cast<float*>(gb + G5_OFF_Q + t * G5_Q_BYTES);
+        const uint32_t p_col = tlane + PQ_COL + t * 2 * G3;            // this chain's P: stays in TMEM for the whole recurrence
 
         mbar_wait(pro_bar, 0);
         tc5_fence_after();
-        f32x2 P2[3 * H / 2];                                    // ego part of the input projection + biases, gate-scaled
+        // neighbour part: this row's Q (+ the gate biases: every step adds exactly one Q row) -> the table (W_ih tiles are dead)
 #pragma unroll
-        for (int c8 = 0; c8 < G3 / 8; ++c8) {
-            float v[8];
-            tc5_ld8_nowait(tlane + PQ_COL + t * 2 * G3 + 8 * c8, v);
-            tc5_wait_ld8(v);
-            const float4 pb0 = *reinterpret_cast<const float4*>(s_pb + t * G3 + 8 * c8);
-            const float4 pb1 = *reinterpret_cast<const float4*>(s_pb + t * G3 + 8 * c8 + 4);
-            P2[4 * c8 + 0] = pk2(v[0] + pb0.x, v[1] + pb0.y);
-            P2[4 * c8 + 1] = pk2(v[2] + pb0.z, v[3] + pb0.w);
-            P2[4 * c8 + 2] = pk2(v[4] + pb1.x, v[5] + pb1.y);
-            P2[4 * c8 + 3] = pk2(v[6] + pb1.z, v[7] + pb1.w);
-        }
+        for (int g = 0; g < 3; ++g)
 #pragma unroll
-        for (int c8 = 0; c8 < G3 / 8; ++c8) {                  // neighbour part: this row's Q -> the table (W_ih tiles are dead)
-            float v[8];
-            tc5_ld8_nowait(tlane + PQ_COL + t * 2 * G3 + G3 + 8 * c8, v);
-            tc5_wait_ld8(v);
-            float4* dst = reinterpret_cast<float4*>(q_tab + row * G5_QP + 8 * c8);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        // h0 = 0: zero this row of the operand tile (tile 0 held enc; its products are complete)
-        {
-            const uint32_t rb = a_tile + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+            for (int k = 0; k < 2; ++k) {
+                const int col = g * H + 16 * hh + 8 * k;
+                float v[8];
+                tc5_ld8_nowait(p_col + G3 + col, v);
+                tc5_wait_ld8(v);
+                const float4 pb0 = *reinterpret_cast<const float4*>(s_pb + t * G3 + col);
+                const float4 pb1 = *reinterpret_cast<const float4*>(s_pb + t * G3 + col + 4);
+                float4* dst = reinterpret_cast<float4*>(q_tab + row * G5_QP + col);
+                dst[0] = make_float4(v[0] + pb0.x, v[1] + pb0.y, v[2] + pb0.z, v[3] + pb0.w);
+                dst[1] = make_float4(v[4] + pb1.x, v[5] + pb1.y, v[6] + pb1.z, v[7] + pb1.w);
+            }
+        const uint32_t row_base = a_tile + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
+        const uint32_t rx = (uint32_t)(row & 7);
+        // h0 = 0: zero this thread's part of the row (tile 0 held enc; its products are complete)
 #pragma unroll
-            for (int ch = 0; ch < 8; ++ch) sts128(rb + 16 * ch, 0u, 0u, 0u, 0u);
+        for (int k = 0; k < 2; ++k) {
+            sts128(row_base + (((uint32_t)(2 * hh + k) ^ rx) << 4), 0u, 0u, 0u, 0u);
+            sts128(row_base + (((uint32_t)(4 + 2 * hh + k) ^ rx) << 4), 0u, 0u, 0u, 0u);
         }
         fence_proxy_async();
         tc5_fence_before();
-        __syncthreads();                                        // Q tables complete, TMEM [P | Q] columns free
+        __syncthreads();                                        // Q tables complete, TMEM Q columns free
         tc5_fence_after();
-        // the tile's product h . W_hh^T: issued by one lane once the tile's four warps have written h (named barrier)
-        const bool issuer = (warp & 3) == 0 && lane == 0;
+        // the tile's product h . W_hh^T: issued by one lane once the tile's eight warps have written h (named barrier)
+        const bool issuer = (warp & 3) == 0 && hh == 0 && lane == 0;
         const uint64_t mma_a = tc5_smem_desc(a_tile), mma_b = tc5_smem_desc(base + G5_OFF_BHH + t * G5_BHH_BYTES);
-        const uint32_t mma_d = tmem_base + (t ? 128u : 0u);
+        // accumulators: tile 0 at columns 0..95; tile 1 takes over the forward Q columns (224..319), free by now
+        const uint32_t d_off = t ? (uint32_t)(PQ_COL + G3) : 0u;
+        const uint32_t mma_d = tmem_base + d_off;
         auto issue = [&]() {
             tc5_fence_after();
             tc5_mma(mma_d, mma_a + 0, mma_b + 0, IDESC_HH, 0);      // hi * hi
@@ -264,17 +266,16 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
         };
         if (issuer) issue();                                    // step 0 (h = 0)
 
-        f32x2 h2[H / 2];
+        f32x2 h2[8];                                            // this thread's 16 hidden units, fp32
 #pragma unroll
-        for (int p = 0; p < H / 2; ++p) h2[p] = pk2(0.0f, 0.0f);
+        for (int p = 0; p < 8; ++p) h2[p] = pk2(0.0f, 0.0f);
         const f32x2 one2 = pk2(1.0f, 1.0f), mtwo2 = pk2(-2.0f, -2.0f);
-        const uint32_t d_col = tlane + (t ? 128u : 0u);
+        const uint32_t d_col = tlane + d_off;
         const float* q_env = q_tab + (e * 64) * G5_QP;
         const float* bn = s_bn + t * H;
         const float* lw = s_lw + t * H;
         float* dlp = a.dl + ((((int64_t)ag * a.n_envs + (ok ? b : 0)) * 2 + t) * NM1) * DLP + i;
-        const uint32_t row_base = a_tile + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
-        const uint32_t rx = (uint32_t)(row & 7);
+        float* plb = s_pl + t * 256 + row;
 
         for (int step = 0; step < NM1; ++step) {
             const int s = t ? NM1 - 1 - step : step;
@@ -283,34 +284,39 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
             tc5_fence_after();
             f32x2 pl = pk2(0.0f, 0.0f);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {                               // hidden units 8c .. 8c+7
-                float vr[8], vz[8], vn[8];
+            for (int k = 0; k < 2; ++k) {                               // hidden units 8c .. 8c+7
+                const int c = 2 * hh + k;
+                float vr[8], vz[8], vn[8], pr[8], pz[8], pn[8];
                 tc5_ld8_nowait(d_col + 8 * c, vr);
                 tc5_ld8_nowait(d_col + H + 8 * c, vz);
                 tc5_ld8_nowait(d_col + 2 * H + 8 * c, vn);
+                tc5_ld8_nowait(p_col + 8 * c, pr);
+                tc5_ld8_nowait(p_col + H + 8 * c, pz);
+                tc5_ld8_nowait(p_col + 2 * H + 8 * c, pn);
                 const float4 qr0 = *reinterpret_cast<const float4*>(q + 8 * c), qr1 = *reinterpret_cast<const float4*>(q + 8 * c + 4);
                 const float4 qz0 = *reinterpret_cast<const float4*>(q + H + 8 * c), qz1 = *reinterpret_cast<const float4*>(q + H + 8 * c + 4);
                 tc5_wait_ld24(vr, vz, vn);
+                tc5_wait_ld24(pr, pz, pn);
                 f32x2 r[4], z[4], xx[4];
-                xx[0] = add2(add2(pk2(vr[0], vr[1]), P2[4 * c + 0]), pk2(qr0.x, qr0.y));
-                xx[1] = add2(add2(pk2(vr[2], vr[3]), P2[4 * c + 1]), pk2(qr0.z, qr0.w));
-                xx[2] = add2(add2(pk2(vr[4], vr[5]), P2[4 * c + 2]), pk2(qr1.x, qr1.y));
-                xx[3] = add2(add2(pk2(vr[6], vr[7]), P2[4 * c + 3]), pk2(qr1.z, qr1.w));
+                xx[0] = add2(add2(pk2(vr[0], vr[1]), pk2(pr[0], pr[1])), pk2(qr0.x, qr0.y));
+                xx[1] = add2(add2(pk2(vr[2], vr[3]), pk2(pr[2], pr[3])), pk2(qr0.z, qr0.w));
+                xx[2] = add2(add2(pk2(vr[4], vr[5]), pk2(pr[4], pr[5])), pk2(qr1.x, qr1.y));
+                xx[3] = add2(add2(pk2(vr[6], vr[7]), pk2(pr[6], pr[7])), pk2(qr1.z, qr1.w));
                 sigmoid4_den(xx[0], xx[1], r[0], r[1]);                 // r = 1 / (1 + 2^x')
                 sigmoid4_den(xx[2], xx[3], r[2], r[3]);
-                xx[0] = add2(add2(pk2(vz[0], vz[1]), P2[16 + 4 * c + 0]), pk2(qz0.x, qz0.y));
-                xx[1] = add2(add2(pk2(vz[2], vz[3]), P2[16 + 4 * c + 1]), pk2(qz0.z, qz0.w));
-                xx[2] = add2(add2(pk2(vz[4], vz[5]), P2[16 + 4 * c + 2]), pk2(qz1.x, qz1.y));
-                xx[3] = add2(add2(pk2(vz[6], vz[7]), P2[16 + 4 * c + 3]), pk2(qz1.z, qz1.w));
+                xx[0] = add2(add2(pk2(vz[0], vz[1]), pk2(pz[0], pz[1])), pk2(qz0.x, qz0.y));
+                xx[1] = add2(add2(pk2(vz[2], vz[3]), pk2(pz[2], pz[3])), pk2(qz0.z, qz0.w));
+                xx[2] = add2(add2(pk2(vz[4], vz[5]), pk2(pz[4], pz[5])), pk2(qz1.x, qz1.y));
+                xx[3] = add2(add2(pk2(vz[6], vz[7]), pk2(pz[6], pz[7])), pk2(qz1.z, qz1.w));
                 sigmoid4_den(xx[0], xx[1], z[0], z[1]);
                 sigmoid4_den(xx[2], xx[3], z[2], z[3]);
                 const float4 qn0 = *reinterpret_cast<const float4*>(q + 2 * H + 8 * c), qn1 = *reinterpret_cast<const float4*>(q + 2 * H + 8 * c + 4);
                 const float4 bn0 = *reinterpret_cast<const float4*>(bn + 8 * c), bn1 = *reinterpret_cast<const float4*>(bn + 8 * c + 4);
-                // n pre-activation: (W_in x + b_in) + r (W_hn h + b_hn)   (:GRU gate order r, z, n)
-                xx[0] = fma2(r[0], add2(pk2(vn[0], vn[1]), pk2(bn0.x, bn0.y)), add2(P2[32 + 4 * c + 0], pk2(qn0.x, qn0.y)));
-                xx[1] = fma2(r[1], add2(pk2(vn[2], vn[3]), pk2(bn0.z, bn0.w)), add2(P2[32 + 4 * c + 1], pk2(qn0.z, qn0.w)));
-                xx[2] = fma2(r[2], add2(pk2(vn[4], vn[5]), pk2(bn1.x, bn1.y)), add2(P2[32 + 4 * c + 2], pk2(qn1.x, qn1.y)));
-                xx[3] = fma2(r[3], add2(pk2(vn[6], vn[7]), pk2(bn1.z, bn1.w)), add2(P2[32 + 4 * c + 3], pk2(qn1.z, qn1.w)));
+                // n pre-activation: (W_in x + b_in) + r (W_hn h + b_hn)   (GRU gate order r, z, n)
+                xx[0] = fma2(r[0], add2(pk2(vn[0], vn[1]), pk2(bn0.x, bn0.y)), add2(pk2(pn[0], pn[1]), pk2(qn0.x, qn0.y)));
+                xx[1] = fma2(r[1], add2(pk2(vn[2], vn[3]), pk2(bn0.z, bn0.w)), add2(pk2(pn[2], pn[3]), pk2(qn0.z, qn0.w)));
+                xx[2] = fma2(r[2], add2(pk2(vn[4], vn[5]), pk2(bn1.x, bn1.y)), add2(pk2(pn[4], pn[5]), pk2(qn1.x, qn1.y)));
+                xx[3] = fma2(r[3], add2(pk2(vn[6], vn[7]), pk2(bn1.z, bn1.w)), add2(pk2(pn[6], pn[7]), pk2(qn1.z, qn1.w)));
                 f32x2 in[4];
                 sigmoid4_den(xx[0], xx[1], in[0], in[1]);
                 sigmoid4_den(xx[2], xx[3], in[2], in[3]);
@@ -320,20 +326,21 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     const f32x2 nn = fma2(mtwo2, in[p], one2);                      // tanh = 1 - 2 / (1 + 2^x')
-                    h2[4 * c + p] = fma2(z[p], sub2(h2[4 * c + p], nn), nn);        // (1 - z) n + z h
-                    pl = fma2(lwp[p], h2[4 * c + p], pl);
-                    split_f16p(h2[4 * c + p], hi[p], lo[p]);
+                    h2[4 * k + p] = fma2(z[p], sub2(h2[4 * k + p], nn), nn);        // (1 - z) n + z h
+                    pl = fma2(lwp[p], h2[4 * k + p], pl);
+                    split_f16p(h2[4 * k + p], hi[p], lo[p]);
                 }
                 sts128(row_base + (((uint32_t)c ^ rx) << 4), hi[0], hi[1], hi[2], hi[3]);
                 sts128(row_base + (((uint32_t)(4 + c) ^ rx) << 4), lo[0], lo[1], lo[2], lo[3]);
             }
-            fence_proxy_async();                                        // this thread's h stores -> async proxy
-            tc5_fence_before();
-            asm volatile("barrier.sync %0, 128;" ::"r"(1 + t) : "memory");   // the tile's 4 warps: h tile complete, D consumed
-            if (issuer && step + 1 < NM1) issue();
             float pa, pb;
             upk2(pl, pa, pb);
-            if (ok) dlp[(int64_t)s * DLP] = pa + pb;                    // lanes = consecutive egos: coalesced
+            if (hh) plb[(step & 1) * 128] = pa + pb;                    // the other half's thread adds it after the barrier
+            fence_proxy_async();                                        // this thread's h stores -> async proxy
+            tc5_fence_before();
+            asm volatile("barrier.sync %0, 256;" ::"r"(1 + t) : "memory");   // the tile's 8 warps: h tile complete, D consumed
+            if (issuer && step + 1 < NM1) issue();
+            if (!hh && ok) dlp[(int64_t)s * DLP] = (pa + pb) + plb[(step & 1) * 128];   // lanes = consecutive egos: coalesced
         }
     }
     tc5_fence_before();

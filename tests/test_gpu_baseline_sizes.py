@@ -119,7 +119,11 @@ def test_learner_vs_oracle_baseline_shape():
     returns / advantages / values / old log-probs, first-epoch gradients and the post-update weights."""
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
-    from test_gpu_learner import build
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("test_gpu_learner", os.path.join(ROOT, "tests", "test_gpu_learner.py"))
+    tgl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tgl)
+    build = tgl.build
     from iplan_b200.config import make_args
     from iplan_b200.modules.flat import ParamStack
     from oracle import iplan_oracle as O
