@@ -96,7 +96,8 @@ __device__ __forceinline__ void split_f16(float x, float y, uint32_t& hi, uint32
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-// tcgen05 recurrence (gat_tc5.cu): same inputs, same dl scratch layout as gat_recur_kernel
-int launch_gat_recur_tc5(const GatArgs& a, int n_agents, cudaStream_t st);
+// tcgen05 kernel (gat_tc5.cu): fused = the whole step in one launch; else the recurrence only (same dl scratch layout as
+// gat_recur_kernel, consumed by gat_attend_kernel)
+int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, cudaStream_t st);
 
 }  // namespace iplan

@@ -459,19 +459,20 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
 }  // namespace iplan
 
 namespace iplan {
-// 0 = tcgen05 recurrence (gat_tc5.cu, default), 1 = mma.sync recurrence (gat_recur_kernel: kept as the cross-check)
+// 0 = ONE fused tcgen05 kernel (gat_tc5.cu, default), 1 = mma.sync recurrence + attention kernel (the cross-check),
+// 2 = tcgen05 recurrence + attention kernel
 static int g_gat_impl = -1;
 static int gat_impl() {
     if (g_gat_impl < 0) {
         const char* e = getenv("IPLAN_GAT_IMPL");
-        g_gat_impl = (e && (e[0] == '1' || e[0] == 'm')) ? 1 : 0;
+        g_gat_impl = (e && (e[0] == '1' || e[0] == 'm')) ? 1 : ((e && e[0] == '2') ? 2 : 0);
     }
     return g_gat_impl;
 }
 }  // namespace iplan
 
 extern "C" int iplan_gat_set_impl(int impl) {
-    IPLAN_REQUIRE(impl == 0 || impl == 1, "gat_set_impl: %d not in {0 (tcgen05), 1 (mma.sync)}", impl);
+    IPLAN_REQUIRE(impl >= 0 && impl <= 2, "gat_set_impl: %d not in {0 (fused tcgen05), 1 (mma.sync + attention), 2 (tcgen05 recurrence + attention)}", impl);
     iplan::g_gat_impl = impl;
     return 0;
 }
@@ -516,8 +517,9 @@ extern "C" int iplan_gat_step_ex(const float* gat_params, int64_t param_stride,
     }
     if (ev_begin) cudaEventRecord((cudaEvent_t)ev_begin, (cudaStream_t)stream);
     int rc;
-    if (gat_impl() == 0) {
-        rc = launch_gat_recur_tc5(a, n_agents, (cudaStream_t)stream);
+    bool fused = false;
+    if (gat_impl() != 1) {
+        rc = launch_gat_tc5(a, n_agents, gat_impl() == 0, &fused, (cudaStream_t)stream);
     } else {
         gat_recur_kernel<<<dim3(n_envs, n_agents, 2), REC_THREADS, smem_r, (cudaStream_t)stream>>>(a);
         count_launch();
@@ -525,9 +527,11 @@ extern "C" int iplan_gat_step_ex(const float* gat_params, int64_t param_stride,
     }
     if (rc) return rc;
     if (ev_mid) cudaEventRecord((cudaEvent_t)ev_mid, (cudaStream_t)stream);
-    gat_attend_kernel<<<dim3(n_envs, n_agents), GAT_THREADS, smem_a, (cudaStream_t)stream>>>(a);
-    count_launch();
-    rc = check_launch("gat_step(attend)");
+    if (!fused) {
+        gat_attend_kernel<<<dim3(n_envs, n_agents), GAT_THREADS, smem_a, (cudaStream_t)stream>>>(a);
+        count_launch();
+        rc = check_launch("gat_step(attend)");
+    }
     if (ev_end) cudaEventRecord((cudaEvent_t)ev_end, (cudaStream_t)stream);
     return rc;
 }

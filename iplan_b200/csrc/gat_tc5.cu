@@ -31,6 +31,8 @@
 #include "gat_common.cuh"
 #include "tc5.cuh"
 
+#include <stdlib.h>
+
 namespace iplan {
 
 constexpr int G5_THREADS = 512;             // warp w: tile (direction) (w >> 2) & 1, unit half w >> 3, TMEM lane quarter w & 3
@@ -39,16 +41,32 @@ constexpr int G5_A_BYTES = 128 * 128;       // h operand tile: 128 rows x (32 hi
 constexpr int G5_BHH_BYTES = G3 * 128;      // W_hh operand tile: 96 rows
 constexpr int G5_BIH_BYTES = 2 * G3 * 128;  // [W_ih ego | W_ih neighbour]: 192 rows (prologue only)
 constexpr int G5_QP = 100;                  // Q table row pitch in floats: lanes 16 B apart mod 128 B -> conflict-free row writes
-constexpr int G5_Q_BYTES = 128 * G5_QP * 4;
-constexpr int G5_OFF_A = 0;
-constexpr int G5_OFF_BHH = G5_OFF_A + 2 * G5_A_BYTES;
-constexpr int G5_OFF_Q = G5_OFF_BHH + 2 * G5_BHH_BYTES;          // the W_ih tiles alias the Q tables (dead before Q is written)
-constexpr int G5_OFF_SMALL = G5_OFF_Q + 2 * G5_Q_BYTES;
-constexpr int G5_SMALL_FLOATS = H * IN_MAX + H + 2 * G3 + 2 * H + 2 * H + 2 * 2 * 128;   // W_e | b_e | P bias | b_hn | logit weights | logit partials
-constexpr int G5_OFF_BAR = G5_OFF_SMALL + G5_SMALL_FLOATS * 4;
-constexpr size_t G5_SMEM = G5_OFF_BAR + 64 + 1024;
-static_assert(2 * G5_BIH_BYTES <= 2 * G5_Q_BYTES, "W_ih tiles must fit under the Q tables");
-static_assert(G5_OFF_BHH % 1024 == 0 && G5_OFF_Q % 1024 == 0 && G5_BIH_BYTES % 1024 == 0 && G5_BHH_BYTES % 1024 == 0, "swizzle atoms are 1024-byte aligned");
+constexpr int G5_KP = 36;                   // k / v table row pitch (attention phase)
+// small constants: W_e | b_e | P bias | b_hn | logit weights | logit partials | (fused) v bias | GRUCell biases | soft-max exchange
+constexpr int G5_SMALL_FLOATS = H * IN_MAX + H + 2 * G3 + 2 * H + 2 * H + 2 * 2 * 128 + H + 2 * G3 + 2 * 4 * 128;
+constexpr int G5_ATT_BYTES = 2 * 128 * G5_KP * 4 + 3 * H * 128 * 4;     // k | v tables + three partial aggregates [3][32][128]
+
+// Shared-memory map (byte offsets from the 1024-aligned base).  FUSED adds a copy of the enc operand tile (the h tile
+// overwrites the first one) and the per-edge logit tables dl[dir][s][row]; after the recurrence the attention phase
+// reuses the Q tables (k, v, partial aggregates), the W_hh tiles (W_q|k|v, GRUCell W_hh) and the h tiles (h_prev / x, GRUCell W_ih).
+struct G5Layout { uint32_t a, enc, bhh, q, q_dir, dl, small, bar, total; };
+__host__ __device__ inline G5Layout g5_layout(int N, bool fused) {
+    G5Layout l;
+    l.a = 0;
+    l.enc = l.a + 2 * G5_A_BYTES;
+    l.bhh = l.enc + (fused ? G5_A_BYTES : 0);
+    l.q = l.bhh + 2 * G5_BHH_BYTES;                                  // the W_ih tiles alias the Q tables (dead before Q is written)
+    uint32_t qd = (uint32_t)(2 * N * G5_QP * 4);
+    if (qd < (uint32_t)G5_BIH_BYTES) qd = G5_BIH_BYTES;
+    if (fused && 2 * qd < (uint32_t)G5_ATT_BYTES) qd = (G5_ATT_BYTES + 1) / 2;
+    l.q_dir = (qd + 1023u) & ~1023u;
+    l.dl = l.q + 2 * l.q_dir;
+    l.small = l.dl + (fused ? (uint32_t)(2 * (N - 1) * 128 * 4) : 0u);
+    l.bar = l.small + G5_SMALL_FLOATS * 4;
+    l.total = l.bar + 64 + 1024;
+    return l;
+}
+constexpr size_t G5_SMEM_MAX = 227 * 1024;
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
@@ -66,7 +84,10 @@ __device__ __forceinline__ void tc5_wait_ld8(float (&a)[8]) {
                  : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]) :: "memory");
 }
 
-__global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a) {
+// DBG (timing experiments only, results are garbage): bit 0 = tile 1 (reverse direction) does nothing; bit 1 = the MUFU
+// instructions of the gates are replaced by FMA-pipe stand-ins
+template <int DBG, bool FUSED>
+__global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
     extern __shared__ unsigned char g5_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ag = blockIdx.y, b0 = blockIdx.x * 2;
@@ -77,19 +98,26 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
     const uint32_t raw_u = smem_u32(g5_raw);
     const uint32_t base = (raw_u + 1023u) & ~1023u;                 // swizzle atoms are 1024-byte aligned
     unsigned char* gb = g5_raw + (base - raw_u);
-    float* s_we = reinterpret_cast<float*>(gb + G5_OFF_SMALL);      // [H][IN_MAX] zero padded
+    const G5Layout Y = g5_layout(N, FUSED);
+    float* s_we = reinterpret_cast<float*>(gb + Y.small);           // [H][IN_MAX] zero padded
     float* s_be = s_we + H * IN_MAX;                                // [H]
     float* s_pb = s_be + H;                                         // [2][96] gate-scaled b_ih (+ b_hh for r|z)
     float* s_bn = s_pb + 2 * G3;                                    // [2][32] K_N b_hn
     float* s_lw = s_bn + 2 * H;                                     // [2][32] logit-difference weights
     float* s_pl = s_lw + 2 * H;                                     // [2 tiles][2 step parities][128 rows] logit partial of unit half 1
-    const uint32_t bars = base + G5_OFF_BAR;
+    float* s_vb = s_pl + 2 * 2 * 128;                               // (fused) [32] v bias | [96] GRUCell b_ih | [96] b_hh | [4][128] max | [4][128] sum
+    float* s_cb = s_vb + H;
+    float* s_pm = s_cb + 2 * G3;
+    float* s_ps = s_pm + 4 * 128;
+    float* s_dl = reinterpret_cast<float*>(gb + Y.dl);              // (fused) [2 dirs][N-1][128 rows]
+    const uint32_t bars = base + Y.bar;
     auto d_full = [&](int t) { return bars + 8u * (2 + t); };       // MMA issuer -> the tile's warps: accumulator complete
-    const uint32_t pro_bar = bars + 32u, tmem_slot = bars + 40u;
+    const uint32_t pro_bar = bars + 32u, tmem_slot = bars + 40u, att_bar = bars + 48u;
 
     if (tid == 0) {
         for (int t = 0; t < 2; ++t) mbar_init(d_full(t), 1);
         mbar_init(pro_bar, 1);
+        mbar_init(att_bar, 1);
         mbar_init_fence();
     }
     if (warp == 0) tc5_alloc<G5_TMEM_COLS>(tmem_slot);
@@ -139,14 +167,14 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
             const int d = task / (G3 * 4), rr = task - d * (G3 * 4);
             row = rr >> 2; ch = rr & 3; gate = row;
             src = W + (d ? L.whh_r : L.whh_f) + row * H + ch * 8;
-            tile = base + G5_OFF_BHH + d * G5_BHH_BYTES;
+            tile = base + Y.bhh + d * G5_BHH_BYTES;
         } else {
             const int tt = task - HH_TASKS, d = tt / (2 * G3 * 4), rr = tt - d * (2 * G3 * 4);
             row = rr >> 2; ch = rr & 3;
             const int part = row / G3;                      // 0: ego columns (-> P), 1: neighbour columns (-> Q)
             gate = row - part * G3;
             src = W + (d ? L.wih_r : L.wih_f) + gate * 2 * H + part * H + ch * 8;
-            tile = base + G5_OFF_Q + d * G5_BIH_BYTES;
+            tile = base + Y.q + d * G5_BIH_BYTES;
         }
         const float ks = gate < 2 * H ? K_RZ : K_N;
         const float4 w0 = *reinterpret_cast<const float4*>(src), w1 = *reinterpret_cast<const float4*>(src + 4);
@@ -166,7 +194,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
 
     // ---- enc = ReLU(W_e x + b_e) (:50) -> operand tile 0 (shared by both directions' [P | Q] products) ----
     if (tid < 128) {
-        const uint32_t tile = base + G5_OFF_A;
+        const uint32_t tile = base + Y.a;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
             uint32_t hi[4], lo[4];
@@ -185,6 +213,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
             }
             sts128(tile + swz128(tid, ch), hi[0], hi[1], hi[2], hi[3]);
             sts128(tile + swz128(tid, 4 + ch), lo[0], lo[1], lo[2], lo[3]);
+            if constexpr (FUSED) {                                // the attention phase needs enc again; the h tile overwrites this one
+                sts128(base + Y.enc + swz128(tid, ch), hi[0], hi[1], hi[2], hi[3]);
+                sts128(base + Y.enc + swz128(tid, 4 + ch), lo[0], lo[1], lo[2], lo[3]);
+            }
         }
     }
     fence_proxy_async();
@@ -194,10 +226,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
     constexpr int PQ_COL = 128;                               // [P | Q] fwd at TMEM columns 128..319, rev at 320..511
     if (tid == 0) {
         tc5_fence_after();
-        const uint64_t da = tc5_smem_desc(base + G5_OFF_A);
+        const uint64_t da = tc5_smem_desc(base + Y.a);
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
-            const uint64_t db = tc5_smem_desc(base + G5_OFF_Q + d * G5_BIH_BYTES);
+            const uint64_t db = tc5_smem_desc(base + Y.q + d * G5_BIH_BYTES);
             const uint32_t dst = tmem_base + PQ_COL + d * 2 * G3;
             tc5_mma(dst, da + 0, db + 0, IDESC_IH, 0);        // hi * hi
             tc5_mma(dst, da + 2, db + 2, IDESC_IH, 1);
@@ -215,8 +247,8 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
         const int e = row >> 6, i = row & 63, b = b0 + e;
         const bool ok = i < N && b < a.n_envs;
         const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t a_tile = base + G5_OFF_A + t * G5_A_BYTES;
-        float* q_tab = reinterpret_cast<float*>(gb + G5_OFF_Q + t * G5_Q_BYTES);
+        const uint32_t a_tile = base + Y.a + t * G5_A_BYTES;
+        float* q_tab = reinterpret_cast<float*>(gb + Y.q + t * Y.q_dir);     // [2 envs x N slots][G5_QP]
         const uint32_t p_col = tlane + PQ_COL + t * 2 * G3;            // this chain's P: stays in TMEM for the whole recurrence
 
         mbar_wait(pro_bar, 0);
@@ -232,9 +264,11 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
                 tc5_wait_ld8(v);
                 const float4 pb0 = *reinterpret_cast<const float4*>(s_pb + t * G3 + col);
                 const float4 pb1 = *reinterpret_cast<const float4*>(s_pb + t * G3 + col + 4);
-                float4* dst = reinterpret_cast<float4*>(q_tab + row * G5_QP + col);
-                dst[0] = make_float4(v[0] + pb0.x, v[1] + pb0.y, v[2] + pb0.z, v[3] + pb0.w);
-                dst[1] = make_float4(v[4] + pb1.x, v[5] + pb1.y, v[6] + pb1.z, v[7] + pb1.w);
+                float4* dst = reinterpret_cast<float4*>(q_tab + (e * N + (i < N ? i : 0)) * G5_QP + col);
+                if (i < N) {                                   // rows of padding slots have no table entry
+                    dst[0] = make_float4(v[0] + pb0.x, v[1] + pb0.y, v[2] + pb0.z, v[3] + pb0.w);
+                    dst[1] = make_float4(v[4] + pb1.x, v[5] + pb1.y, v[6] + pb1.z, v[7] + pb1.w);
+                }
             }
         const uint32_t row_base = a_tile + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
         const uint32_t rx = (uint32_t)(row & 7);
@@ -250,7 +284,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
         tc5_fence_after();
         // the tile's product h . W_hh^T: issued by one lane once the tile's eight warps have written h (named barrier)
         const bool issuer = (warp & 3) == 0 && hh == 0 && lane == 0;
-        const uint64_t mma_a = tc5_smem_desc(a_tile), mma_b = tc5_smem_desc(base + G5_OFF_BHH + t * G5_BHH_BYTES);
+        const uint64_t mma_a = tc5_smem_desc(a_tile), mma_b = tc5_smem_desc(base + Y.bhh + t * G5_BHH_BYTES);
         // accumulators: tile 0 at columns 0..95; tile 1 takes over the forward Q columns (224..319), free by now
         const uint32_t d_off = t ? (uint32_t)(PQ_COL + G3) : 0u;
         const uint32_t mma_d = tmem_base + d_off;
@@ -271,13 +305,13 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
         for (int p = 0; p < 8; ++p) h2[p] = pk2(0.0f, 0.0f);
         const f32x2 one2 = pk2(1.0f, 1.0f), mtwo2 = pk2(-2.0f, -2.0f);
         const uint32_t d_col = tlane + d_off;
-        const float* q_env = q_tab + (e * 64) * G5_QP;
+        const float* q_env = q_tab + (e * N) * G5_QP;
         const float* bn = s_bn + t * H;
         const float* lw = s_lw + t * H;
         float* dlp = a.dl + ((((int64_t)ag * a.n_envs + (ok ? b : 0)) * 2 + t) * NM1) * DLP + i;
         float* plb = s_pl + t * 256 + row;
 
-        for (int step = 0; step < NM1; ++step) {
+        for (int step = 0; step < ((DBG & 1) && t ? 0 : NM1); ++step) {
             const int s = t ? NM1 - 1 - step : step;
             const float* q = q_env + (s < i ? s : s + 1) * G5_QP;       // neighbour of ego i at position s (:60-66)
             mbar_wait(d_full(t), step & 1);
@@ -302,14 +336,18 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
                 xx[1] = add2(add2(pk2(vr[2], vr[3]), pk2(pr[2], pr[3])), pk2(qr0.z, qr0.w));
                 xx[2] = add2(add2(pk2(vr[4], vr[5]), pk2(pr[4], pr[5])), pk2(qr1.x, qr1.y));
                 xx[3] = add2(add2(pk2(vr[6], vr[7]), pk2(pr[6], pr[7])), pk2(qr1.z, qr1.w));
-                sigmoid4_den(xx[0], xx[1], r[0], r[1]);                 // r = 1 / (1 + 2^x')
-                sigmoid4_den(xx[2], xx[3], r[2], r[3]);
+                auto sig4 = [&](f32x2 x01, f32x2 x23, f32x2& ia, f32x2& ib) {
+                    if constexpr (DBG & 2) { ia = fma2(x01, x23, one2); ib = fma2(x23, x01, mtwo2); }
+                    else sigmoid4_den(x01, x23, ia, ib);
+                };
+                sig4(xx[0], xx[1], r[0], r[1]);                         // r = 1 / (1 + 2^x')
+                sig4(xx[2], xx[3], r[2], r[3]);
                 xx[0] = add2(add2(pk2(vz[0], vz[1]), pk2(pz[0], pz[1])), pk2(qz0.x, qz0.y));
                 xx[1] = add2(add2(pk2(vz[2], vz[3]), pk2(pz[2], pz[3])), pk2(qz0.z, qz0.w));
                 xx[2] = add2(add2(pk2(vz[4], vz[5]), pk2(pz[4], pz[5])), pk2(qz1.x, qz1.y));
                 xx[3] = add2(add2(pk2(vz[6], vz[7]), pk2(pz[6], pz[7])), pk2(qz1.z, qz1.w));
-                sigmoid4_den(xx[0], xx[1], z[0], z[1]);
-                sigmoid4_den(xx[2], xx[3], z[2], z[3]);
+                sig4(xx[0], xx[1], z[0], z[1]);
+                sig4(xx[2], xx[3], z[2], z[3]);
                 const float4 qn0 = *reinterpret_cast<const float4*>(q + 2 * H + 8 * c), qn1 = *reinterpret_cast<const float4*>(q + 2 * H + 8 * c + 4);
                 const float4 bn0 = *reinterpret_cast<const float4*>(bn + 8 * c), bn1 = *reinterpret_cast<const float4*>(bn + 8 * c + 4);
                 // n pre-activation: (W_in x + b_in) + r (W_hn h + b_hn)   (GRU gate order r, z, n)
@@ -318,8 +356,8 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
                 xx[2] = fma2(r[2], add2(pk2(vn[4], vn[5]), pk2(bn1.x, bn1.y)), add2(pk2(pn[4], pn[5]), pk2(qn1.x, qn1.y)));
                 xx[3] = fma2(r[3], add2(pk2(vn[6], vn[7]), pk2(bn1.z, bn1.w)), add2(pk2(pn[6], pn[7]), pk2(qn1.z, qn1.w)));
                 f32x2 in[4];
-                sigmoid4_den(xx[0], xx[1], in[0], in[1]);
-                sigmoid4_den(xx[2], xx[3], in[2], in[3]);
+                sig4(xx[0], xx[1], in[0], in[1]);
+                sig4(xx[2], xx[3], in[2], in[3]);
                 const float4 lw0 = *reinterpret_cast<const float4*>(lw + 8 * c), lw1 = *reinterpret_cast<const float4*>(lw + 8 * c + 4);
                 const f32x2 lwp[4] = {pk2(lw0.x, lw0.y), pk2(lw0.z, lw0.w), pk2(lw1.x, lw1.y), pk2(lw1.z, lw1.w)};
                 uint32_t hi[4], lo[4];
@@ -340,7 +378,220 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
             tc5_fence_before();
             asm volatile("barrier.sync %0, 256;" ::"r"(1 + t) : "memory");   // the tile's 8 warps: h tile complete, D consumed
             if (issuer && step + 1 < NM1) issue();
-            if (!hh && ok) dlp[(int64_t)s * DLP] = (pa + pb) + plb[(step & 1) * 128];   // lanes = consecutive egos: coalesced
+            if (!hh) {
+                const float dlv = (pa + pb) + plb[(step & 1) * 128];
+                if constexpr (FUSED) s_dl[(t * NM1 + s) * 128 + row] = dlv;
+                else if (ok) dlp[(int64_t)s * DLP] = dlv;               // lanes = consecutive egos: coalesced
+            }
+        }
+    }
+    if constexpr (FUSED) {
+        // ================= attention + GRUCell (nova/GAT_Net.py:99-142), 4 threads per row =================
+        // thread = (row, part): part p owns the neighbours j = p, p + 4, ... and the hidden units 8p .. 8p + 7 of its row
+        const int part = warp >> 2, row = (warp & 3) * 32 + lane;
+        const int e = row >> 6, i = row & 63, b = b0 + e;
+        const bool ok = i < N && b < a.n_envs;
+        const uint32_t tlane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const float* hprev = a.hprev.ptr + ag * a.hprev.stride_agent + (ok ? b : 0) * a.hprev.stride_env + (ok ? i : 0) * a.hprev.stride_slot;
+        float* k_s = reinterpret_cast<float*>(gb + Y.q);                       // [128 rows][G5_KP]
+        float* v_s = k_s + 128 * G5_KP;
+        float* x_part = v_s + 128 * G5_KP;                                     // [3 parts][32 units][128 rows]
+        const uint32_t t_hx = base + Y.a, t_wih = base + Y.a + G5_A_BYTES;     // h_prev / x operand tile | GRUCell W_ih tile
+        const uint32_t t_qkv = base + Y.bhh, t_whh = base + Y.bhh + G5_BHH_BYTES;
+        const uint32_t row_base = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u, rx = (uint32_t)(row & 7);
+
+        tc5_fence_before();
+        __syncthreads();                       // both recurrences done: dl tables complete, operand tiles and TMEM columns free
+        tc5_fence_after();
+        // ---- stage W_q|k|v, GRUCell W_hh, GRUCell W_ih as operand tiles; h_prev as an operand tile; biases -----------
+        for (int task = tid; task < 3 * G3 * 4; task += G5_THREADS) {
+            const int sel = task / (G3 * 4), rr = task - sel * (G3 * 4), wr = rr >> 2, ch = rr & 3;
+            const float* src = W + (sel == 0 ? L.q_w : (sel == 1 ? L.c_whh : L.c_wih)) + wr * H + ch * 8;
+            const uint32_t tile = sel == 0 ? t_qkv : (sel == 1 ? t_whh : t_wih);
+            const float4 w0 = *reinterpret_cast<const float4*>(src), w1 = *reinterpret_cast<const float4*>(src + 4);
+            uint32_t hi[4], lo[4];
+            split_f16(w0.x, w0.y, hi[0], lo[0]);
+            split_f16(w0.z, w0.w, hi[1], lo[1]);
+            split_f16(w1.x, w1.y, hi[2], lo[2]);
+            split_f16(w1.z, w1.w, hi[3], lo[3]);
+            sts128(tile + swz128(wr, ch), hi[0], hi[1], hi[2], hi[3]);
+            sts128(tile + swz128(wr, 4 + ch), lo[0], lo[1], lo[2], lo[3]);
+        }
+        float hp[8];                           // h_prev of this thread's 8 units (fp32, kept for the GRUCell's last line)
+        {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) hp[q] = ok ? hprev[8 * part + q] : 0.0f;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_f16(hp[2 * q], hp[2 * q + 1], hi[q], lo[q]);
+            sts128(t_hx + row_base + (((uint32_t)part ^ rx) << 4), hi[0], hi[1], hi[2], hi[3]);
+            sts128(t_hx + row_base + (((uint32_t)(4 + part) ^ rx) << 4), lo[0], lo[1], lo[2], lo[3]);
+        }
+        if (tid < H) s_vb[tid] = W[L.v_b + tid];
+        if (tid < G3) { s_cb[tid] = W[L.c_bih + tid]; s_cb[G3 + tid] = W[L.c_bhh + tid]; }
+        fence_proxy_async();
+        tc5_fence_before();
+        __syncthreads();
+        tc5_fence_after();
+        constexpr int QKV_COL = 0, GH_COL = G3, GI_COL = 2 * G3;
+        auto product = [&](uint32_t col, uint32_t ta, uint32_t tb) {          // D[128 x 96] = A . B^T, fp32-class (3 passes)
+            const uint64_t da = tc5_smem_desc(ta), db = tc5_smem_desc(tb);
+            const uint32_t dst = tmem_base + col;
+            tc5_mma(dst, da + 0, db + 0, IDESC_HH, 0);
+            tc5_mma(dst, da + 2, db + 2, IDESC_HH, 1);
+            tc5_mma(dst, da + 4, db + 0, IDESC_HH, 1);
+            tc5_mma(dst, da + 6, db + 2, IDESC_HH, 1);
+            tc5_mma(dst, da + 0, db + 4, IDESC_HH, 1);
+            tc5_mma(dst, da + 2, db + 6, IDESC_HH, 1);
+        };
+        if (tid == 0) {
+            product(QKV_COL, base + Y.enc, t_qkv);                             // q | k | v = enc [W_q | W_k | W_v]^T      (:99-103)
+            product(GH_COL, t_hx, t_whh);                                      // GRUCell: h_prev W_hh^T                   (:140)
+            tc5_commit(att_bar);
+        }
+        mbar_wait(att_bar, 0);
+        tc5_fence_after();
+        float qv[H];
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {
+            float v[8];
+            tc5_ld8_nowait(tlane + QKV_COL + 8 * c8, v);
+            tc5_wait_ld8(v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) qv[8 * c8 + q] = v[q];
+        }
+        {
+            float kk[8], vv[8];
+            tc5_ld8_nowait(tlane + QKV_COL + H + 8 * part, kk);
+            tc5_ld8_nowait(tlane + QKV_COL + 2 * H + 8 * part, vv);
+            tc5_wait_ld8(kk);
+            tc5_wait_ld8(vv);
+            float4* kd = reinterpret_cast<float4*>(k_s + row * G5_KP + 8 * part);
+            float4* vd = reinterpret_cast<float4*>(v_s + row * G5_KP + 8 * part);
+            kd[0] = make_float4(kk[0], kk[1], kk[2], kk[3]);
+            kd[1] = make_float4(kk[4], kk[5], kk[6], kk[7]);
+            const float* vb = s_vb + 8 * part;                                 // v = ReLU(W_v enc + b_v)                  (:103)
+            vd[0] = make_float4(fmaxf(vv[0] + vb[0], 0.f), fmaxf(vv[1] + vb[1], 0.f), fmaxf(vv[2] + vb[2], 0.f), fmaxf(vv[3] + vb[3], 0.f));
+            vd[1] = make_float4(fmaxf(vv[4] + vb[4], 0.f), fmaxf(vv[5] + vb[5], 0.f), fmaxf(vv[6] + vb[6], 0.f), fmaxf(vv[7] + vb[7], 0.f));
+        }
+        __syncthreads();
+        // ---- scores, hard gate, soft-max over the neighbours (:107-129); this thread's neighbours j = part + 4 u --------
+        constexpr int JU = IPLAN_MAX_SLOTS / 4;
+        float sc[JU], hd[JU];
+        const float db = W[L.he_b + 1] - W[L.he_b + 0];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int u = 0; u < JU; ++u) {
+            const int j = part + 4 * u;
+            sc[u] = -INFINITY; hd[u] = 0.0f;
+            if (j < N && j != i && i < N) {
+                const float4* kr = reinterpret_cast<const float4*>(k_s + (e * 64 + j) * G5_KP);
+                float d = 0.0f;
+#pragma unroll
+                for (int c4 = 0; c4 < H / 4; ++c4) {
+                    const float4 kq = kr[c4];
+                    d = fmaf(qv[4 * c4], kq.x, d); d = fmaf(qv[4 * c4 + 1], kq.y, d);
+                    d = fmaf(qv[4 * c4 + 2], kq.z, d); d = fmaf(qv[4 * c4 + 3], kq.w, d);
+                }
+                sc[u] = d / 5.656854249492381f;                                // np.sqrt(attention_dim), :126
+                const int s = j < i ? j : j - 1;                               // position of neighbour j in ego i's sequence
+                const int64_t edge = (((int64_t)ag * a.n_envs + (ok ? b : 0)) * N + i) * NM1 + s;
+                float noise;
+                if (a.gumbel) {
+                    noise = ok ? a.gumbel[2 * edge + 1] - a.gumbel[2 * edge] : 0.0f;
+                } else {                                                       // same Philox stream as gat_attend_kernel: key (ego, j & 31), word j >> 5
+                    const int64_t key = (((int64_t)ag * a.n_envs + (ok ? b : 0)) * N + i) * 32 + (j & 31);
+                    const uint4 rnd = philox4x32(make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.counter, (uint32_t)(a.counter >> 32)),
+                                                 make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+                    const float uu = u01(j < 32 ? rnd.x : rnd.y);
+                    noise = __logf(uu) - __logf(1.0f - uu);                    // Gumbel - Gumbel ~ Logistic(0,1)
+                }
+                const float dlog = (s_dl[s * 128 + row] + s_dl[(NM1 + s) * 128 + row]) + db;
+                hd[u] = sigmoidf_acc((dlog + noise) * a.inv_tau);              // gumbel-softmax(tau)[..., 1]              (:93-95)
+                if (a.dbg_hard && ok) a.dbg_hard[edge] = hd[u];
+                mx = fmaxf(mx, sc[u]);
+            }
+        }
+        s_pm[part * 128 + row] = mx;
+        __syncthreads();
+        mx = fmaxf(fmaxf(s_pm[row], s_pm[128 + row]), fmaxf(s_pm[256 + row], s_pm[384 + row]));
+        float psum = 0.0f;
+#pragma unroll
+        for (int u = 0; u < JU; ++u) { sc[u] = expf(sc[u] - mx); psum += sc[u]; }     // exp(-inf) = 0 for self / padding
+        s_ps[part * 128 + row] = psum;
+        __syncthreads();
+        const float den = ((s_ps[row] + s_ps[128 + row]) + s_ps[256 + row]) + s_ps[384 + row];
+        // ---- x_i = sum_j soft_ij hard_ij v_j (no renormalisation, :132): this part's neighbours, then the four parts -----
+        float xa[H];
+#pragma unroll
+        for (int c = 0; c < H; ++c) xa[c] = 0.0f;
+#pragma unroll
+        for (int u = 0; u < JU; ++u) {
+            const int j = part + 4 * u;
+            if (j < N && j != i && i < N) {
+                const float wgt = (sc[u] / den) * hd[u];
+                const float4* vr = reinterpret_cast<const float4*>(v_s + (e * 64 + j) * G5_KP);
+#pragma unroll
+                for (int c4 = 0; c4 < H / 4; ++c4) {
+                    const float4 vq = vr[c4];
+                    xa[4 * c4] = fmaf(wgt, vq.x, xa[4 * c4]); xa[4 * c4 + 1] = fmaf(wgt, vq.y, xa[4 * c4 + 1]);
+                    xa[4 * c4 + 2] = fmaf(wgt, vq.z, xa[4 * c4 + 2]); xa[4 * c4 + 3] = fmaf(wgt, vq.w, xa[4 * c4 + 3]);
+                }
+            }
+        }
+        if (part) {
+#pragma unroll
+            for (int c = 0; c < H; ++c) x_part[((part - 1) * H + c) * 128 + row] = xa[c];
+        }
+        __syncthreads();
+        if (!part) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float v2[2];
+#pragma unroll
+                    for (int w2 = 0; w2 < 2; ++w2) {
+                        const int c = 8 * ch + 2 * q + w2;
+                        v2[w2] = ((xa[c] + x_part[c * 128 + row]) + x_part[(H + c) * 128 + row]) + x_part[(2 * H + c) * 128 + row];
+                    }
+                    split_f16(v2[0], v2[1], hi[q], lo[q]);
+                }
+                sts128(t_hx + row_base + (((uint32_t)ch ^ rx) << 4), hi[0], hi[1], hi[2], hi[3]);     // h_prev tile is dead: its product is complete
+                sts128(t_hx + row_base + (((uint32_t)(4 + ch) ^ rx) << 4), lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        fence_proxy_async();
+        tc5_fence_before();
+        __syncthreads();
+        tc5_fence_after();
+        if (tid == 0) {
+            product(GI_COL, t_hx, t_wih);                                      // GRUCell: x W_ih^T                        (:140)
+            tc5_commit(att_bar);
+        }
+        mbar_wait(att_bar, 1);
+        tc5_fence_after();
+        {
+            float gir[8], giz[8], gin[8], ghr[8], ghz[8], ghn[8];
+            tc5_ld8_nowait(tlane + GI_COL + 8 * part, gir);
+            tc5_ld8_nowait(tlane + GI_COL + H + 8 * part, giz);
+            tc5_ld8_nowait(tlane + GI_COL + 2 * H + 8 * part, gin);
+            tc5_ld8_nowait(tlane + GH_COL + 8 * part, ghr);
+            tc5_ld8_nowait(tlane + GH_COL + H + 8 * part, ghz);
+            tc5_ld8_nowait(tlane + GH_COL + 2 * H + 8 * part, ghn);
+            tc5_wait_ld24(gir, giz, gin);
+            tc5_wait_ld24(ghr, ghz, ghn);
+            float* outp = a.out.ptr + ag * a.out.stride_agent + (ok ? b : 0) * a.out.stride_env + (ok ? i : 0) * a.out.stride_slot;
+            const float* bi = s_cb, * bh = s_cb + G3;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int c = 8 * part + q;
+                const float r = sigmoidf_acc((gir[q] + bi[c]) + (ghr[q] + bh[c]));
+                const float z = sigmoidf_acc((giz[q] + bi[H + c]) + (ghz[q] + bh[H + c]));
+                const float nn = tanhf_acc((gin[q] + bi[2 * H + c]) + r * (ghn[q] + bh[2 * H + c]));
+                if (ok) outp[c] = (1.0f - z) * nn + z * hp[q];
+            }
         }
     }
     tc5_fence_before();
@@ -351,16 +602,34 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_recur_tc5_kernel(GatArgs a)
     }
 }
 
-int launch_gat_recur_tc5(const GatArgs& a, int n_agents, cudaStream_t st) {
+// fused == true: the whole K1 step in ONE launch (falls back to false when the fused shared-memory map does not fit, i.e.
+// n_slots close to IPLAN_MAX_SLOTS); fused == false: the recurrence only, dl scratch for gat_attend_kernel.
+// Returns 0 / error; *did_fuse tells the caller whether the attention kernel is still needed.
+int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, cudaStream_t st) {
     static bool configured = false;
+    static int dbg = 0;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gat_recur_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM);
-        if (e != cudaSuccess) { set_error("gat_step: tcgen05 recurrence smem attr %zu: %s", G5_SMEM, cudaGetErrorString(e)); return (int)e; }
+        const char* ev = getenv("IPLAN_GAT_DBG");
+        dbg = ev ? atoi(ev) : 0;
+        cudaError_t e = cudaFuncSetAttribute(gat_tc5_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
+        if (e != cudaSuccess) { set_error("gat_step: tcgen05 kernel smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
-    gat_recur_tc5_kernel<<<dim3((a.n_envs + 1) / 2, n_agents), G5_THREADS, G5_SMEM, st>>>(a);
+    if (fused && g5_layout(a.n_slots, true).total > G5_SMEM_MAX) fused = false;
+    if (dbg) fused = false;
+    const G5Layout Y = g5_layout(a.n_slots, fused);
+    if (Y.total > G5_SMEM_MAX) { set_error("gat_step: n_slots %d needs %u bytes of shared memory", a.n_slots, Y.total); return -1; }
+    const dim3 grid((a.n_envs + 1) / 2, n_agents);
+    if (fused) gat_tc5_kernel<0, true><<<grid, G5_THREADS, Y.total, st>>>(a);
+    else if (dbg == 1) gat_tc5_kernel<1, false><<<grid, G5_THREADS, Y.total, st>>>(a);
+    else if (dbg == 2) gat_tc5_kernel<2, false><<<grid, G5_THREADS, Y.total, st>>>(a);
+    else gat_tc5_kernel<0, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     count_launch();
-    return check_launch("gat_step(recur, tcgen05)");
+    if (did_fuse) *did_fuse = fused;
+    return check_launch(fused ? "gat_step(fused, tcgen05)" : "gat_step(recur, tcgen05)");
 }
 
 }  // namespace iplan

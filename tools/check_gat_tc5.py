@@ -1,5 +1,5 @@
-"""Compare the tcgen05 recurrence of K1 (gat_recur_tc5_kernel, impl 0) with the mma.sync one (gat_recur_kernel,
-impl 1) on the same inputs -- the dl scratch both hand to the attention kernel and the final output -- and time the
+"""Compare the tcgen05 kernels of K1 (impl 0: one fused launch; impl 2: tcgen05 recurrence + attention kernel) with the
+mma.sync path (impl 1) on the same inputs -- the dl scratch both hand to the attention kernel and the final output -- and time the
 recurrence kernel of each with the CUDA events of iplan_gat_step_ex.  Run on a B200:
 
     timeout 300 python tools/check_gat_tc5.py            # B = 3, 6 (ragged CTA pairs), 64, 512 at the Highway shape; MPE shape
@@ -25,7 +25,7 @@ def run(B, A, N, o=5, L=8, reps=5, label=""):
     gum = -torch.log(torch.empty(A, B, N, N - 1, 2, device=dev).exponential_())
     need = _lib.lib.iplan_gat_scratch_floats(B, A, N)
     res = {}
-    for impl in (1, 0):
+    for impl in (1, 2, 0):
         _lib.check(_lib.lib.iplan_gat_set_impl(impl), "set_impl")
         scratch = torch.zeros(need, device=dev)
         out = torch.zeros(A, B, N, 32, device=dev)
@@ -43,14 +43,16 @@ def run(B, A, N, o=5, L=8, reps=5, label=""):
             times.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
         res[impl] = (scratch.view(A, B, 2, N - 1, 64)[..., :N].clone(), out.clone(), times)
     dl1, out1, t1 = res[1]
-    dl0, out0, t0 = res[0]
-    ddl = float((dl1 - dl0).abs().max())
-    dout = float((out1 - out0).abs().max())
-    nan = bool(torch.isnan(dl0).any() or torch.isnan(out0).any())
+    dl2, out2, t2 = res[2]
+    _, out0, t0 = res[0]                        # fused: no dl scratch
+    ddl = float((dl1 - dl2).abs().max())
+    dout = max(float((out1 - out2).abs().max()), float((out1 - out0).abs().max()))
+    nan = bool(torch.isnan(dl2).any() or torch.isnan(out2).any() or torch.isnan(out0).any())
     best = lambda ts, k: min(t[k] for t in ts[1:] or ts)
     print(f"[{label} B={B} A={A} N={N}] max|dl tc5 - dl mma| = {ddl:.3e} (|dl| max {float(dl1.abs().max()):.2f})  "
-          f"max|out diff| = {dout:.3e}  nan={nan}   recur ms: mma {best(t1, 0):.4f}  tc5 {best(t0, 0):.4f}   attend ms {best(t0, 1):.4f}",
-          flush=True)
+          f"max|out - out mma|: tc5+attend {float((out1 - out2).abs().max()):.3e}, fused {float((out1 - out0).abs().max()):.3e}  nan={nan}\n"
+          f"      ms: mma recur {best(t1, 0):.4f} + attend {best(t1, 1):.4f} | tc5 recur {best(t2, 0):.4f} + attend {best(t2, 1):.4f} | "
+          f"fused {best(t0, 0) + best(t0, 1):.4f}", flush=True)
     return ddl, dout, nan
 
 
