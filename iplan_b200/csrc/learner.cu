@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -505,6 +506,9 @@ __global__ void __launch_bounds__(HEAD_THREADS, 3) gru_head_kernel(HeadArgs h) {
     }
 }
 
+// the whole train-mode tail as one kernel
+#include "tail_fused.cuh"
+
 // ---------------------------------------------------------------------------------------
 // K2a gae_adv: GAE backward scan + raw advantages + their moments (one CTA per agent)
 // ---------------------------------------------------------------------------------------
@@ -648,6 +652,50 @@ extern "C" int iplan_learner_tail(const iplan_learner_ctx* c, int train, void* s
         lin_configured = true;
     }
     int launches = 0;
+    HeadArgs h;
+    h.gi = gi; h.gh = gh; h.h0a = c->rnn_a; h.h0c = c->rnn_c; h.h0_sa = c->rnn_stride_agent; h.h0_ld = c->rnn_ld;
+    h.P = P; h.G = G; h.F = c->feat_dim; h.n_actions = c->n_actions; h.T1 = c->T1; h.n_eps = c->n_eps;
+    h.n_train_eps = c->n_train_eps; h.rows = (int)rows; h.actions = c->actions; h.avail = c->avail;
+    h.logp_out = c->logp_out; h.ent_out = c->ent_out; h.value_out = c->value_out;
+    h.old_logp = c->old_logp; h.old_value = c->old_value; h.returns = c->returns; h.adv_raw = c->adv_raw; h.alive = c->alive;
+    h.norm = c->norm; h.clip = c->clip; h.ent_coef = c->ent_coef; h.v_coef = c->v_coef; h.huber_delta = c->huber_delta;
+    h.gscale = c->grad_scale > 0.0f ? c->grad_scale : 1.0f;
+    h.stats = c->stats; h.train = train;
+    if (train) IPLAN_REQUIRE(c->g_actor && c->g_critic && c->old_logp && c->old_value && c->returns && c->adv_raw && c->alive && c->norm && c->stats && c->SM && c->stat,
+                             "learner_tail: train mode needs gradient/loss buffers");
+    static int tail_impl = -1;          // 0 = fused kernel (default), 1 = the twelve separate kernels (cross-check); IPLAN_TAIL_IMPL
+    if (tail_impl < 0) { const char* e = getenv("IPLAN_TAIL_IMPL"); tail_impl = (e && e[0] == '1') ? 1 : 0; }
+    if (train && tail_impl == 0 && c->n_actions <= TF_NOUT) {
+        static bool tf_configured = false;
+        if (!tf_configured) {
+            cudaError_t e = cudaFuncSetAttribute(tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+            if (e != cudaSuccess) { set_error("learner_tail: fused kernel smem attr %zu: %s", TF_SMEM, cudaGetErrorString(e)); return (int)e; }
+            tf_configured = true;
+        }
+        TfArgs fa;
+        fa.h = h; fa.z1 = z1; fa.a1 = a1; fa.z2 = z2; fa.a2 = a2; fa.stat = c->stat; fa.SM = c->SM; fa.rows = rows;
+        const int64_t n_tiles16 = (rows + 15) / 16;
+        // (2A nets) x ctas: one CTA per SM, whole waves of 148
+        int ctas = (int)std::min<int64_t>((n_tiles16 + TF_WARPS - 1) / TF_WARPS, std::max(1, 148 / (2 * A)));
+        tail_fused_kernel<<<dim3((unsigned)ctas, 2 * A), TF_THREADS, TF_SMEM, st>>>(fa);
+        launches = 1;
+        const int64_t n_tiles64 = (rows + 63) / 64;
+        const unsigned dw_ctas = (unsigned)std::min<int64_t>(n_tiles64, 32);
+        const int dw_tiles = (int)((n_tiles64 + dw_ctas - 1) / dw_ctas);
+        lin64_dw_kernel<192><<<dim3(dw_ctas, 2 * A), 256, Lin64Dw<192>::SMEM, st>>>(gi, a2, G, L.wih, rows, dw_tiles, 2); ++launches;
+        {
+            RowBuf h0a{const_cast<float*>(c->rnn_a), c->rnn_stride_agent, 0, c->rnn_ld};
+            RowBuf h0c{const_cast<float*>(c->rnn_c), c->rnn_stride_agent, 0, c->rnn_ld};
+            RowBuf gha{c->GH, 2 * rows * RH3, 0, RH3}, ghc{c->GH + rows * RH3, 2 * rows * RH3, 0, RH3};
+            NetGrads Ga{c->g_actor, c->g_actor, c->actor_stride, c->actor_stride};
+            NetGrads Gc{c->g_critic, c->g_critic, c->critic_stride, c->critic_stride};
+            lin64_dw_kernel<192><<<dim3(dw_ctas, A), 256, Lin64Dw<192>::SMEM, st>>>(gha, h0a, Ga, L.whh, rows, dw_tiles, 1); ++launches;
+            lin64_dw_kernel<192><<<dim3(dw_ctas, A), 256, Lin64Dw<192>::SMEM, st>>>(ghc, h0c, Gc, L.whh, rows, dw_tiles, 1); ++launches;
+        }
+        lin64_dw_kernel<64><<<dim3(dw_ctas, 2 * A), 256, Lin64Dw<64>::SMEM, st>>>(z2, a1, G, L.fc2_w, rows, dw_tiles, 2); ++launches;
+        count_launch(launches);
+        return check_launch("learner_tail(fused)");
+    }
     ln_relu_fwd_kernel<<<dim3(rw, 2 * A), 256, 0, st>>>(z1, a1, P, L.ln1_w, L.ln1_b, rows, 2); ++launches;
     lin64_rows_kernel<64, 64, 128, false><<<dim3(mt128, 2 * A), 256, Lin64Rows<64, 64, 128, false>::SMEM, st>>>(a1, z2, P, L.fc2_w, L.fc2_b, rows, 2); ++launches;
     ln_relu_fwd_kernel<<<dim3(rw, 2 * A), 256, 0, st>>>(z2, a2, P, L.ln2_w, L.ln2_b, rows, 2); ++launches;
@@ -661,17 +709,6 @@ extern "C" int iplan_learner_tail(const iplan_learner_ctx* c, int train, void* s
         lin64_rows_kernel<64, 192, 128, false><<<dim3(mt128, A), 256, Lin64Rows<64, 192, 128, false>::SMEM, st>>>(h0a, gha, Pa, L.whh, L.bhh, rows, 1); ++launches;
         lin64_rows_kernel<64, 192, 128, false><<<dim3(mt128, A), 256, Lin64Rows<64, 192, 128, false>::SMEM, st>>>(h0c, ghc, Pc, L.whh, L.bhh, rows, 1); ++launches;
     }
-    HeadArgs h;
-    h.gi = gi; h.gh = gh; h.h0a = c->rnn_a; h.h0c = c->rnn_c; h.h0_sa = c->rnn_stride_agent; h.h0_ld = c->rnn_ld;
-    h.P = P; h.G = G; h.F = c->feat_dim; h.n_actions = c->n_actions; h.T1 = c->T1; h.n_eps = c->n_eps;
-    h.n_train_eps = c->n_train_eps; h.rows = (int)rows; h.actions = c->actions; h.avail = c->avail;
-    h.logp_out = c->logp_out; h.ent_out = c->ent_out; h.value_out = c->value_out;
-    h.old_logp = c->old_logp; h.old_value = c->old_value; h.returns = c->returns; h.adv_raw = c->adv_raw; h.alive = c->alive;
-    h.norm = c->norm; h.clip = c->clip; h.ent_coef = c->ent_coef; h.v_coef = c->v_coef; h.huber_delta = c->huber_delta;
-    h.gscale = c->grad_scale > 0.0f ? c->grad_scale : 1.0f;
-    h.stats = c->stats; h.train = train;
-    if (train) IPLAN_REQUIRE(c->g_actor && c->g_critic && c->old_logp && c->old_value && c->returns && c->adv_raw && c->alive && c->norm && c->stats && c->SM && c->stat,
-                             "learner_tail: train mode needs gradient/loss buffers");
     {
         const dim3 hgrid((unsigned)std::min<int64_t>((rows + 7) / 8, 148 * 6), A);
         if (c->n_actions <= 5) gru_head_kernel<0, 5><<<hgrid, HEAD_THREADS, 0, st>>>(h);
