@@ -214,3 +214,46 @@ def test_behavior_learn_vs_reference_golden(case):
     import importlib
     mod = importlib.import_module("tools.check_beh_learn")
     assert mod.run(case)
+
+
+def test_packed_batch_last_action_with_list_bs_and_popart_checkpoint_formats(tmp_path):
+    """(a) ``update(..., bs=[0, 2])`` (the pymarl ``envs_not_terminated`` pattern) must reach the packed
+    rows' last-action columns; (b) critic checkpoints in the CUDA reference's format (no ``v_out.*`` keys, 20 optimiser
+    parameters: utils/mappo_utils/popart.py:21-27 on CUDA) load, and ``popart_cuda_quirk`` writes that format."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from iplan_b200.components.episode_buffer import EpisodeBatch
+    from iplan_b200.config import make_args
+    from iplan_b200.controllers.dcntrl_controller import DcntrlMAC
+    from iplan_b200.learners.ippo_learner import IPPOLearner
+    args = make_args("MPE", batch_size_run=3, buffer_size=3, batch_size=2, use_cuda=True, device="cuda")
+    scheme, groups, pre = make_scheme(args)
+    batch = EpisodeBatch(scheme, groups, 3, args.episode_limit + 1, preprocess=pre, device="cuda")
+    d = batch.packed_dims
+    acts = torch.tensor([[[1], [2], [3]], [[4], [0], [1]]])                     # [2 envs, A = 3, 1]
+    batch.update({"actions": acts}, bs=[0, 2], ts=1, mark_filled=False)
+    cols = batch.packed[:, :, 2, d.col_act:d.col_act + d.n_actions].cpu()       # row t + 1 holds onehot(a_t)
+    assert cols[:, 0].argmax(-1).tolist() == [1, 2, 3] and cols[:, 2].argmax(-1).tolist() == [4, 0, 1]
+    assert float(cols[:, 1].abs().sum()) == 0.0 and float(cols[:, 0].sum()) == 3.0
+    # ---- checkpoint formats
+    mac = DcntrlMAC(batch.scheme, groups, args)
+    sd = {k: v.clone() for k, v in mac.critics[0].state_dict().items()}
+    cuda_fmt = {k: v + 1.0 for k, v in sd.items() if not k.startswith("v_out.")}
+    assert len(cuda_fmt) == 20 and len(sd) == 26
+    keep = mac.critics[0].state_dict()["v_out.weight"].clone()
+    mac.critics[0].load_state_dict(cuda_fmt)                                    # strict load of the 20-key format
+    new = mac.critics[0].state_dict()
+    assert torch.equal(new["v_out.weight"], keep) and torch.allclose(new["base.mlp.fc2.0.0.weight"], sd["base.mlp.fc2.0.0.weight"] + 1.0)
+    with pytest.raises(RuntimeError):
+        mac.critics[0].load_state_dict({k: v for k, v in sd.items() if k != "rnn.norm.bias"})       # other keys still strict
+    args.popart_cuda_quirk = True
+    mac2 = DcntrlMAC(batch.scheme, groups, args)
+    learner = IPPOLearner(mac2, batch.scheme, Log(), args)
+    learner.steps["critic"] = 3
+    mac2.save_models(str(tmp_path))
+    learner.save_models(str(tmp_path))
+    assert not any(k.startswith("v_out.") for k in torch.load(tmp_path / "critic_0.th", weights_only=False))
+    opt = torch.load(tmp_path / "critic_0_opt.th", weights_only=False)
+    assert len(opt["param_groups"][0]["params"]) == 20
+    assert float(learner.masks["critic"][mac2.critic_stack.named_offsets()["v_out.weight"][0]]) == 0.0
+    learner.load_models([str(tmp_path)] * 3, load_optimisers=True)
