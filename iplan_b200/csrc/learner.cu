@@ -668,31 +668,37 @@ extern "C" int iplan_learner_tail(const iplan_learner_ctx* c, int train, void* s
     if (train && tail_impl == 0 && c->n_actions <= TF_NOUT) {
         static bool tf_configured = false;
         if (!tf_configured) {
-            cudaError_t e = cudaFuncSetAttribute(tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+            cudaError_t e = cudaFuncSetAttribute(tail_fused_kernel<0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_fused_kernel<0, TF_NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_fused_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
             if (e != cudaSuccess) { set_error("learner_tail: fused kernel smem attr %zu: %s", TF_SMEM, cudaGetErrorString(e)); return (int)e; }
             tf_configured = true;
         }
         TfArgs fa;
         fa.h = h; fa.z1 = z1; fa.a1 = a1; fa.z2 = z2; fa.a2 = a2; fa.stat = c->stat; fa.SM = c->SM; fa.rows = rows;
         const int64_t n_tiles16 = (rows + 15) / 16;
-        // (2A nets) x ctas: one CTA per SM, whole waves of 148
-        int ctas = (int)std::min<int64_t>((n_tiles16 + TF_WARPS - 1) / TF_WARPS, std::max(1, 148 / (2 * A)));
-        tail_fused_kernel<<<dim3((unsigned)ctas, 2 * A), TF_THREADS, TF_SMEM, st>>>(fa);
-        launches = 1;
+        // one CTA per SM: (A agents) x ctas CTAs per net type, the two launches fill the 148 SMs together
+        const int ctas = (int)std::min<int64_t>((n_tiles16 + TF_WARPS - 1) / TF_WARPS, std::max(1, 148 / (2 * A)));
+        if (c->n_actions <= 5) tail_fused_kernel<0, 5><<<dim3((unsigned)ctas, A), TF_THREADS, TF_SMEM, st>>>(fa);
+        else tail_fused_kernel<0, TF_NOUT><<<dim3((unsigned)ctas, A), TF_THREADS, TF_SMEM, st>>>(fa);
+        tail_fused_kernel<1, 1><<<dim3((unsigned)ctas, A), TF_THREADS, TF_SMEM, st>>>(fa);
+        launches = 2;
         const int64_t n_tiles64 = (rows + 63) / 64;
         const unsigned dw_ctas = (unsigned)std::min<int64_t>(n_tiles64, 32);
         const int dw_tiles = (int)((n_tiles64 + dw_ctas - 1) / dw_ctas);
-        lin64_dw_kernel<192><<<dim3(dw_ctas, 2 * A), 256, Lin64Dw<192>::SMEM, st>>>(gi, a2, G, L.wih, rows, dw_tiles, 2); ++launches;
+        // weight gradients (K = rows) + the bias gradients = column sums of the same dY arrays
+        lin64_dw_kernel<192><<<dim3(dw_ctas, 2 * A), 256, Lin64Dw<192>::SMEM, st>>>(gi, a2, G, L.wih, rows, dw_tiles, 2, L.bih); ++launches;
         {
             RowBuf h0a{const_cast<float*>(c->rnn_a), c->rnn_stride_agent, 0, c->rnn_ld};
             RowBuf h0c{const_cast<float*>(c->rnn_c), c->rnn_stride_agent, 0, c->rnn_ld};
             RowBuf gha{c->GH, 2 * rows * RH3, 0, RH3}, ghc{c->GH + rows * RH3, 2 * rows * RH3, 0, RH3};
             NetGrads Ga{c->g_actor, c->g_actor, c->actor_stride, c->actor_stride};
             NetGrads Gc{c->g_critic, c->g_critic, c->critic_stride, c->critic_stride};
-            lin64_dw_kernel<192><<<dim3(dw_ctas, A), 256, Lin64Dw<192>::SMEM, st>>>(gha, h0a, Ga, L.whh, rows, dw_tiles, 1); ++launches;
-            lin64_dw_kernel<192><<<dim3(dw_ctas, A), 256, Lin64Dw<192>::SMEM, st>>>(ghc, h0c, Gc, L.whh, rows, dw_tiles, 1); ++launches;
+            lin64_dw_kernel<192><<<dim3(dw_ctas, A), 256, Lin64Dw<192>::SMEM, st>>>(gha, h0a, Ga, L.whh, rows, dw_tiles, 1, L.bhh); ++launches;
+            lin64_dw_kernel<192><<<dim3(dw_ctas, A), 256, Lin64Dw<192>::SMEM, st>>>(ghc, h0c, Gc, L.whh, rows, dw_tiles, 1, L.bhh); ++launches;
         }
-        lin64_dw_kernel<64><<<dim3(dw_ctas, 2 * A), 256, Lin64Dw<64>::SMEM, st>>>(z2, a1, G, L.fc2_w, rows, dw_tiles, 2); ++launches;
+        lin64_dw_kernel<64><<<dim3(dw_ctas, 2 * A), 256, Lin64Dw<64>::SMEM, st>>>(z2, a1, G, L.fc2_w, rows, dw_tiles, 2, L.fc2_b); ++launches;
+        tail_beta_kernel<<<2 * A, RH, 0, st>>>(P, G, c->feat_dim, c->n_actions); ++launches;
         count_launch(launches);
         return check_launch("learner_tail(fused)");
     }

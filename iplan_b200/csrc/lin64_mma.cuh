@@ -131,9 +131,10 @@ struct Lin64Dw {
     static constexpr int MTW = NO / 64;                  // m-tiles per warp (warp grid 4 x 2)
 };
 
+// bias_off >= 0: also adds the column sums of dY (the gradient of the layer's bias) to Gr[bias_off + n]
 template <int NO>
 __global__ void __launch_bounds__(256) lin64_dw_kernel(RowBuf dy, RowBuf x, NetGrads Gr, int64_t w_off, int64_t rows,
-                                                        int tiles_per_cta, int n_types) {
+                                                        int tiles_per_cta, int n_types, int64_t bias_off = -1) {
     using C = Lin64Dw<NO>;
     extern __shared__ __align__(16) unsigned char l64_smem[];
     float* Ds = reinterpret_cast<float*>(l64_smem);       // [64][DP]  dY tile
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(256) lin64_dw_kernel(RowBuf dy, RowBuf x, NetG
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.0f;
 
+    float colsum = 0.0f;                                    // thread n < NO: sum_r dY[r][n] over this CTA's tiles
     for (int64_t tile = t0; tile < t1; ++tile) {
         const int64_t r_base = tile * C::TR;
         for (int c = tid; c < C::TR * (NO / 4); c += C::THREADS) {
@@ -167,6 +169,12 @@ __global__ void __launch_bounds__(256) lin64_dw_kernel(RowBuf dy, RowBuf x, NetG
         }
         l64_cp_wait_all();
         __syncthreads();
+        if (bias_off >= 0 && tid < NO) {
+            float cs = 0.0f;
+#pragma unroll 8
+            for (int r = 0; r < C::TR; ++r) cs += Ds[r * C::DP + tid];
+            colsum += cs;
+        }
         float part[C::MTW][4][4];
 #pragma unroll
         for (int i = 0; i < C::MTW; ++i)
@@ -207,6 +215,7 @@ __global__ void __launch_bounds__(256) lin64_dw_kernel(RowBuf dy, RowBuf x, NetG
             }
         __syncthreads();
     }
+    if (bias_off >= 0 && tid < NO) atomicAdd(&Gr.net(a, type)[bias_off + tid], colsum);
     float* gw = Gr.net(a, type) + w_off;
 #pragma unroll
     for (int i = 0; i < C::MTW; ++i)

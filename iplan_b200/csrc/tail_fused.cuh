@@ -11,8 +11,11 @@
 // It replaces ln_relu_fwd x2, lin64_rows x6, gru_head x2 and ln_relu_bwd x2 (12 launches whose 64 / 192-wide
 // intermediates each made a round trip through HBM).  What leaves the kernel is what the weight-gradient products need
 // (lin64_dw_kernel: dGI with a2, dGH with h0, dZ2 with a1) and dZ1 (scaled by the input LayerNorm's rstd) for the fc1
-// backward; the small gradients (biases, LayerNorm parameters, head) are accumulated in shared memory and flushed once
-// per CTA.
+// backward.  The small gradients: bias gradients are column sums of dGI / dGH / dZ2 and are taken by the weight-gradient
+// kernel that reads those arrays anyway; LayerNorm beta gradients follow from them linearly (colsum(dY W) = colsum(dY) W:
+// tail_beta_kernel); what remains (LayerNorm gammas, head, the S / M sums of the fc1 backward) is reduced over the eight
+// row groups of a warp with shuffles and added to global memory by four lanes (shared-memory float atomics are CAS
+// loops on this architecture: the first version of this kernel spent most of its time spinning in them).
 //
 // One warp = 16 rows; 8 warps per CTA walk the row tiles of one (agent, net).  Every matrix product is
 // mma.sync.m16n8k16 on f16 hi/lo splits (hi*hi + lo*hi + hi*lo, chains <= 12, fp32 adds between chains); the accumulator
@@ -39,9 +42,6 @@ struct TfFrag {                                    // B fragments {b0, b1} per (
 struct TfVec {
     float ln1_g[RH], ln1_b[RH], b2[RH], ln2_g[RH], ln2_b[RH], bih[RH3], bhh[RH3], ln3_g[RH], ln3_b[RH];
     float head_w[TF_NOUT][RH], head_b[TF_NOUT];
-    // accumulators (zeroed at kernel start)
-    float d_ln1_g[RH], d_ln1_b[RH], d_s[RH], d_m[RH], d_b2[RH], d_ln2_g[RH], d_ln2_b[RH];
-    float d_bih[RH3], d_bhh_n[RH], d_ln3_g[RH], d_ln3_b[RH], d_head_w[TF_NOUT][RH], d_head_b[TF_NOUT], d_stat[4];
 };
 constexpr size_t TF_SMEM = sizeof(TfFrag) + sizeof(TfVec);
 
@@ -58,7 +58,13 @@ __device__ __forceinline__ float tf_quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
 }
-__device__ __forceinline__ void tf_red(float* addr, float v) { atomicAdd(addr, v); }
+// sum over the eight row groups of the warp (lanes with the same t = lane & 3), then lanes 0..3 add to global memory
+__device__ __forceinline__ void tf_red(float* addr, float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if ((threadIdx.x & 31) < 4) atomicAdd(addr, v);
+}
 
 // A fragments (hi, lo) of k-block kb from a 16 x 64 accumulator-layout array
 __device__ __forceinline__ void tf_afrag(const float (&x)[8][4], int kb, uint32_t (&hi)[4], uint32_t (&lo)[4]) {
@@ -97,10 +103,10 @@ __device__ __forceinline__ void tf_ln_relu(const float (&z)[8][4], const float* 
         out[nt][2] = xh[nt][2] * g2.x + b2.x; out[nt][3] = xh[nt][3] * g2.y + b2.y;
     }
 }
-// backward of out = LN(ReLU(z)) g + b for the two rows: dz (in place of dy), column sums of dy x_hat, dy, dz into shared memory
+// backward of out = LN(ReLU(z)) g + b for the two rows: dz (in place of dy); column sums of dy x_hat (-> d gamma) and, if asked, of dz
 __device__ __forceinline__ void tf_ln_relu_bwd(const float (&z)[8][4], const float (&xh)[8][4], const float (&rstd)[2],
                                                const float* __restrict__ gam, int t, float (&dy)[8][4],
-                                               float* d_gam, float* d_bet, float* d_colsum, bool live0, bool live1) {
+                                               float* d_gam, float* d_colsum, float* d_colsum2, bool live0, bool live1) {
     float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
     float dx[8][4];
 #pragma unroll
@@ -119,23 +125,27 @@ __device__ __forceinline__ void tf_ln_relu_bwd(const float (&z)[8][4], const flo
         // rows past the end carry dy = 0 (live = false): they add nothing
         tf_red(d_gam + c, dy[nt][0] * xh[nt][0] + dy[nt][2] * xh[nt][2]);
         tf_red(d_gam + c + 1, dy[nt][1] * xh[nt][1] + dy[nt][3] * xh[nt][3]);
-        tf_red(d_bet + c, dy[nt][0] + dy[nt][2]);
-        tf_red(d_bet + c + 1, dy[nt][1] + dy[nt][3]);
         dy[nt][0] = (live0 && z[nt][0] > 0.f) ? rstd[0] * (dx[nt][0] - m10 - xh[nt][0] * m20) : 0.f;
         dy[nt][1] = (live0 && z[nt][1] > 0.f) ? rstd[0] * (dx[nt][1] - m10 - xh[nt][1] * m20) : 0.f;
         dy[nt][2] = (live1 && z[nt][2] > 0.f) ? rstd[1] * (dx[nt][2] - m11 - xh[nt][2] * m21) : 0.f;
         dy[nt][3] = (live1 && z[nt][3] > 0.f) ? rstd[1] * (dx[nt][3] - m11 - xh[nt][3] * m21) : 0.f;
-        tf_red(d_colsum + c, dy[nt][0] + dy[nt][2]);
-        tf_red(d_colsum + c + 1, dy[nt][1] + dy[nt][3]);
+        if (d_colsum) {
+            tf_red(d_colsum + c, dy[nt][0] + dy[nt][2]);
+            tf_red(d_colsum + c + 1, dy[nt][1] + dy[nt][3]);
+            if (d_colsum2) { tf_red(d_colsum2 + c, dy[nt][0] + dy[nt][2]); tf_red(d_colsum2 + c + 1, dy[nt][1] + dy[nt][3]); }
+        }
     }
 }
 
+// TYPE 0 = actor (NOUT >= n_actions head rows), TYPE 1 = critic (NOUT = 1); blockIdx.y = agent
+template <int TYPE, int NOUT>
 __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
     extern __shared__ __align__(16) unsigned char tf_raw[];
     TfFrag& F = *reinterpret_cast<TfFrag*>(tf_raw);
     TfVec& V = *reinterpret_cast<TfVec*>(tf_raw + sizeof(TfFrag));
     const HeadArgs& h = A.h;
-    const int a = blockIdx.y >> 1, type = blockIdx.y & 1;
+    const int a = blockIdx.y;
+    constexpr int type = TYPE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const float* __restrict__ p = h.P.net(a, type);
@@ -178,17 +188,15 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
         V.head_w[l][c] = l < n_out ? p[L.head_w + l * RH + c] : 0.0f;
     }
     if (tid < TF_NOUT) V.head_b[tid] = tid < n_out ? p[L.head_b + tid] : 0.0f;
-    {
-        float* z0 = V.d_ln1_g;                                              // the accumulators are contiguous up to d_stat
-        const int n_acc = (int)((V.d_stat + 4) - V.d_ln1_g);
-        for (int i = tid; i < n_acc; i += TF_THREADS) z0[i] = 0.0f;
-    }
     __syncthreads();
 
     const float nrm_mean = h.norm[a * 4], nrm_istd = h.norm[a * 4 + 1], inv_msum = h.norm[a * 4 + 2], inv_rows = h.norm[a * 4 + 3];
     const int64_t rows = A.rows;
     const int64_t n_tiles = (rows + 15) / 16;
     const float* h0base = (type == 0 ? h.h0a : h.h0c) + a * h.h0_sa;
+    float* gg = h.G.net(a, type);                                           // this net's gradient buffer
+    float* smS = A.SM + (a * 2 + 0) * 128 + type * 64;
+    float* smM = A.SM + (a * 2 + 1) * 128 + type * 64;
 
     for (int64_t tile = (int64_t)blockIdx.x * TF_WARPS + warp; tile < n_tiles; tile += (int64_t)gridDim.x * TF_WARPS) {
         const int64_t r0 = tile * 16 + g, r1 = r0 + 8;
@@ -284,12 +292,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
             }
         };
         float h1[8][4];
-#pragma unroll
+        // rolled (the body is ~300 instructions; unrolled, the kernel outgrows the instruction cache): the register arrays
+        // are indexed by the loop counter through compare-and-select, never through local memory
+#pragma unroll 1
         for (int ut = 0; ut < 8; ++ut) {
             float rg[4], zg[4], ng[4], ghn[4];
             gates(ut, rg, zg, ng, ghn);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) h1[ut][e] = (1.0f - zg[e]) * ng[e] + zg[e] * h0v[ut][e];
+            for (int e = 0; e < 4; ++e) {
+                float h0e = 0.f;
+#pragma unroll
+                for (int u2 = 0; u2 < 8; ++u2) h0e = u2 == ut ? h0v[u2][e] : h0e;
+                const float v = (1.0f - zg[e]) * ng[e] + zg[e] * h0e;
+#pragma unroll
+                for (int u2 = 0; u2 < 8; ++u2) h1[u2][e] = u2 == ut ? v : h1[u2][e];
+            }
         }
         // LN3 (no ReLU) and the head
         float xh3[8][4], a3[8][4], rs3[2];
@@ -315,9 +332,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
                 a3[nt][2] = xh3[nt][2] * g2.x + b2.x; a3[nt][3] = xh3[nt][3] * g2.y + b2.y;
             }
         }
-        float out0[TF_NOUT], out1[TF_NOUT];                                 // head outputs of the thread's two rows (quad-uniform)
+        float out0[NOUT], out1[NOUT];                                 // head outputs of the thread's two rows (quad-uniform)
 #pragma unroll
-        for (int l = 0; l < TF_NOUT; ++l) {
+        for (int l = 0; l < NOUT; ++l) {
             float d0 = 0.f, d1 = 0.f;
             if (l < n_out) {
 #pragma unroll
@@ -333,32 +350,32 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
             }
         }
         // ---- losses and d loss / d head outputs, per row (all four lanes of a quad compute the same numbers) -------------
-        float dl0[TF_NOUT], dl1[TF_NOUT];
+        float dl0[NOUT], dl1[NOUT];
         float st_loss = 0.f, st_ent = 0.f, st_ratio = 0.f;
-        auto row_loss = [&](int64_t r, bool live, float (&outv)[TF_NOUT], float (&dl)[TF_NOUT]) {
+        auto row_loss = [&](int64_t r, bool live, float (&outv)[NOUT], float (&dl)[NOUT]) {
 #pragma unroll
-            for (int l = 0; l < TF_NOUT; ++l) dl[l] = 0.0f;
+            for (int l = 0; l < NOUT; ++l) dl[l] = 0.0f;
             const int b = (int)(r / h.T1), tt = (int)(r - (int64_t)b * h.T1);
             const bool train_row = live && tt < h.T1 - 1 && b < h.n_train_eps;
             const int64_t ridx = (int64_t)a * h.rows + r;
             if (type == 0) {
                 const int nA = h.n_actions;
                 const int actn = h.actions[ridx];
-                bool masked[TF_NOUT];
+                bool masked[NOUT];
                 float mx = -INFINITY;
 #pragma unroll
-                for (int l = 0; l < TF_NOUT; ++l) {
+                for (int l = 0; l < NOUT; ++l) {
                     masked[l] = l < nA && h.avail && h.avail[ridx * nA + l] == 0;
                     if (masked[l]) outv[l] = -1e10f;
                     if (l < nA) mx = fmaxf(mx, outv[l]);
                 }
                 float den = 0.0f;
 #pragma unroll
-                for (int l = 0; l < TF_NOUT; ++l) if (l < nA) den += expf(outv[l] - mx);
+                for (int l = 0; l < NOUT; ++l) if (l < nA) den += expf(outv[l] - mx);
                 const float lse = mx + logf(den);
-                float ent = 0.0f, lp_a = 0.0f, pl[TF_NOUT], lpl[TF_NOUT];
+                float ent = 0.0f, lp_a = 0.0f, pl[NOUT], lpl[NOUT];
 #pragma unroll
-                for (int l = 0; l < TF_NOUT; ++l) {
+                for (int l = 0; l < NOUT; ++l) {
                     lpl[l] = l < nA ? outv[l] - lse : 0.0f;
                     pl[l] = l < nA ? expf(lpl[l]) : 0.0f;
                     ent -= pl[l] * lpl[l];
@@ -377,7 +394,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
                     const float g_lp = -m * inv_msum * d * h.gscale;
                     const float g_ent = -h.ent_coef * inv_rows * h.gscale;
 #pragma unroll
-                    for (int l = 0; l < TF_NOUT; ++l)
+                    for (int l = 0; l < NOUT; ++l)
                         if (l < nA && !masked[l])
                             dl[l] = g_lp * ((l == actn ? 1.0f : 0.0f) - pl[l]) + g_ent * (-pl[l] * (lpl[l] + ent));
                     st_loss += -fminf(s1_, s2_) * m * inv_msum;
@@ -404,11 +421,17 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
         };
         row_loss(q0, live0, out0, dl0);
         row_loss(q1, live1, out1, dl1);
-        if (t == 0) {                                                       // one lane per row carries the per-row scalars
-            if (st_loss != 0.f) tf_red(&V.d_stat[0], st_loss);
-            if (type == 0) { tf_red(&V.d_stat[1], st_ent); tf_red(&V.d_stat[2], st_ratio); }
+        {   // per-row scalars: the four lanes of a quad hold the same numbers; reduce over the row groups, lane 0 adds
+            auto red0 = [&](float* addr, float v) {
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 8);
+                v += __shfl_xor_sync(0xffffffffu, v, 16);
+                if (lane == 0) atomicAdd(addr, v);
+            };
+            red0(&h.stats[a * 8 + (type == 0 ? 0 : 1)], st_loss);           // policy | value loss
+            if (type == 0) { red0(&h.stats[a * 8 + 2], st_ent); red0(&h.stats[a * 8 + 3], st_ratio); }
 #pragma unroll
-            for (int l = 0; l < TF_NOUT; ++l) if (l < n_out) tf_red(&V.d_head_b[l], dl0[l] + dl1[l]);
+            for (int l = 0; l < NOUT; ++l) if (l < n_out) red0(&gg[L.head_b + l], dl0[l] + dl1[l]);
         }
         // ---- backward: head, LN3 -> dh1 ------------------------------------------------------------------------------
         float dh[8][4];
@@ -417,15 +440,15 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) { dA[nt][0] = dA[nt][1] = dA[nt][2] = dA[nt][3] = 0.f; }
 #pragma unroll
-            for (int l = 0; l < TF_NOUT; ++l) {
+            for (int l = 0; l < NOUT; ++l) {
                 if (l < n_out) {
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {
                         const float2 w = *reinterpret_cast<const float2*>(&V.head_w[l][8 * nt + 2 * t]);
                         dA[nt][0] = fmaf(dl0[l], w.x, dA[nt][0]); dA[nt][1] = fmaf(dl0[l], w.y, dA[nt][1]);
                         dA[nt][2] = fmaf(dl1[l], w.x, dA[nt][2]); dA[nt][3] = fmaf(dl1[l], w.y, dA[nt][3]);
-                        tf_red(&V.d_head_w[l][8 * nt + 2 * t], dl0[l] * a3[nt][0] + dl1[l] * a3[nt][2]);
-                        tf_red(&V.d_head_w[l][8 * nt + 2 * t + 1], dl0[l] * a3[nt][1] + dl1[l] * a3[nt][3]);
+                        tf_red(&gg[L.head_w + l * RH + 8 * nt + 2 * t], dl0[l] * a3[nt][0] + dl1[l] * a3[nt][2]);
+                        tf_red(&gg[L.head_w + l * RH + 8 * nt + 2 * t + 1], dl0[l] * a3[nt][1] + dl1[l] * a3[nt][3]);
                     }
                 }
             }
@@ -434,10 +457,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
             for (int nt = 0; nt < 8; ++nt) {
                 const int c = 8 * nt + 2 * t;
                 const float2 g2 = *reinterpret_cast<const float2*>(V.ln3_g + c);
-                tf_red(&V.d_ln3_g[c], dA[nt][0] * xh3[nt][0] + dA[nt][2] * xh3[nt][2]);
-                tf_red(&V.d_ln3_g[c + 1], dA[nt][1] * xh3[nt][1] + dA[nt][3] * xh3[nt][3]);
-                tf_red(&V.d_ln3_b[c], dA[nt][0] + dA[nt][2]);
-                tf_red(&V.d_ln3_b[c + 1], dA[nt][1] + dA[nt][3]);
+                tf_red(&gg[L.ln3_w + c], dA[nt][0] * xh3[nt][0] + dA[nt][2] * xh3[nt][2]);
+                tf_red(&gg[L.ln3_w + c + 1], dA[nt][1] * xh3[nt][1] + dA[nt][3] * xh3[nt][3]);
                 dA[nt][0] *= g2.x; dA[nt][1] *= g2.y; dA[nt][2] *= g2.x; dA[nt][3] *= g2.y;
                 a0 += dA[nt][0] + dA[nt][1]; a1 += dA[nt][2] + dA[nt][3];
                 c0 = fmaf(dA[nt][0], xh3[nt][0], c0); c0 = fmaf(dA[nt][1], xh3[nt][1], c0);
@@ -459,7 +480,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
         float* gi1 = h.gi.row(a, type, q1);
         float* gh0 = h.gh.row(a, type, q0);
         float* gh1 = h.gh.row(a, type, q1);
-#pragma unroll
+#pragma unroll 1
         for (int up = 0; up < 4; ++up) {                                    // 16 hidden units = one k-block of each gate
             float dgi[3][2][4];                                             // [gate][unit tile of the pair][e]
 #pragma unroll
@@ -470,8 +491,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
                 float dghn[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float dn = dh[ut][e] * (1.0f - zg[e]);
-                    const float dz = dh[ut][e] * (h0v[ut][e] - ng[e]);
+                    float dhe = 0.f, h0e = 0.f;
+#pragma unroll
+                    for (int u2 = 0; u2 < 8; ++u2) { dhe = u2 == ut ? dh[u2][e] : dhe; h0e = u2 == ut ? h0v[u2][e] : h0e; }
+                    const float dn = dhe * (1.0f - zg[e]);
+                    const float dz = dhe * (h0e - ng[e]);
                     const float dan = dn * (1.0f - ng[e] * ng[e]);
                     const float dr = dan * ghn[e];
                     dgi[0][w2][e] = dr * rg[e] * (1.0f - rg[e]);
@@ -490,11 +514,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
                         *reinterpret_cast<float2*>(gi1 + q * RH + c) = make_float2(dgi[q][w2][2], dgi[q][w2][3]);
                         *reinterpret_cast<float2*>(gh1 + q * RH + c) = q < 2 ? make_float2(dgi[q][w2][2], dgi[q][w2][3]) : make_float2(dghn[2], dghn[3]);
                     }
-                    tf_red(&V.d_bih[q * RH + c], dgi[q][w2][0] + dgi[q][w2][2]);
-                    tf_red(&V.d_bih[q * RH + c + 1], dgi[q][w2][1] + dgi[q][w2][3]);
                 }
-                tf_red(&V.d_bhh_n[c], dghn[0] + dghn[2]);
-                tf_red(&V.d_bhh_n[c + 1], dghn[1] + dghn[3]);
             }
             // dA2 += dGI[:, this k-block of each gate] . W_ih   (three k-blocks: a chain of 9 per n-tile, then an fp32 add)
             uint32_t dh_[3][4], dl_[3][4];
@@ -517,7 +537,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
         {
             float xh2[8][4], tmp[8][4], rs2[2];                             // x_hat of LN2 again (cheaper than keeping 32 registers alive)
             tf_ln_relu(z2, V.ln2_g, V.ln2_b, t, xh2, tmp, rs2);
-            tf_ln_relu_bwd(z2, xh2, rs2, V.ln2_g, t, da2, V.d_ln2_g, V.d_ln2_b, V.d_b2, live0, live1);   // da2 = dZ2 now
+            tf_ln_relu_bwd(z2, xh2, rs2, V.ln2_g, t, da2, gg + L.ln2_w, nullptr, nullptr, live0, live1);   // da2 = dZ2 now
         }
         {
             float* o0 = A.z2.row(a, type, q0);
@@ -549,7 +569,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
                 z[nt][0] = v0.x; z[nt][1] = v0.y; z[nt][2] = v1.x; z[nt][3] = v1.y;
             }
             tf_ln_relu(z, V.ln1_g, V.ln1_b, t, xh, tmp, rs1);
-            tf_ln_relu_bwd(z, xh, rs1, V.ln1_g, t, da1, V.d_ln1_g, V.d_ln1_b, V.d_s, live0, live1);  // da1 = dZ1 now
+            tf_ln_relu_bwd(z, xh, rs1, V.ln1_g, t, da1, gg + L.ln1_w, gg + L.fc1_b, smS, live0, live1);  // da1 = dZ1 now; S = colsum
         }
         {
             const float mu0 = A.stat[(a * rows + q0) * 2], rs0 = A.stat[(a * rows + q0) * 2 + 1];
@@ -558,34 +578,29 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
             for (int nt = 0; nt < 8; ++nt) {
                 const int c = 8 * nt + 2 * t;
                 const float v00 = da1[nt][0] * rs0, v01 = da1[nt][1] * rs0, v10 = da1[nt][2] * rs1_, v11 = da1[nt][3] * rs1_;
-                tf_red(&V.d_m[c], v00 * mu0 + v10 * mu1);
-                tf_red(&V.d_m[c + 1], v01 * mu0 + v11 * mu1);
+                tf_red(smM + c, v00 * mu0 + v10 * mu1);
+                tf_red(smM + c + 1, v01 * mu0 + v11 * mu1);
                 if (live0) *reinterpret_cast<float2*>(z1p0 + c) = make_float2(v00, v01);
                 if (live1) *reinterpret_cast<float2*>(z1p1 + c) = make_float2(v10, v11);
             }
         }
     }
-    // ---- flush the CTA's small gradients ------------------------------------------------------------------------------
-    __syncthreads();
-    float* gg = h.G.net(a, type);
-    for (int c = tid; c < RH; c += TF_THREADS) {
-        atomicAdd(&gg[L.ln1_w + c], V.d_ln1_g[c]); atomicAdd(&gg[L.ln1_b + c], V.d_ln1_b[c]);
-        atomicAdd(&gg[L.fc1_b + c], V.d_s[c]);
-        atomicAdd(&A.SM[(a * 2 + 0) * 128 + type * 64 + c], V.d_s[c]);
-        atomicAdd(&A.SM[(a * 2 + 1) * 128 + type * 64 + c], V.d_m[c]);
-        atomicAdd(&gg[L.fc2_b + c], V.d_b2[c]);
-        atomicAdd(&gg[L.ln2_w + c], V.d_ln2_g[c]); atomicAdd(&gg[L.ln2_b + c], V.d_ln2_b[c]);
-        atomicAdd(&gg[L.ln3_w + c], V.d_ln3_g[c]); atomicAdd(&gg[L.ln3_b + c], V.d_ln3_b[c]);
-        atomicAdd(&gg[L.bhh + 2 * RH + c], V.d_bhh_n[c]);
-    }
-    for (int c = tid; c < RH3; c += TF_THREADS) {
-        atomicAdd(&gg[L.bih + c], V.d_bih[c]);
-        if (c < 2 * RH) atomicAdd(&gg[L.bhh + c], V.d_bih[c]);             // the r and z gate biases see the same gradient on both sides
-    }
-    for (int idx = tid; idx < n_out * RH; idx += TF_THREADS) atomicAdd(&gg[L.head_w + idx], V.d_head_w[idx / RH][idx % RH]);
-    if (tid < n_out) atomicAdd(&gg[L.head_b + tid], V.d_head_b[tid]);
-    if (tid == 0) {
-        atomicAdd(&h.stats[a * 8 + (type == 0 ? 0 : 1)], V.d_stat[0]);     // policy | value loss
-        if (type == 0) { atomicAdd(&h.stats[a * 8 + 2], V.d_stat[1]); atomicAdd(&h.stats[a * 8 + 3], V.d_stat[2]); }
-    }
+}
+
+// LayerNorm beta gradients and the rest of the gate-bias bookkeeping, from the column sums the weight-gradient kernels
+// left in the bias slots:  d beta2 = (d b_ih) W_ih,  d beta1 = (d b2) W2,  d beta3 = (d head_b) W_head   (colsum(dY W) = colsum(dY) W).
+// One CTA per (agent, net); 64 threads.
+__global__ void tail_beta_kernel(NetParams P, NetGrads G, int F, int n_actions) {
+    const int a = blockIdx.x >> 1, type = blockIdx.x & 1, c = threadIdx.x;
+    const float* p = P.net(a, type);
+    float* g = G.net(a, type);
+    const int n_out = type == 0 ? n_actions : 1;
+    const TrunkLayout L = trunk_layout(F, n_out, type == 1);
+    float b2 = 0.f, b1 = 0.f, b3 = 0.f;
+    for (int k = 0; k < RH3; ++k) b2 = fmaf(g[L.bih + k], p[L.wih + k * RH + c], b2);
+    for (int k = 0; k < RH; ++k) b1 = fmaf(g[L.fc2_b + k], p[L.fc2_w + k * RH + c], b1);
+    for (int k = 0; k < n_out; ++k) b3 = fmaf(g[L.head_b + k], p[L.head_w + k * RH + c], b3);
+    g[L.ln2_b + c] = b2;
+    g[L.ln1_b + c] = b1;
+    g[L.ln3_b + c] = b3;
 }
