@@ -42,6 +42,8 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--with-aux", action="store_true",
+                   help="also run Behavior_policy.learn and Prediction_policy.learn in every step (run_ippo.py:263-286 order) and report their time")
     return p.parse_args()
 
 
@@ -256,6 +258,15 @@ def main():
         batch, *_ = sysm.runner.run()
         s1.record()
         sysm.learner.insert_episode_batch(batch)
+        if args.with_aux:                                   # run_ippo.py:269-284: both auxiliary learners, then the IPPO update
+            x0, x1, x2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            x0.record()
+            sysm.behavior.learn(batch, sysm.runner.t_env)
+            x1.record()
+            sysm.prediction.learn(batch, sysm.runner.t_env)
+            x2.record()
+            gat_events.append(("aux_behavior_learn", x0, x1))
+            gat_events.append(("aux_prediction_learn", x1, x2))
         sysm.learner.train(sysm.runner.t_env)
         gat_events.append(("roll", s0, s1))
     e1.record()
@@ -284,6 +295,7 @@ def main():
     gat_mean = sum(gat_ms) / max(1, len(gat_ms))
     rec_mean = sum(rec_ms) / max(1, len(rec_ms))
     breakdown = {tag: sum(times(tag)) / args.steps for tag in ("gat", "gat_recur", "gat_attend", "ctrl", "beh")}
+    aux = {tag: sum(times(tag)) / args.steps for tag in ("aux_behavior_learn", "aux_prediction_learn")} if args.with_aux else None
 
     # ---- e2e: same work through the reference-facing numpy API -----------------------------
     log(f"timed region done: {ms_per_step:.1f} ms/step; e2e leg")
@@ -352,7 +364,7 @@ def main():
                    "feat_dim": sysm.mac.input_shape, "episode_limit": T, "ppo_epoch": a.ppo_epoch,
                    "parallelism": f"env-sharded x{world}", "l2": "inputs (2.3 GB episode store) exceed L2"},
         "ms_rollout": sum(roll_ms) / max(1, len(roll_ms)), "ms_update": ms_per_step - sum(roll_ms) / max(1, len(roll_ms)),
-        "rollout_kernels_ms": breakdown, "update_phases_ms": upd, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
+        "rollout_kernels_ms": breakdown, "update_phases_ms": upd, "aux_learners_ms": aux, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e,
     }
     log("gpu legs done" + ("; cpu baseline" if world == 1 and not args.no_cpu_baseline else ""))
     if world == 1 and not args.no_cpu_baseline:

@@ -668,21 +668,19 @@ extern "C" int iplan_learner_tail(const iplan_learner_ctx* c, int train, void* s
     if (train && tail_impl == 0 && c->n_actions <= TF_NOUT) {
         static bool tf_configured = false;
         if (!tf_configured) {
-            cudaError_t e = cudaFuncSetAttribute(tail_fused_kernel<0, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_fused_kernel<0, TF_NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_fused_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+            cudaError_t e = cudaFuncSetAttribute(tail_fused_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(tail_fused_kernel<TF_NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TF_SMEM);
             if (e != cudaSuccess) { set_error("learner_tail: fused kernel smem attr %zu: %s", TF_SMEM, cudaGetErrorString(e)); return (int)e; }
             tf_configured = true;
         }
         TfArgs fa;
         fa.h = h; fa.z1 = z1; fa.a1 = a1; fa.z2 = z2; fa.a2 = a2; fa.stat = c->stat; fa.SM = c->SM; fa.rows = rows;
         const int64_t n_tiles16 = (rows + 15) / 16;
-        // one CTA per SM: (A agents) x ctas CTAs per net type, the two launches fill the 148 SMs together
+        // one CTA per SM: ctas x (2A nets) CTAs, actor and critic tiles side by side
         const int ctas = (int)std::min<int64_t>((n_tiles16 + TF_WARPS - 1) / TF_WARPS, std::max(1, 148 / (2 * A)));
-        if (c->n_actions <= 5) tail_fused_kernel<0, 5><<<dim3((unsigned)ctas, A), TF_THREADS, TF_SMEM, st>>>(fa);
-        else tail_fused_kernel<0, TF_NOUT><<<dim3((unsigned)ctas, A), TF_THREADS, TF_SMEM, st>>>(fa);
-        tail_fused_kernel<1, 1><<<dim3((unsigned)ctas, A), TF_THREADS, TF_SMEM, st>>>(fa);
-        launches = 2;
+        if (c->n_actions <= 5) tail_fused_kernel<5><<<dim3((unsigned)ctas, 2 * A), TF_THREADS, TF_SMEM, st>>>(fa);
+        else tail_fused_kernel<TF_NOUT><<<dim3((unsigned)ctas, 2 * A), TF_THREADS, TF_SMEM, st>>>(fa);
+        launches = 1;
         const int64_t n_tiles64 = (rows + 63) / 64;
         const unsigned dw_ctas = (unsigned)std::min<int64_t>(n_tiles64, 32);
         const int dw_tiles = (int)((n_tiles64 + dw_ctas - 1) / dw_ctas);

@@ -137,14 +137,12 @@ __device__ __forceinline__ void tf_ln_relu_bwd(const float (&z)[8][4], const flo
     }
 }
 
-// TYPE 0 = actor (NOUT >= n_actions head rows), TYPE 1 = critic (NOUT = 1); blockIdx.y = agent
+// TYPE 0 = actor (NOUT >= n_actions head rows), TYPE 1 = critic (NOUT = 1)
 template <int TYPE, int NOUT>
-__global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
-    extern __shared__ __align__(16) unsigned char tf_raw[];
+__device__ __forceinline__ void tail_fused_body(const TfArgs& A, unsigned char* tf_raw, int a) {
     TfFrag& F = *reinterpret_cast<TfFrag*>(tf_raw);
     TfVec& V = *reinterpret_cast<TfVec*>(tf_raw + sizeof(TfFrag));
     const HeadArgs& h = A.h;
-    const int a = blockIdx.y;
     constexpr int type = TYPE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -585,6 +583,14 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
             }
         }
     }
+}
+
+// blockIdx.y = 2 * agent + net type: actor and critic tiles run side by side so that one launch covers all 148 SMs
+template <int NOUT_ACTOR>
+__global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
+    extern __shared__ __align__(16) unsigned char tf_raw[];
+    if ((blockIdx.y & 1) == 0) tail_fused_body<0, NOUT_ACTOR>(A, tf_raw, blockIdx.y >> 1);
+    else tail_fused_body<1, 1>(A, tf_raw, blockIdx.y >> 1);
 }
 
 // LayerNorm beta gradients and the rest of the gate-bias bookkeeping, from the column sums the weight-gradient kernels
