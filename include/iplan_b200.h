@@ -98,6 +98,25 @@ int iplan_gat_step_ex(const float* gat_params, int64_t param_stride,
                       int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
                       void* ev_begin, void* ev_mid, void* ev_end, void* stream);
 
+/* ---- GAT_Net.forward at hidden width 128 (BASELINE.json configs[4], the synthetic GAT + GRU microbench) -----------------
+ * nova/GAT_Net.py:41-142 with GAT_hidden_dim = attention_dim = 128 and 16 slots per (env, agent-net) "item".  The row x weight
+ * products of the op (encode, factored input projections, q|k|v, GRUCell projections) are plain GEMMs that the host runs
+ * through a library (iplan_b200/nova/gat128.py); these three kernels are the rest:
+ *   iplan_gat128_recur   the bidirectional hard-attention GRU over the 15 neighbours of every ego (:57-97) with W_hh held in
+ *                        tensor memory (tcgen05.mma, A operand from TMEM) -> per-edge logit differences
+ *       P, Q   [2 dirs][A][items][16][384]  ego / neighbour halves of W_ih [enc_i ; enc_j], rows r|z|n, pre-multiplied by the
+ *              gate scales (-log2 e for r|z, 2 log2 e for n); Q additionally carries b_ih (+ b_hh for r|z), scaled alike
+ *       whh    [A][2][384][128]   bhn [A][2][128] (b_hh of the n gate)   lw [A][2][128] (hard_encoding row 1 - row 0, per direction)
+ *       dl     [A][items][2][15][16]  out
+ *   iplan_gat128_attend  scores, gumbel hard gate, soft-max, aggregation (:99-133); qkv [A*items*16][384] (v without bias),
+ *                        gumbel NULL (Philox) or [A][items][16][15][2];  x out [A*items*16][128]
+ *   iplan_gat128_gates   GRUCell gate math (:140) from gi, gh [rows][384] (biases included) and h_prev -> out [rows][128] */
+int iplan_gat128_recur(const float* P, const float* Q, const float* whh, const float* bhn, const float* lw, float* dl,
+                       int n_agents, int64_t n_items, void* stream);
+int iplan_gat128_attend(const float* qkv, const float* v_bias, const float* dl, const float* he_b, const float* gumbel,
+                        uint64_t seed, uint64_t counter, float tau, float* x, int n_agents, int64_t n_items, void* stream);
+int iplan_gat128_gates(const float* gi, const float* gh, const float* hprev, float* out, int64_t rows, void* stream);
+
 /* ---- K1b: behaviour-encoder step -----------------------------------------------
  * replaces Behavior_policy.latent_update (nova/stable_behavior_policy.py:83-123)
  * = EncoderRNN.forward (nova/behavior_net.py:17-22) over the history window from the

@@ -43,6 +43,9 @@ _SIGNATURES = {
                             _i, _i, _i, _i, _i, _p]),
     "iplan_gat_step_ex": (_i, [_p, _i64, View, View, View, View, _p, _u64, _u64, _f, _p, _p, _i64,
                                _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "iplan_gat128_recur": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _p]),
+    "iplan_gat128_attend": (_i, [_p, _p, _p, _p, _p, _u64, _u64, _f, _p, _i, _i64, _p]),
+    "iplan_gat128_gates": (_i, [_p, _p, _p, _p, _i64, _p]),
     "iplan_behavior_step": (_i, [_p, _i64, View, View, View, View, _f, _i, _i, _i, _i, _i, _i, _p]),
     "iplan_behavior_step_ex": (_i, [_p, _i64, View, _i64, _i, View, View, View, _f, _i, _i, _i, _i, _i, _i, _p]),
     "iplan_controller_step": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64,
