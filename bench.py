@@ -42,6 +42,8 @@ def parse():
     p.add_argument("--e2e-steps", type=int, default=3)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--workload", default="highway", choices=["highway", "microbench"],
+                   help="highway = BASELINE configs[2] (headline); microbench = configs[4], the 8192 x 32 x 16 x 128-d GAT + GRU forward")
     p.add_argument("--with-aux", action="store_true",
                    help="also run Behavior_policy.learn and Prediction_policy.learn in every step (run_ippo.py:263-286 order) and report their time")
     return p.parse_args()
@@ -205,8 +207,141 @@ def log(msg):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
+MB_ENVS, MB_AGENTS, MB_SLOTS, MB_DIM = 8192, 32, 16, 128
+MB_METRIC = "env-steps/sec synthetic GAT+GRU microbench (8192 envs x 32 agent-nets x 16 slots x 128-d)"
+
+
+def run_microbench_reference(args):
+    """--impl reference --workload microbench: the reference's own GAT_Net at width 128 on the host cores, bounded sample."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from oracle import ref_driver as R
+    cores = R.usable_cpus()
+    torch.set_num_threads(cores)
+    per_item = []
+    for it in range(args.warmup + args.steps):
+        t = R.time_gat_net_128(n_envs=16, n_nets=2, seed=it)
+        if it >= min(args.warmup, 1):
+            per_item.append(t)
+    t_item = sum(per_item) / len(per_item)
+    step_s = t_item * MB_ENVS * MB_AGENTS                 # one forward of the whole 8192 x 32 problem (no sharding on CPU)
+    value = MB_ENVS / step_s
+    print(json.dumps({
+        "impl": "reference", "metric": MB_METRIC, "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GAT_Net.forward, hidden 128, 16 slots, 8192 envs x 32 agent-nets (BASELINE configs[4])"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "reference",
+                         "sample": f"the reference's own GAT_Net(128) (oracle/_ref) on 2 nets x 16 envs per step, scaled x{MB_ENVS * MB_AGENTS / 32:g} in items; {cores} torch threads"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_microbench(args):
+    """BASELINE configs[4]: one step = one GAT_Net.forward (width 128) over this rank's shard of the 8192 envs x 32 agent-nets."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from iplan_b200 import _lib
+    from iplan_b200.nova.gat128 import GAT128
+    envs = MB_ENVS // world                               # strong scaling: the 8192 envs are sharded, no exchange (forward only)
+    A, N, H = MB_AGENTS, MB_SLOTS, MB_DIM
+    net = GAT128(A, seed=0)                               # same weights on every rank (same seed)
+    g = torch.Generator(device="cuda").manual_seed(112358 + rank)
+    x = (torch.rand(A, envs, N, H, device="cuda", generator=g) * 2 - 1)
+    h = torch.tanh(torch.randn(A, envs, N, H, device="cuda", generator=g))
+    out = torch.empty_like(x)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        net.forward(x, h, out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        net.forward(x, h, out=out, events=evs[k])          # x (2.1 GB / rank at N=1) exceeds L2: nothing stays cached between steps
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t) / args.steps
+    launches = (_lib.launch_count() - l0) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    rec_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    # e2e: host buffers in, host result out, every step
+    xh, hh = torch.empty(x.shape, pin_memory=True).copy_(x), torch.empty(h.shape, pin_memory=True).copy_(h)
+    oh = torch.empty(x.shape, pin_memory=True)
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        x.copy_(xh, non_blocking=True); h.copy_(hh, non_blocking=True)
+        net.forward(x, h, out=out)
+        oh.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    dt = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device="cuda")
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    f_recur, f_all, b_all = GAT128.algorithmic(A, envs)
+    ach = f_recur / (rec_ms * 1e-3) / 1e12
+    out_json = {
+        "metric": MB_METRIC, "value": MB_ENVS / (ms_per_step / 1e3), "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "GAT_Net.forward, hidden 128, 16 slots, 8192 envs x 32 agent-nets (BASELINE configs[4])",
+                   "envs": MB_ENVS, "envs_per_gpu": envs, "agent_nets": A, "slots": N, "dim": H,
+                   "parallelism": f"env-sharded x{world} (forward only: no collective)", "l2": "inputs (2.1 GB per tensor per GPU at N=1) exceed L2"},
+        "gpu_launches": launches, "library_gemms_per_step": 9, "clocks": clocks,
+        "roofline": {"kernel": "gat128_recur_kernel (bidirectional 15-step GRU of every ego, W_hh in tensor memory, tcgen05.mma.kind::f16 x3 passes)",
+                     "bound": "tensor", "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"], "traffic": None,
+                     "peak_source": pk["src"] + " bf16 sustained (MEASURED_PEAKS.json)", "launch_ms": rec_ms,
+                     "algorithmic_flops_per_launch": f_recur, "share_of_step": rec_ms / ms_per_step,
+                     "whole_op": {"algorithmic_flops": f_all, "algorithmic_bytes": b_all, "tflops": f_all / (ms_per_step * 1e-3) / 1e12,
+                                  "hbm_frac_of_algorithmic_bytes": b_all / (ms_per_step * 1e-3) / 1e9 / pk["hbm"]}},
+        "e2e": {"value": MB_ENVS / float(dt), "unit": "env-steps/s", "h2d_bytes_per_step": 2 * x.numel() * 4, "d2h_bytes_per_step": x.numel() * 4,
+                "ms_per_step": float(dt) * 1e3, "steps": e2e_steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_driver as R
+        if R.available():
+            torch.set_num_threads(R.usable_cpus())
+            t_item = R.time_gat_net_128(n_envs=16, n_nets=2)
+            v = MB_ENVS / (t_item * MB_ENVS * MB_AGENTS)
+            out_json["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": R.usable_cpus(), "kind": "reference",
+                                        "sample": "the reference's own GAT_Net(128) (oracle/_ref) on 2 nets x 16 envs, scaled in items"}
+    print(json.dumps(out_json))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
+    if args.workload == "microbench":
+        return run_microbench_reference(args) if args.impl == "reference" else run_microbench(args)
     if args.impl == "reference":
         return run_reference(args)
     import torch

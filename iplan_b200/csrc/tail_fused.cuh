@@ -53,6 +53,12 @@ struct TfArgs {
     int64_t rows;
 };
 
+// gates with ex2.approx / rcp.approx (abs error ~1e-7, as in K1): sigmoid(x) = 1 / (1 + 2^(-x log2 e)), tanh(x) = 1 - 2 / (1 + 2^(2 x log2 e))
+__device__ __forceinline__ float tf_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tf_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tf_sigmoid(float x) { return tf_rcp(1.0f + tf_ex2(fminf(-1.4426950408889634f * x, 80.0f))); }
+__device__ __forceinline__ float tf_tanh(float x) { return fmaf(-2.0f, tf_rcp(1.0f + tf_ex2(fminf(2.8853900817779268f * x, 80.0f))), 1.0f); }
+
 __device__ __forceinline__ float tf_quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -137,13 +143,16 @@ __device__ __forceinline__ void tf_ln_relu_bwd(const float (&z)[8][4], const flo
     }
 }
 
-// TYPE 0 = actor (NOUT >= n_actions head rows), TYPE 1 = critic (NOUT = 1)
-template <int TYPE, int NOUT>
-__device__ __forceinline__ void tail_fused_body(const TfArgs& A, unsigned char* tf_raw, int a) {
+// blockIdx.y = 2 * agent + net type (0 actor: NOUT >= n_actions head rows; 1 critic: one head row): actor and critic tiles
+// run side by side so that one launch covers all 148 SMs.  ONE body for both (only the loss section branches on the type):
+// two instantiations of this much straight-line code would not stay in the instruction cache.
+template <int NOUT>
+__global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
+    extern __shared__ __align__(16) unsigned char tf_raw[];
+    const int a = blockIdx.y >> 1, type = blockIdx.y & 1;
     TfFrag& F = *reinterpret_cast<TfFrag*>(tf_raw);
     TfVec& V = *reinterpret_cast<TfVec*>(tf_raw + sizeof(TfFrag));
     const HeadArgs& h = A.h;
-    constexpr int type = TYPE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const float* __restrict__ p = h.P.net(a, type);
@@ -283,10 +292,10 @@ __device__ __forceinline__ void tail_fused_body(const TfArgs& A, unsigned char* 
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                rg[e] = sigmoidf_acc(gi[0][e] + gh[0][e]);
-                zg[e] = sigmoidf_acc(gi[1][e] + gh[1][e]);
+                rg[e] = tf_sigmoid(gi[0][e] + gh[0][e]);
+                zg[e] = tf_sigmoid(gi[1][e] + gh[1][e]);
                 ghn[e] = gh[2][e];
-                ng[e] = tanhf_acc(gi[2][e] + rg[e] * ghn[e]);
+                ng[e] = tf_tanh(gi[2][e] + rg[e] * ghn[e]);
             }
         };
         float h1[8][4];
@@ -583,14 +592,6 @@ __device__ __forceinline__ void tail_fused_body(const TfArgs& A, unsigned char* 
             }
         }
     }
-}
-
-// blockIdx.y = 2 * agent + net type: actor and critic tiles run side by side so that one launch covers all 148 SMs
-template <int NOUT_ACTOR>
-__global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
-    extern __shared__ __align__(16) unsigned char tf_raw[];
-    if ((blockIdx.y & 1) == 0) tail_fused_body<0, NOUT_ACTOR>(A, tf_raw, blockIdx.y >> 1);
-    else tail_fused_body<1, 1>(A, tf_raw, blockIdx.y >> 1);
 }
 
 // LayerNorm beta gradients and the rest of the gate-bias bookkeeping, from the column sums the weight-gradient kernels

@@ -312,3 +312,24 @@ def measure(B=512, T=90, threads=None, seed=0, rollout_envs=ROLLOUT_ENVS, update
               f"(T={T}, 15 epochs, 5 agents) x{B / update_episodes:g} in rows; {threads} torch threads")
     return dict(value=value, t_step=t_step, t_train=t_upd, parts=parts, cores=threads, sample=sample,
                 sample_s=time.perf_counter() - t0)
+
+
+# ---- BASELINE configs[4]: the reference's GAT_Net at hidden width 128 (synthetic GAT + GRU microbench) -----------------------
+def time_gat_net_128(n_envs=16, n_nets=1, seed=0):
+    """Seconds per (env, agent-net) item of the reference's own GAT_Net.forward (nova/GAT_Net.py:41-142) at
+    GAT_hidden_dim = attention_dim = input width = 128 and 16 slots, measured on `n_nets` nets x `n_envs` envs."""
+    activate()
+    from nova.GAT_Net import GAT_Net
+    args = ref_args("highway", GAT_hidden_dim=128, attention_dim=128)
+    args.max_vehicle_num = 16
+    torch.manual_seed(seed)
+    nets = [GAT_Net(input_shape=128, args=args) for _ in range(n_nets)]
+    x = torch.rand(n_envs, 16, 128) * 2 - 1
+    h = torch.tanh(torch.randn(n_envs * 16, 128))
+    with torch.no_grad():
+        nets[0](x, h)                                                   # warm-up
+        t0 = time.perf_counter()
+        for net in nets:
+            net(x, h)
+        dt = time.perf_counter() - t0
+    return dt / (n_envs * n_nets)
