@@ -80,13 +80,17 @@ int iplan_gat_step(const float* gat_params, int64_t param_stride,
                    int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim,
                    void* stream);
 
-/* Which kernel runs the hard-attention recurrence of K1 (nova/GAT_Net.py:57-97):
- *   0  gat_recur_tc5_kernel   tcgen05.mma + TMEM, one CTA per (2 envs, agent-net), both directions   (default)
- *   1  gat_recur_kernel       mma.sync m16n8k16, one CTA per (env, agent-net, direction)              (cross-check)
- * Same inputs, same scratch layout, same attention kernel afterwards.  Process-wide; the default can also be chosen
- * with the environment variable IPLAN_GAT_IMPL (0 / 1) read at the first call. */
+/* Which kernels run K1 (nova/GAT_Net.py:41-142):
+ *   0  gat_tc5_kernel<fused>   tcgen05.mma + TMEM, one CTA per (2 envs, agent-net): recurrence (both directions),
+ *                              attention and GRUCell in ONE launch                                         (default)
+ *   1  gat_recur_kernel (mma.sync m16n8k16, one CTA per (env, agent-net, direction)) + gat_attend_kernel  (cross-check)
+ *   2  gat_tc5_kernel<recurrence only> + gat_attend_kernel (also what 0 falls back to when n_slots > 57)
+ * Same inputs and outputs.  Process-wide; the default can also be chosen with the environment variable IPLAN_GAT_IMPL
+ * read at the first call. */
 int iplan_gat_set_impl(int impl);
 int iplan_gat_get_impl(void);
+/* Timing experiments only (IPLAN_GAT_DBG=4): clock64() stamps of one CTA's phase boundaries in the last fused launch. */
+int iplan_gat_debug_clocks(long long* out32);
 
 /* iplan_gat_step with optional cudaEvent_t handles (NULL = skip) recorded on `stream` before the recurrence kernel,
  * between the two kernels and after the attention kernel: per-kernel timing of the dominant kernel inside a running

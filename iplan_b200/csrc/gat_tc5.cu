@@ -86,6 +86,14 @@ __device__ __forceinline__ void tc5_wait_ld8(float (&a)[8]) {
 
 // DBG (timing experiments only, results are garbage): bit 0 = tile 1 (reverse direction) does nothing; bit 1 = the MUFU
 // instructions of the gates are replaced by FMA-pipe stand-ins
+// bit 2 = one CTA stamps clock64() at its phase boundaries into g5_clk (read back with iplan_gat_debug_clocks)
+__device__ long long g5_clk[32];
+#define G5_STAMP(k)                                                                             \
+    do {                                                                                        \
+        if constexpr ((DBG & 4) != 0) {                                                         \
+            if (blockIdx.x == 3 && blockIdx.y == 0 && tid == 0) g5_clk[k] = clock64();         \
+        }                                                                                       \
+    } while (0)
 template <int DBG, bool FUSED>
 __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
     extern __shared__ unsigned char g5_raw[];
@@ -120,6 +128,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         mbar_init(att_bar, 1);
         mbar_init_fence();
     }
+    G5_STAMP(0);
     if (warp == 0) tc5_alloc<G5_TMEM_COLS>(tmem_slot);
 
     // ---- inputs of this thread's row (threads 0..127): x = [history | behaviour latent] ----------
@@ -189,6 +198,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
     tc5_fence_before();
     __syncthreads();
     tc5_fence_after();
+    G5_STAMP(1);                                                  // constants + weight operand tiles staged
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -221,6 +231,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
     }
     fence_proxy_async();
     __syncthreads();
+    G5_STAMP(2);                                                  // enc tile written
 
     constexpr uint32_t IDESC_IH = tc5_idesc(128, 2 * G3), IDESC_HH = tc5_idesc(128, G3);
     constexpr int PQ_COL = 128;                               // [P | Q] fwd at TMEM columns 128..319, rev at 320..511
@@ -253,6 +264,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
 
         mbar_wait(pro_bar, 0);
         tc5_fence_after();
+        G5_STAMP(3);                                              // [P | Q] products complete
         // neighbour part: this row's Q (+ the gate biases: every step adds exactly one Q row) -> the table (W_ih tiles are dead)
 #pragma unroll
         for (int g = 0; g < 3; ++g)
@@ -282,6 +294,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         tc5_fence_before();
         __syncthreads();                                        // Q tables complete, TMEM Q columns free
         tc5_fence_after();
+        G5_STAMP(4);
         // the tile's product h . W_hh^T: issued by one lane once the tile's eight warps have written h (named barrier)
         const bool issuer = (warp & 3) == 0 && hh == 0 && lane == 0;
         const uint64_t mma_a = tc5_smem_desc(a_tile), mma_b = tc5_smem_desc(base + Y.bhh + t * G5_BHH_BYTES);
@@ -401,8 +414,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         const uint32_t row_base = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u, rx = (uint32_t)(row & 7);
 
         tc5_fence_before();
+        G5_STAMP(5);                           // this thread's recurrence done
         __syncthreads();                       // both recurrences done: dl tables complete, operand tiles and TMEM columns free
         tc5_fence_after();
+        G5_STAMP(6);
         // ---- stage W_q|k|v, GRUCell W_hh, GRUCell W_ih as operand tiles; h_prev as an operand tile; biases -----------
         for (int task = tid; task < 3 * G3 * 4; task += G5_THREADS) {
             const int sel = task / (G3 * 4), rr = task - sel * (G3 * 4), wr = rr >> 2, ch = rr & 3;
@@ -433,6 +448,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         tc5_fence_before();
         __syncthreads();
         tc5_fence_after();
+        G5_STAMP(7);                           // attention operand tiles staged
         constexpr int QKV_COL = 0, GH_COL = G3, GI_COL = 2 * G3;
         auto product = [&](uint32_t col, uint32_t ta, uint32_t tb) {          // D[128 x 96] = A . B^T, fp32-class (3 passes)
             const uint64_t da = tc5_smem_desc(ta), db = tc5_smem_desc(tb);
@@ -451,6 +467,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         }
         mbar_wait(att_bar, 0);
         tc5_fence_after();
+        G5_STAMP(8);                           // q|k|v and gh products complete
         float qv[H];
 #pragma unroll
         for (int c8 = 0; c8 < 4; ++c8) {
@@ -475,6 +492,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
             vd[1] = make_float4(fmaxf(vv[4] + vb[4], 0.f), fmaxf(vv[5] + vb[5], 0.f), fmaxf(vv[6] + vb[6], 0.f), fmaxf(vv[7] + vb[7], 0.f));
         }
         __syncthreads();
+        G5_STAMP(9);                           // k / v tables written
         // ---- scores, hard gate, soft-max over the neighbours (:107-129); this thread's neighbours j = part + 4 u --------
         constexpr int JU = IPLAN_MAX_SLOTS / 4;
         float sc[JU], hd[JU];
@@ -514,12 +532,14 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         }
         s_pm[part * 128 + row] = mx;
         __syncthreads();
+        G5_STAMP(10);                          // scores + hard gates
         mx = fmaxf(fmaxf(s_pm[row], s_pm[128 + row]), fmaxf(s_pm[256 + row], s_pm[384 + row]));
         float psum = 0.0f;
 #pragma unroll
         for (int u = 0; u < JU; ++u) { sc[u] = expf(sc[u] - mx); psum += sc[u]; }     // exp(-inf) = 0 for self / padding
         s_ps[part * 128 + row] = psum;
         __syncthreads();
+        G5_STAMP(11);
         const float den = ((s_ps[row] + s_ps[128 + row]) + s_ps[256 + row]) + s_ps[384 + row];
         // ---- x_i = sum_j soft_ij hard_ij v_j (no renormalisation, :132): this part's neighbours, then the four parts -----
         float xa[H];
@@ -544,6 +564,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
             for (int c = 0; c < H; ++c) x_part[((part - 1) * H + c) * 128 + row] = xa[c];
         }
         __syncthreads();
+        G5_STAMP(12);                          // aggregation partials
         if (!part) {
             uint32_t hi[4], lo[4];
 #pragma unroll
@@ -570,8 +591,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
             product(GI_COL, t_hx, t_wih);                                      // GRUCell: x W_ih^T                        (:140)
             tc5_commit(att_bar);
         }
+        G5_STAMP(13);                          // x operand tile written, product issued
         mbar_wait(att_bar, 1);
         tc5_fence_after();
+        G5_STAMP(14);
         {
             float gir[8], giz[8], gin[8], ghr[8], ghz[8], ghn[8];
             tc5_ld8_nowait(tlane + GI_COL + 8 * part, gir);
@@ -596,6 +619,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
     }
     tc5_fence_before();
     __syncthreads();
+    G5_STAMP(15);
     if (warp == 0) {
         tc5_fence_after();
         tc5_dealloc<G5_TMEM_COLS>(tmem_base);
@@ -615,15 +639,17 @@ int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, c
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e != cudaSuccess) { set_error("gat_step: tcgen05 kernel smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
     if (fused && g5_layout(a.n_slots, true).total > G5_SMEM_MAX) fused = false;
-    if (dbg) fused = false;
+    if (dbg & 3) fused = false;
     const G5Layout Y = g5_layout(a.n_slots, fused);
     if (Y.total > G5_SMEM_MAX) { set_error("gat_step: n_slots %d needs %u bytes of shared memory", a.n_slots, Y.total); return -1; }
     const dim3 grid((a.n_envs + 1) / 2, n_agents);
-    if (fused) gat_tc5_kernel<0, true><<<grid, G5_THREADS, Y.total, st>>>(a);
+    if (fused && dbg == 4) gat_tc5_kernel<4, true><<<grid, G5_THREADS, Y.total, st>>>(a);
+    else if (fused) gat_tc5_kernel<0, true><<<grid, G5_THREADS, Y.total, st>>>(a);
     else if (dbg == 1) gat_tc5_kernel<1, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     else if (dbg == 2) gat_tc5_kernel<2, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     else gat_tc5_kernel<0, false><<<grid, G5_THREADS, Y.total, st>>>(a);
@@ -633,3 +659,10 @@ int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, c
 }
 
 }  // namespace iplan
+
+// timing experiments (IPLAN_GAT_DBG=4): the phase-boundary clock stamps of one CTA of the last fused launch
+extern "C" int iplan_gat_debug_clocks(long long* out32) {
+    const cudaError_t e = cudaMemcpyFromSymbol(out32, iplan::g5_clk, sizeof(long long) * 32);
+    if (e != cudaSuccess) { iplan::set_error("gat_debug_clocks: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
