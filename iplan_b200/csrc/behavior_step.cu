@@ -133,17 +133,63 @@ __global__ void __launch_bounds__(BEH_THREADS, 2) behavior_step_kernel(BehArgs a
     const bool ok0 = nd0 < total_nodes, ok1 = nd1 < total_nodes;
     const int c0n = ok0 ? nd0 : 0, c1n = ok1 ? nd1 : 0;
     const int b0 = c0n / N, n0 = c0n - b0 * N, b1 = c1n / N, n1 = c1n - b1 * N;
-    for (int r = 0; r < NODES_W; ++r) {                      // stage the 16 windows (coalesced per node)
-        const int nd = min(node_base + r, total_nodes - 1);
-        const int bb = nd / N, nn = nd - bb * N;
-        const float* src = a.window.ptr + ag * a.window.stride_agent + bb * a.window.stride_env + nn * a.window.stride_slot;
-        if (a.win_step == 0) {
-            for (int q = lane; q < Wn * o; q += 32) S.win[warp][r][q] = src[q];
-        } else {                                               // rows live `win_step` apart (e.g. the episode store's time axis)
-            for (int q = lane; q < Wn * o; q += 32) {
-                const int w = q / o, c = q - w * o;
-                S.win[warp][r][q] = w >= a.win_pad ? src[(int64_t)(w - a.win_pad) * a.win_step + c] : 0.0f;
+    // stage the 16 windows.  All loads of a batch are issued before the first store (one L2 round trip per batch: the
+    // kernel used to spend 40 % of its time in a load -> store -> next load chain here)
+    if (a.win_step != 0 && o <= 8) {
+        // rows live `win_step` apart (the episode store's time axis): lane -> (node r, window row w) pairs, o floats each
+        constexpr int PB = 5, OM = 8;
+        const int pairs = NODES_W * Wn;
+        for (int p0 = 0; p0 < pairs; p0 += 32 * PB) {
+            float v[PB][OM];
+            int dsto[PB];
+#pragma unroll
+            for (int k = 0; k < PB; ++k) {
+                const int pp = p0 + 32 * k + lane;
+                const bool on = pp < pairs;
+                const int r = on ? pp / Wn : 0, w = on ? pp - r * Wn : 0;
+                const int nd = min(node_base + r, total_nodes - 1);
+                const int bb = nd / N, nn = nd - bb * N;
+                const bool ld = on && w >= a.win_pad;
+                const float* src = a.window.ptr + ag * a.window.stride_agent + bb * a.window.stride_env + nn * a.window.stride_slot
+                                   + (int64_t)(ld ? w - a.win_pad : 0) * a.win_step;
+                dsto[k] = on ? r * WIN_MAX + w * o : -1;
+#pragma unroll
+                for (int c = 0; c < OM; ++c) v[k][c] = (ld && c < o) ? src[c] : 0.0f;
             }
+#pragma unroll
+            for (int k = 0; k < PB; ++k) {
+                if (dsto[k] >= 0) {
+                    float* dst = &S.win[warp][0][0] + dsto[k];
+#pragma unroll
+                    for (int c = 0; c < OM; ++c)
+                        if (c < o) dst[c] = v[k][c];
+                }
+            }
+        }
+    } else {
+        for (int r0 = 0; r0 < NODES_W; r0 += 8) {
+            float v[8][2];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int nd = min(node_base + r0 + k, total_nodes - 1);
+                const int bb = nd / N, nn = nd - bb * N;
+                const float* src = a.window.ptr + ag * a.window.stride_agent + bb * a.window.stride_env + nn * a.window.stride_slot;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int q = lane + 32 * u;
+                    float x = 0.0f;
+                    if (q < Wn * o) {
+                        if (a.win_step == 0) x = src[q];
+                        else { const int w = q / o, c = q - w * o; x = w >= a.win_pad ? src[(int64_t)(w - a.win_pad) * a.win_step + c] : 0.0f; }
+                    }
+                    v[k][u] = x;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    if (lane + 32 * u < Wn * o) S.win[warp][r0 + k][lane + 32 * u] = v[k][u];
         }
     }
     float h[4][4];

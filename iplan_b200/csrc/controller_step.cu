@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -34,6 +35,7 @@ struct CtrlArgs {
     int32_t* actions; float* logp; float* values; float* logits;
     float* next_onehot; float* this_onehot;
     int n_envs, feat_dim, feat_ld, n_actions;
+    int allow_vec;          // 0: always the scalar staging path (timing experiments: IPLAN_CTRL_VEC=0)
 };
 
 // y[k] = b[k] + sum_j W[k][j] * x[j]  for one output row k (64 inputs, x in shared memory)
@@ -159,25 +161,105 @@ __global__ void __launch_bounds__(CTRL_THREADS, 1) controller_step_kernel(CtrlAr
     float* s_gi = reinterpret_cast<float*>(smem_raw);    // [2*ROWS][192] GRU input projections (aliases s_yh/s_yl: dead after fc1)
     float* s_gh = s_gi + 2 * CTRL_ROWS * 3 * R;          // [2*ROWS][192] GRU hidden projections
 
-    // ---- LayerNorm statistics over the F input features (two passes, rows stay in L1/L2) -------
-    for (int r = warp; r < CTRL_ROWS; r += CTRL_WARPS) {
-        const int b = min(b0 + r, a.n_envs - 1);
-        const float* src = a.feat + ag * a.feat_sa + b * a.feat_se;
-        float s = 0.0f;
-        for (int f = lane; f < F; f += 32) s += src[f];
-        const float mean = warp_sum(s) / (float)F;
-        float v = 0.0f;
-        for (int f = lane; f < F; f += 32) { const float d = src[f] - mean; v = fmaf(d, d, v); }
-        const float var = warp_sum(v) / (float)F;
-        if (lane == 0) { s_stat[2 * r] = mean; s_stat[2 * r + 1] = 1.0f / sqrtf(var + LN_EPS); }
+    // ---- LayerNorm statistics over the F input features ------------------------------------------------
+    // Vector path (rows 16-byte aligned, as in the packed episode store): a warp owns rows warp, warp + 8, ...; a row is read
+    // with ONE batch of float4 loads per net (all in flight together), statistics from registers.  The scalar path keeps two
+    // passes over L1/L2.
+    constexpr int V4 = 20, RPW = (CTRL_ROWS + CTRL_WARPS - 1) / CTRL_WARPS;
+    const bool vec = a.allow_vec && (reinterpret_cast<uintptr_t>(a.feat) & 15) == 0 && (a.feat_sa & 3) == 0 && (a.feat_se & 3) == 0 &&
+                     a.feat_ld >= ((F + 3) & ~3) && K16 <= 128 * V4 && 2 * K16 <= 4 * CTRL_ROWS * TAP &&
+                     ((reinterpret_cast<uintptr_t>(a.actor) | reinterpret_cast<uintptr_t>(a.critic)) & 15) == 0 &&
+                     (a.actor_stride & 3) == 0 && (a.critic_stride & 3) == 0;
+    float mean_r[RPW], rstd_r[RPW];
+#pragma unroll
+    for (int k = 0; k < RPW; ++k) { mean_r[k] = 0.0f; rstd_r[k] = 0.0f; }
+    if (!vec) {
+        for (int r = warp; r < CTRL_ROWS; r += CTRL_WARPS) {
+            const int b = min(b0 + r, a.n_envs - 1);
+            const float* src = a.feat + ag * a.feat_sa + b * a.feat_se;
+            float s = 0.0f;
+            for (int f = lane; f < F; f += 32) s += src[f];
+            const float mean = warp_sum(s) / (float)F;
+            float v = 0.0f;
+            for (int f = lane; f < F; f += 32) { const float d = src[f] - mean; v = fmaf(d, d, v); }
+            const float var = warp_sum(v) / (float)F;
+            if (lane == 0) { s_stat[2 * r] = mean; s_stat[2 * r + 1] = 1.0f / sqrtf(var + LN_EPS); }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-
     // ---- fc1 for both nets on the tensor cores: [16 rows x K] . W1^T, one 8-output n-tile per warp
     const int gq = lane >> 2, tq = lane & 3;
     for (int net = 0; net < 2; ++net) {
         const float* P = net == 0 ? a.actor + (int64_t)ag * a.actor_stride : a.critic + (int64_t)ag * a.critic_stride;
         const TrunkLayout L = trunk_layout(F, net == 0 ? a.n_actions : 1, net == 1);
+        if (vec) {                                               // y = LN(x) as f16 hi + lo, a row per warp pass
+            // this net's LayerNorm gamma / beta: staged once in shared memory (the tail's activation rows, unused until both
+            // fc1 products are done), so that the row passes below wait for global memory once per row, not once per float4
+            float4* g4 = reinterpret_cast<float4*>(s_act);
+            float4* bt4 = g4 + K16 / 4;
+            {
+                const float4* gg4 = reinterpret_cast<const float4*>(P + L.ln0_w);
+                const float4* gb4 = reinterpret_cast<const float4*>(P + L.ln0_b);
+                const int n4 = (F + 3) >> 2;
+                for (int i = tid; i < n4; i += CTRL_THREADS) { g4[i] = __ldg(gg4 + i); bt4[i] = __ldg(gb4 + i); }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < RPW; ++k) {
+                const int r = warp + CTRL_WARPS * k;
+                if (r < CTRL_ROWS) {
+                    const int b = min(b0 + r, a.n_envs - 1);
+                    const float4* src4 = reinterpret_cast<const float4*>(a.feat + ag * a.feat_sa + b * a.feat_se);
+                    float4 xv[V4];
+#pragma unroll
+                    for (int j = 0; j < V4; ++j) {
+                        const int f = 4 * (lane + 32 * j);
+                        xv[j] = f < F ? __ldg(src4 + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (f + 1 >= F) xv[j].y = 0.0f;                 // the row's last float4 may run past F
+                        if (f + 2 >= F) xv[j].z = 0.0f;
+                        if (f + 3 >= F) xv[j].w = 0.0f;
+                    }
+                    if (net == 0) {
+                        float sm = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < V4; ++j) sm += (xv[j].x + xv[j].y) + (xv[j].z + xv[j].w);
+                        const float mean = warp_sum(sm) / (float)F;
+                        float vs = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < V4; ++j) {
+                            const int f = 4 * (lane + 32 * j);
+                            const float d0 = xv[j].x - mean, d1 = xv[j].y - mean, d2 = xv[j].z - mean, d3 = xv[j].w - mean;
+                            if (f < F) vs = fmaf(d0, d0, vs);
+                            if (f + 1 < F) vs = fmaf(d1, d1, vs);
+                            if (f + 2 < F) vs = fmaf(d2, d2, vs);
+                            if (f + 3 < F) vs = fmaf(d3, d3, vs);
+                        }
+                        mean_r[k] = mean;
+                        rstd_r[k] = 1.0f / sqrtf(warp_sum(vs) / (float)F + LN_EPS);
+                    }
+                    const float mean = mean_r[k], rstd = rstd_r[k];
+#pragma unroll
+                    for (int j = 0; j < V4; ++j) {
+                        const int f = 4 * (lane + 32 * j);
+                        if (f < K16) {
+                            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (f < F) {
+                                const float4 g = g4[lane + 32 * j], bt = bt4[lane + 32 * j];
+                                y.x = (xv[j].x - mean) * rstd * g.x + bt.x;
+                                y.y = f + 1 < F ? (xv[j].y - mean) * rstd * g.y + bt.y : 0.0f;
+                                y.z = f + 2 < F ? (xv[j].z - mean) * rstd * g.z + bt.z : 0.0f;
+                                y.w = f + 3 < F ? (xv[j].w - mean) * rstd * g.w + bt.w : 0.0f;
+                            }
+                            uint32_t h0, l0, h1, l1;
+                            csplit(y.x, y.y, h0, l0);
+                            csplit(y.z, y.w, h1, l1);
+                            *reinterpret_cast<uint2*>(s_yh + r * LDH + f) = make_uint2(h0, h1);
+                            *reinterpret_cast<uint2*>(s_yl + r * LDH + f) = make_uint2(l0, l1);
+                        }
+                    }
+                }
+            }
+        } else
         for (int f = tid; f < K16; f += CTRL_THREADS) {          // y = LN(x) as f16 hi + lo
             const float g = f < F ? P[L.ln0_w + f] : 0.0f;
             const float bt = f < F ? P[L.ln0_b + f] : 0.0f;
@@ -420,6 +502,8 @@ extern "C" int iplan_controller_step(const float* actor_params, int64_t actor_st
     a.actions = actions; a.logp = logp; a.values = values; a.logits = logits;
     a.next_onehot = next_onehot; a.this_onehot = this_onehot;
     a.n_envs = n_envs; a.feat_dim = feat_dim; a.feat_ld = (feat_dim + 3) & ~3; a.n_actions = n_actions;
+    static const int allow_vec = getenv("IPLAN_CTRL_VEC") ? atoi(getenv("IPLAN_CTRL_VEC")) : 1;
+    a.allow_vec = allow_vec;
     const size_t ldh = ((feat_dim + 15) & ~15) + 8;
     const size_t stage = std::max((size_t)2 * CTRL_ROWS * ldh * 2, (size_t)4 * CTRL_ROWS * 3 * R * sizeof(float));
     const size_t smem = stage + ((size_t)2 * CTRL_ROWS * R + 4 * CTRL_ROWS * TAP + 2 * CTRL_ROWS) * sizeof(float);

@@ -401,11 +401,14 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
     const float db = W[L.he_b + 1] - W[L.he_b + 0];
     for (int i = warp; i < N; i += GAT_WARPS) {
         float sc[2], hd[2];
-        uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
-        if (!a.gumbel) {
-            const int64_t key = (((int64_t)ag * a.n_envs + b) * N + i) * 32 + lane;
-            rnd = philox4x32(make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.counter, (uint32_t)(a.counter >> 32)),
-                             make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+        uint4 rnd[2] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+        if (!a.gumbel) {                                                  // Philox key (ego, j >> 2), word j & 3 (as gat_tc5_kernel)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int64_t key = (((int64_t)ag * a.n_envs + b) * N + i) * 16 + ((lane + 32 * u) >> 2);
+                rnd[u] = philox4x32(make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.counter, (uint32_t)(a.counter >> 32)),
+                                    make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+            }
         }
         float* wrow = s_w + i * WP;
 #pragma unroll
@@ -414,18 +417,18 @@ __global__ void __launch_bounds__(GAT_THREADS, 2) gat_attend_kernel(GatArgs a) {
             sc[u] = -INFINITY; hd[u] = 0.0f;
             if (j < N && j != i) {
                 const int s = j < i ? j : j - 1;                         // position of neighbour j in ego i's sequence
-                sc[u] = wrow[j] / 5.656854249492381f;                    // np.sqrt(attention_dim), :126
+                sc[u] = wrow[j] * 0.17677669529663687f;                  // / np.sqrt(attention_dim), :126
                 float noise;
                 const int64_t edge = (((int64_t)ag * a.n_envs + b) * N + i) * NM1 + s;
                 if (a.gumbel) {
                     noise = a.gumbel[2 * edge + 1] - a.gumbel[2 * edge];
                 } else {
-                    // one Philox call per (ego, lane) serves both of the lane's slots
-                    const float uu = u01(u == 0 ? rnd.x : rnd.y);
+                    const int wsel = lane & 3;
+                    const float uu = u01(wsel == 0 ? rnd[u].x : (wsel == 1 ? rnd[u].y : (wsel == 2 ? rnd[u].z : rnd[u].w)));
                     noise = __logf(uu) - __logf(1.0f - uu);  // Gumbel - Gumbel ~ Logistic(0,1)
                 }
                 const float dlog = s_dl[i * NM1 + s] + db;
-                hd[u] = sigmoidf_acc((dlog + noise) * a.inv_tau);
+                hd[u] = __fdividef(1.0f, 1.0f + expf(-(dlog + noise) * a.inv_tau));
                 if (a.dbg_hard) a.dbg_hard[edge] = hd[u];
             }
         }

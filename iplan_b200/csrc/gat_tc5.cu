@@ -131,13 +131,13 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
     G5_STAMP(0);
     if (warp == 0) tc5_alloc<G5_TMEM_COLS>(tmem_slot);
 
-    // ---- inputs of this thread's row (threads 0..127): x = [history | behaviour latent] ----------
+    // ---- inputs of this thread's row (row = tid & 127; the four threads of a row each encode 8 of its 32 units) ----------
     float x[IN_MAX];
 #pragma unroll
     for (int k = 0; k < IN_MAX; ++k) x[k] = 0.0f;
     bool row_ok = false;
-    if (tid < 128) {
-        const int e = tid >> 6, i = tid & 63, b = b0 + e;
+    {
+        const int xr = tid & 127, e = xr >> 6, i = xr & 63, b = b0 + e;
         row_ok = i < N && b < a.n_envs;
         if (row_ok) {
             const float* hist = a.hist.ptr + ag * a.hist.stride_agent + b * a.hist.stride_env + i * a.hist.stride_slot;
@@ -168,32 +168,53 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
     // ---- operand tiles of the weights: f16 hi | lo, gate-activation scale folded in -----------------
     // one task = 8 consecutive k of one row: hi chunk `ch`, lo chunk `4 + ch`
     constexpr int HH_TASKS = 2 * G3 * 4, IH_TASKS = 2 * 2 * G3 * 4;
-    for (int task = tid; task < HH_TASKS + IH_TASKS; task += G5_THREADS) {
-        const float* src;
-        uint32_t tile;
-        int row, ch, gate;
-        if (task < HH_TASKS) {
-            const int d = task / (G3 * 4), rr = task - d * (G3 * 4);
-            row = rr >> 2; ch = rr & 3; gate = row;
-            src = W + (d ? L.whh_r : L.whh_f) + row * H + ch * 8;
-            tile = base + Y.bhh + d * G5_BHH_BYTES;
-        } else {
-            const int tt = task - HH_TASKS, d = tt / (2 * G3 * 4), rr = tt - d * (2 * G3 * 4);
-            row = rr >> 2; ch = rr & 3;
-            const int part = row / G3;                      // 0: ego columns (-> P), 1: neighbour columns (-> Q)
-            gate = row - part * G3;
-            src = W + (d ? L.wih_r : L.wih_f) + gate * 2 * H + part * H + ch * 8;
-            tile = base + Y.q + d * G5_BIH_BYTES;
+    constexpr int W_ITERS = (HH_TASKS + IH_TASKS + G5_THREADS - 1) / G5_THREADS;
+    {
+        // all of a thread's loads are issued before its first store: one L2 round trip instead of one per task
+        float4 w0[W_ITERS], w1[W_ITERS];
+        uint32_t dst[W_ITERS];
+        float ksc[W_ITERS];
+#pragma unroll
+        for (int it = 0; it < W_ITERS; ++it) {
+            const int task = tid + it * G5_THREADS;
+            dst[it] = 0u; ksc[it] = 0.0f;
+            w0[it] = w1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (task < HH_TASKS + IH_TASKS) {
+                const float* src;
+                uint32_t tile;
+                int row, ch, gate;
+                if (task < HH_TASKS) {
+                    const int d = task / (G3 * 4), rr = task - d * (G3 * 4);
+                    row = rr >> 2; ch = rr & 3; gate = row;
+                    src = W + (d ? L.whh_r : L.whh_f) + row * H + ch * 8;
+                    tile = base + Y.bhh + d * G5_BHH_BYTES;
+                } else {
+                    const int tt = task - HH_TASKS, d = tt / (2 * G3 * 4), rr = tt - d * (2 * G3 * 4);
+                    row = rr >> 2; ch = rr & 3;
+                    const int part = row / G3;                      // 0: ego columns (-> P), 1: neighbour columns (-> Q)
+                    gate = row - part * G3;
+                    src = W + (d ? L.wih_r : L.wih_f) + gate * 2 * H + part * H + ch * 8;
+                    tile = base + Y.q + d * G5_BIH_BYTES;
+                }
+                ksc[it] = gate < 2 * H ? K_RZ : K_N;
+                w0[it] = *reinterpret_cast<const float4*>(src);
+                w1[it] = *reinterpret_cast<const float4*>(src + 4);
+                dst[it] = tile + swz128(row, ch);               // hi chunk `ch`; the lo chunk `4 + ch` is 64 bytes further (xor of bit 2 of the chunk index)
+            }
         }
-        const float ks = gate < 2 * H ? K_RZ : K_N;
-        const float4 w0 = *reinterpret_cast<const float4*>(src), w1 = *reinterpret_cast<const float4*>(src + 4);
-        uint32_t hi[4], lo[4];
-        split_f16(ks * w0.x, ks * w0.y, hi[0], lo[0]);
-        split_f16(ks * w0.z, ks * w0.w, hi[1], lo[1]);
-        split_f16(ks * w1.x, ks * w1.y, hi[2], lo[2]);
-        split_f16(ks * w1.z, ks * w1.w, hi[3], lo[3]);
-        sts128(tile + swz128(row, ch), hi[0], hi[1], hi[2], hi[3]);
-        sts128(tile + swz128(row, 4 + ch), lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+        for (int it = 0; it < W_ITERS; ++it) {
+            if (dst[it]) {
+                const float ks = ksc[it];
+                uint32_t hi[4], lo[4];
+                split_f16(ks * w0[it].x, ks * w0[it].y, hi[0], lo[0]);
+                split_f16(ks * w0[it].z, ks * w0[it].w, hi[1], lo[1]);
+                split_f16(ks * w1[it].x, ks * w1[it].y, hi[2], lo[2]);
+                split_f16(ks * w1[it].z, ks * w1[it].w, hi[3], lo[3]);
+                sts128(dst[it], hi[0], hi[1], hi[2], hi[3]);
+                sts128(dst[it] ^ 64u, lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
     }
     tc5_fence_before();
     __syncthreads();
@@ -203,30 +224,28 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     // ---- enc = ReLU(W_e x + b_e) (:50) -> operand tile 0 (shared by both directions' [P | Q] products) ----
-    if (tid < 128) {
+    {
         const uint32_t tile = base + Y.a;
+        const int xr = tid & 127, ch = tid >> 7;                   // 8 units of the row: operand chunk `ch` (hi) and `4 + ch` (lo)
+        uint32_t hi[4], lo[4];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-            uint32_t hi[4], lo[4];
+        for (int p = 0; p < 4; ++p) {
+            float v[2];
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                float v[2];
+            for (int q = 0; q < 2; ++q) {
+                const int c = 8 * ch + 2 * p + q;
+                float acc = s_be[c];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int c = 8 * ch + 2 * p + q;
-                    float acc = s_be[c];
-#pragma unroll
-                    for (int k = 0; k < IN_MAX; ++k) acc = fmaf(s_we[c * IN_MAX + k], x[k], acc);
-                    v[q] = row_ok ? fmaxf(acc, 0.0f) : 0.0f;
-                }
-                split_f16(v[0], v[1], hi[p], lo[p]);
+                for (int k = 0; k < IN_MAX; ++k) acc = fmaf(s_we[c * IN_MAX + k], x[k], acc);
+                v[q] = row_ok ? fmaxf(acc, 0.0f) : 0.0f;
             }
-            sts128(tile + swz128(tid, ch), hi[0], hi[1], hi[2], hi[3]);
-            sts128(tile + swz128(tid, 4 + ch), lo[0], lo[1], lo[2], lo[3]);
-            if constexpr (FUSED) {                                // the attention phase needs enc again; the h tile overwrites this one
-                sts128(base + Y.enc + swz128(tid, ch), hi[0], hi[1], hi[2], hi[3]);
-                sts128(base + Y.enc + swz128(tid, 4 + ch), lo[0], lo[1], lo[2], lo[3]);
-            }
+            split_f16(v[0], v[1], hi[p], lo[p]);
+        }
+        sts128(tile + swz128(xr, ch), hi[0], hi[1], hi[2], hi[3]);
+        sts128(tile + swz128(xr, 4 + ch), lo[0], lo[1], lo[2], lo[3]);
+        if constexpr (FUSED) {                                    // the attention phase needs enc again; the h tile overwrites this one
+            sts128(base + Y.enc + swz128(xr, ch), hi[0], hi[1], hi[2], hi[3]);
+            sts128(base + Y.enc + swz128(xr, 4 + ch), lo[0], lo[1], lo[2], lo[3]);
         }
     }
     fence_proxy_async();
@@ -419,23 +438,41 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         tc5_fence_after();
         G5_STAMP(6);
         // ---- stage W_q|k|v, GRUCell W_hh, GRUCell W_ih as operand tiles; h_prev as an operand tile; biases -----------
-        for (int task = tid; task < 3 * G3 * 4; task += G5_THREADS) {
-            const int sel = task / (G3 * 4), rr = task - sel * (G3 * 4), wr = rr >> 2, ch = rr & 3;
-            const float* src = W + (sel == 0 ? L.q_w : (sel == 1 ? L.c_whh : L.c_wih)) + wr * H + ch * 8;
-            const uint32_t tile = sel == 0 ? t_qkv : (sel == 1 ? t_whh : t_wih);
-            const float4 w0 = *reinterpret_cast<const float4*>(src), w1 = *reinterpret_cast<const float4*>(src + 4);
-            uint32_t hi[4], lo[4];
-            split_f16(w0.x, w0.y, hi[0], lo[0]);
-            split_f16(w0.z, w0.w, hi[1], lo[1]);
-            split_f16(w1.x, w1.y, hi[2], lo[2]);
-            split_f16(w1.z, w1.w, hi[3], lo[3]);
-            sts128(tile + swz128(wr, ch), hi[0], hi[1], hi[2], hi[3]);
-            sts128(tile + swz128(wr, 4 + ch), lo[0], lo[1], lo[2], lo[3]);
+        constexpr int A_ITERS = (3 * G3 * 4 + G5_THREADS - 1) / G5_THREADS;
+        {
+            float4 w0[A_ITERS], w1[A_ITERS];
+            uint32_t dst[A_ITERS];
+#pragma unroll
+            for (int it = 0; it < A_ITERS; ++it) {
+                const int task = tid + it * G5_THREADS;
+                dst[it] = 0u;
+                w0[it] = w1[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (task < 3 * G3 * 4) {
+                    const int sel = task / (G3 * 4), rr = task - sel * (G3 * 4), wr = rr >> 2, ch = rr & 3;
+                    const float* src = W + (sel == 0 ? L.q_w : (sel == 1 ? L.c_whh : L.c_wih)) + wr * H + ch * 8;
+                    w0[it] = *reinterpret_cast<const float4*>(src);
+                    w1[it] = *reinterpret_cast<const float4*>(src + 4);
+                    dst[it] = (sel == 0 ? t_qkv : (sel == 1 ? t_whh : t_wih)) + swz128(wr, ch);
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < A_ITERS; ++it) {
+                if (dst[it]) {
+                    uint32_t hi[4], lo[4];
+                    split_f16(w0[it].x, w0[it].y, hi[0], lo[0]);
+                    split_f16(w0[it].z, w0[it].w, hi[1], lo[1]);
+                    split_f16(w1[it].x, w1[it].y, hi[2], lo[2]);
+                    split_f16(w1[it].z, w1[it].w, hi[3], lo[3]);
+                    sts128(dst[it], hi[0], hi[1], hi[2], hi[3]);
+                    sts128(dst[it] ^ 64u, lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
         }
+        const float he_db = W[L.he_b + 1] - W[L.he_b + 0];
         float hp[8];                           // h_prev of this thread's 8 units (fp32, kept for the GRUCell's last line)
         {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) hp[q] = ok ? hprev[8 * part + q] : 0.0f;
+            for (int q = 0; q < 8; ++q) hp[q] = ok ? hprev[8 * part + q] : 0.0f;      // (rows of the packed store are only 4-byte aligned)
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) split_f16(hp[2 * q], hp[2 * q + 1], hi[q], lo[q]);
@@ -494,40 +531,51 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         __syncthreads();
         G5_STAMP(9);                           // k / v tables written
         // ---- scores, hard gate, soft-max over the neighbours (:107-129); this thread's neighbours j = part + 4 u --------
-        constexpr int JU = IPLAN_MAX_SLOTS / 4;
+        // neighbours of a thread: the four groups g of four consecutive slots j = 16 g + 4 part + w (one Philox call per group)
+        constexpr int JG = IPLAN_MAX_SLOTS / 16, JU = 4 * JG;
         float sc[JU], hd[JU];
-        const float db = W[L.he_b + 1] - W[L.he_b + 0];
+        const float db = he_db;
+        const int64_t ego = ((int64_t)ag * a.n_envs + (ok ? b : 0)) * N + i;
         float mx = -INFINITY;
 #pragma unroll
-        for (int u = 0; u < JU; ++u) {
-            const int j = part + 4 * u;
-            sc[u] = -INFINITY; hd[u] = 0.0f;
-            if (j < N && j != i && i < N) {
-                const float4* kr = reinterpret_cast<const float4*>(k_s + (e * 64 + j) * G5_KP);
-                float d = 0.0f;
+        for (int g = 0; g < JG; ++g) {
+            const int j0 = 16 * g + 4 * part;
+            uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+            if (!a.gumbel && j0 < N && i < N) {                                // same Philox stream as gat_attend_kernel: key (ego, j >> 2), word j & 3
+                const int64_t key = ego * 16 + (j0 >> 2);
+                rnd = philox4x32(make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.counter, (uint32_t)(a.counter >> 32)),
+                                 make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
+            }
 #pragma unroll
-                for (int c4 = 0; c4 < H / 4; ++c4) {
-                    const float4 kq = kr[c4];
-                    d = fmaf(qv[4 * c4], kq.x, d); d = fmaf(qv[4 * c4 + 1], kq.y, d);
-                    d = fmaf(qv[4 * c4 + 2], kq.z, d); d = fmaf(qv[4 * c4 + 3], kq.w, d);
+            for (int w = 0; w < 4; ++w) {
+                const int u = 4 * g + w, j = j0 + w;
+                sc[u] = -INFINITY; hd[u] = 0.0f;
+                if (j < N && j != i && i < N) {
+                    const float4* kr = reinterpret_cast<const float4*>(k_s + (e * 64 + j) * G5_KP);
+                    float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+                    for (int c4 = 0; c4 < H / 4; c4 += 2) {
+                        const float4 ka = kr[c4], kb = kr[c4 + 1];
+                        d0 = fmaf(qv[4 * c4], ka.x, d0); d0 = fmaf(qv[4 * c4 + 1], ka.y, d0);
+                        d0 = fmaf(qv[4 * c4 + 2], ka.z, d0); d0 = fmaf(qv[4 * c4 + 3], ka.w, d0);
+                        d1 = fmaf(qv[4 * c4 + 4], kb.x, d1); d1 = fmaf(qv[4 * c4 + 5], kb.y, d1);
+                        d1 = fmaf(qv[4 * c4 + 6], kb.z, d1); d1 = fmaf(qv[4 * c4 + 7], kb.w, d1);
+                    }
+                    sc[u] = (d0 + d1) * 0.17677669529663687f;                  // / np.sqrt(attention_dim), :126
+                    const int s = j < i ? j : j - 1;                           // position of neighbour j in ego i's sequence
+                    float noise;
+                    if (a.gumbel) {
+                        const int64_t edge = ego * NM1 + s;
+                        noise = ok ? a.gumbel[2 * edge + 1] - a.gumbel[2 * edge] : 0.0f;
+                    } else {
+                        const float uu = u01(w == 0 ? rnd.x : (w == 1 ? rnd.y : (w == 2 ? rnd.z : rnd.w)));
+                        noise = __logf(uu) - __logf(1.0f - uu);                // Gumbel - Gumbel ~ Logistic(0,1)
+                    }
+                    const float dlog = (s_dl[s * 128 + row] + s_dl[(NM1 + s) * 128 + row]) + db;
+                    hd[u] = __fdividef(1.0f, 1.0f + expf(-(dlog + noise) * a.inv_tau));   // gumbel-softmax(tau)[..., 1]   (:93-95)
+                    if (a.dbg_hard && ok) a.dbg_hard[ego * NM1 + s] = hd[u];
+                    mx = fmaxf(mx, sc[u]);
                 }
-                sc[u] = d / 5.656854249492381f;                                // np.sqrt(attention_dim), :126
-                const int s = j < i ? j : j - 1;                               // position of neighbour j in ego i's sequence
-                const int64_t edge = (((int64_t)ag * a.n_envs + (ok ? b : 0)) * N + i) * NM1 + s;
-                float noise;
-                if (a.gumbel) {
-                    noise = ok ? a.gumbel[2 * edge + 1] - a.gumbel[2 * edge] : 0.0f;
-                } else {                                                       // same Philox stream as gat_attend_kernel: key (ego, j & 31), word j >> 5
-                    const int64_t key = (((int64_t)ag * a.n_envs + (ok ? b : 0)) * N + i) * 32 + (j & 31);
-                    const uint4 rnd = philox4x32(make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)a.counter, (uint32_t)(a.counter >> 32)),
-                                                 make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32)));
-                    const float uu = u01(j < 32 ? rnd.x : rnd.y);
-                    noise = __logf(uu) - __logf(1.0f - uu);                    // Gumbel - Gumbel ~ Logistic(0,1)
-                }
-                const float dlog = (s_dl[s * 128 + row] + s_dl[(NM1 + s) * 128 + row]) + db;
-                hd[u] = sigmoidf_acc((dlog + noise) * a.inv_tau);              // gumbel-softmax(tau)[..., 1]              (:93-95)
-                if (a.dbg_hard && ok) a.dbg_hard[edge] = hd[u];
-                mx = fmaxf(mx, sc[u]);
             }
         }
         s_pm[part * 128 + row] = mx;
@@ -540,16 +588,16 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         s_ps[part * 128 + row] = psum;
         __syncthreads();
         G5_STAMP(11);
-        const float den = ((s_ps[row] + s_ps[128 + row]) + s_ps[256 + row]) + s_ps[384 + row];
+        const float rden = 1.0f / (((s_ps[row] + s_ps[128 + row]) + s_ps[256 + row]) + s_ps[384 + row]);
         // ---- x_i = sum_j soft_ij hard_ij v_j (no renormalisation, :132): this part's neighbours, then the four parts -----
         float xa[H];
 #pragma unroll
         for (int c = 0; c < H; ++c) xa[c] = 0.0f;
 #pragma unroll
         for (int u = 0; u < JU; ++u) {
-            const int j = part + 4 * u;
+            const int j = 16 * (u >> 2) + 4 * part + (u & 3);
             if (j < N && j != i && i < N) {
-                const float wgt = (sc[u] / den) * hd[u];
+                const float wgt = (sc[u] * rden) * hd[u];
                 const float4* vr = reinterpret_cast<const float4*>(v_s + (e * 64 + j) * G5_KP);
 #pragma unroll
                 for (int c4 = 0; c4 < H / 4; ++c4) {
@@ -610,9 +658,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int c = 8 * part + q;
-                const float r = sigmoidf_acc((gir[q] + bi[c]) + (ghr[q] + bh[c]));
-                const float z = sigmoidf_acc((giz[q] + bi[H + c]) + (ghz[q] + bh[H + c]));
-                const float nn = tanhf_acc((gin[q] + bi[2 * H + c]) + r * (ghn[q] + bh[2 * H + c]));
+                // ex2.approx / rcp.approx forms (abs error ~1e-7, as in the recurrence); the clamp keeps 2^x finite
+                const float r = rcp_approx(1.0f + ex2_approx(fminf(K_RZ * ((gir[q] + bi[c]) + (ghr[q] + bh[c])), 80.0f)));
+                const float z = rcp_approx(1.0f + ex2_approx(fminf(K_RZ * ((giz[q] + bi[H + c]) + (ghz[q] + bh[H + c])), 80.0f)));
+                const float nn = fmaf(-2.0f, rcp_approx(1.0f + ex2_approx(fminf(K_N * ((gin[q] + bi[2 * H + c]) + r * (ghn[q] + bh[2 * H + c])), 80.0f))), 1.0f);
                 if (ok) outp[c] = (1.0f - z) * nn + z * hp[q];
             }
         }

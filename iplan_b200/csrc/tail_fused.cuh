@@ -43,7 +43,16 @@ struct TfVec {
     float ln1_g[RH], ln1_b[RH], b2[RH], ln2_g[RH], ln2_b[RH], bih[RH3], bhh[RH3], ln3_g[RH], ln3_b[RH];
     float head_w[TF_NOUT][RH], head_b[TF_NOUT];
 };
-constexpr size_t TF_SMEM = sizeof(TfFrag) + sizeof(TfVec);
+// warp-private gradient accumulators: the small gradients (LayerNorm gammas, head, S / M, loss sums) are summed over a warp's
+// tiles here and added to global memory once, when the warp is done
+constexpr int TF_SLOT_LN1 = 0, TF_SLOT_LN2 = 1, TF_SLOT_LN3 = 2, TF_SLOT_S = 3, TF_SLOT_M = 4, TF_SLOT_HEAD = 5;
+constexpr int TF_SLOTS = TF_SLOT_HEAD + TF_NOUT;
+constexpr int TF_WARPS_C = 8;
+struct TfAcc {
+    float v[TF_SLOTS][64];         // vectors over the 64 columns: lane l owns columns 2 l, 2 l + 1
+    float s[3 + TF_NOUT][32];      // per-lane running sums of row scalars: loss | entropy | ratio | d head_b[l]
+};
+constexpr size_t TF_SMEM = sizeof(TfFrag) + sizeof(TfVec) + TF_WARPS_C * sizeof(TfAcc);
 
 struct TfArgs {
     HeadArgs h;                    // parameters, targets, loss constants (h.gi / h.gh = the dGI / dGH buffers)
@@ -64,12 +73,35 @@ __device__ __forceinline__ float tf_quad_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
 }
-// sum over the eight row groups of the warp (lanes with the same t = lane & 3), then lanes 0..3 add to global memory
-__device__ __forceinline__ void tf_red(float* addr, float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 16);
-    if ((threadIdx.x & 31) < 4) atomicAdd(addr, v);
+// v[nt][j] = this thread's partial of column 8 nt + 2 t + j (t = lane & 3).  Sum over the warp's eight row groups g = lane >> 2
+// as a reduce-scatter (14 shuffles for 16 columns: each exchange halves what a lane still carries), after which lane l holds
+// the totals of columns 2 l and 2 l + 1, and add them to the warp's accumulator slot.
+__device__ __forceinline__ void tf_red16(float* slot, int lane, const float (&v)[8][2]) {
+    const bool g2 = lane & 16, g1 = lane & 8, g0 = lane & 4;
+    float w[4][2], x[2][2], y[2];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float send = g2 ? v[n][j] : v[n + 4][j], keep = g2 ? v[n + 4][j] : v[n][j];
+            w[n][j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float send = g1 ? w[n][j] : w[n + 2][j], keep = g1 ? w[n + 2][j] : w[n][j];
+            x[n][j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float send = g0 ? x[0][j] : x[1][j], keep = g0 ? x[1][j] : x[0][j];
+        y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    float2* p = reinterpret_cast<float2*>(slot) + lane;          // column pair 8 g + 2 t = 2 lane
+    float2 c = *p;
+    c.x += y[0]; c.y += y[1];
+    *p = c;
 }
 
 // A fragments (hi, lo) of k-block kb from a 16 x 64 accumulator-layout array
@@ -110,36 +142,41 @@ __device__ __forceinline__ void tf_ln_relu(const float (&z)[8][4], const float* 
     }
 }
 // backward of out = LN(ReLU(z)) g + b for the two rows: dz (in place of dy); column sums of dy x_hat (-> d gamma) and, if asked, of dz
+// go to the warp's accumulator slots
 __device__ __forceinline__ void tf_ln_relu_bwd(const float (&z)[8][4], const float (&xh)[8][4], const float (&rstd)[2],
-                                               const float* __restrict__ gam, int t, float (&dy)[8][4],
-                                               float* d_gam, float* d_colsum, float* d_colsum2, bool live0, bool live1) {
+                                               const float* __restrict__ gam, int t, int lane, float (&dy)[8][4],
+                                               float* acc_gam, float* acc_colsum, bool live0, bool live1) {
     float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
     float dx[8][4];
+    {
+        float gv[8][2];
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-        const float2 g2 = *reinterpret_cast<const float2*>(gam + 8 * nt + 2 * t);
-        dx[nt][0] = dy[nt][0] * g2.x; dx[nt][1] = dy[nt][1] * g2.y; dx[nt][2] = dy[nt][2] * g2.x; dx[nt][3] = dy[nt][3] * g2.y;
-        a0 += dx[nt][0] + dx[nt][1]; a1 += dx[nt][2] + dx[nt][3];
-        c0 = fmaf(dx[nt][0], xh[nt][0], c0); c0 = fmaf(dx[nt][1], xh[nt][1], c0);
-        c1 = fmaf(dx[nt][2], xh[nt][2], c1); c1 = fmaf(dx[nt][3], xh[nt][3], c1);
+        for (int nt = 0; nt < 8; ++nt) {
+            const float2 g2 = *reinterpret_cast<const float2*>(gam + 8 * nt + 2 * t);
+            // rows past the end carry dy = 0 (live = false): they add nothing
+            gv[nt][0] = dy[nt][0] * xh[nt][0] + dy[nt][2] * xh[nt][2];
+            gv[nt][1] = dy[nt][1] * xh[nt][1] + dy[nt][3] * xh[nt][3];
+            dx[nt][0] = dy[nt][0] * g2.x; dx[nt][1] = dy[nt][1] * g2.y; dx[nt][2] = dy[nt][2] * g2.x; dx[nt][3] = dy[nt][3] * g2.y;
+            a0 += dx[nt][0] + dx[nt][1]; a1 += dx[nt][2] + dx[nt][3];
+            c0 = fmaf(dx[nt][0], xh[nt][0], c0); c0 = fmaf(dx[nt][1], xh[nt][1], c0);
+            c1 = fmaf(dx[nt][2], xh[nt][2], c1); c1 = fmaf(dx[nt][3], xh[nt][3], c1);
+        }
+        tf_red16(acc_gam, lane, gv);
     }
     const float m10 = tf_quad_sum(a0) * (1.0f / RH), m11 = tf_quad_sum(a1) * (1.0f / RH);
     const float m20 = tf_quad_sum(c0) * (1.0f / RH), m21 = tf_quad_sum(c1) * (1.0f / RH);
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-        const int c = 8 * nt + 2 * t;
-        // rows past the end carry dy = 0 (live = false): they add nothing
-        tf_red(d_gam + c, dy[nt][0] * xh[nt][0] + dy[nt][2] * xh[nt][2]);
-        tf_red(d_gam + c + 1, dy[nt][1] * xh[nt][1] + dy[nt][3] * xh[nt][3]);
         dy[nt][0] = (live0 && z[nt][0] > 0.f) ? rstd[0] * (dx[nt][0] - m10 - xh[nt][0] * m20) : 0.f;
         dy[nt][1] = (live0 && z[nt][1] > 0.f) ? rstd[0] * (dx[nt][1] - m10 - xh[nt][1] * m20) : 0.f;
         dy[nt][2] = (live1 && z[nt][2] > 0.f) ? rstd[1] * (dx[nt][2] - m11 - xh[nt][2] * m21) : 0.f;
         dy[nt][3] = (live1 && z[nt][3] > 0.f) ? rstd[1] * (dx[nt][3] - m11 - xh[nt][3] * m21) : 0.f;
-        if (d_colsum) {
-            tf_red(d_colsum + c, dy[nt][0] + dy[nt][2]);
-            tf_red(d_colsum + c + 1, dy[nt][1] + dy[nt][3]);
-            if (d_colsum2) { tf_red(d_colsum2 + c, dy[nt][0] + dy[nt][2]); tf_red(d_colsum2 + c + 1, dy[nt][1] + dy[nt][3]); }
-        }
+    }
+    if (acc_colsum) {
+        float cv[8][2];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) { cv[nt][0] = dy[nt][0] + dy[nt][2]; cv[nt][1] = dy[nt][1] + dy[nt][3]; }
+        tf_red16(acc_colsum, lane, cv);
     }
 }
 
@@ -154,6 +191,9 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
     TfVec& V = *reinterpret_cast<TfVec*>(tf_raw + sizeof(TfFrag));
     const HeadArgs& h = A.h;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    static_assert(TF_WARPS == TF_WARPS_C, "accumulator count");
+    TfAcc& ACC = reinterpret_cast<TfAcc*>(tf_raw + sizeof(TfFrag) + sizeof(TfVec))[warp];
+    for (int i = lane; i < (int)(sizeof(TfAcc) / sizeof(float)); i += 32) reinterpret_cast<float*>(&ACC)[i] = 0.0f;
     const int g = lane >> 2, t = lane & 3;
     const float* __restrict__ p = h.P.net(a, type);
     const TrunkLayout L = trunk_layout(h.F, type == 0 ? h.n_actions : 1, type == 1);
@@ -428,17 +468,11 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
         };
         row_loss(q0, live0, out0, dl0);
         row_loss(q1, live1, out1, dl1);
-        {   // per-row scalars: the four lanes of a quad hold the same numbers; reduce over the row groups, lane 0 adds
-            auto red0 = [&](float* addr, float v) {
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 8);
-                v += __shfl_xor_sync(0xffffffffu, v, 16);
-                if (lane == 0) atomicAdd(addr, v);
-            };
-            red0(&h.stats[a * 8 + (type == 0 ? 0 : 1)], st_loss);           // policy | value loss
-            if (type == 0) { red0(&h.stats[a * 8 + 2], st_ent); red0(&h.stats[a * 8 + 3], st_ratio); }
+        {   // per-row scalars (the four lanes of a quad hold the same numbers): per-lane running sums, reduced when the warp is done
+            ACC.s[0][lane] += st_loss;                                      // policy | value loss
+            if (type == 0) { ACC.s[1][lane] += st_ent; ACC.s[2][lane] += st_ratio; }
 #pragma unroll
-            for (int l = 0; l < NOUT; ++l) if (l < n_out) red0(&gg[L.head_b + l], dl0[l] + dl1[l]);
+            for (int l = 0; l < NOUT; ++l) if (l < n_out) ACC.s[3 + l][lane] += dl0[l] + dl1[l];
         }
         // ---- backward: head, LN3 -> dh1 ------------------------------------------------------------------------------
         float dh[8][4];
@@ -449,23 +483,32 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
 #pragma unroll
             for (int l = 0; l < NOUT; ++l) {
                 if (l < n_out) {
+                    float hv[8][2];
 #pragma unroll
                     for (int nt = 0; nt < 8; ++nt) {
                         const float2 w = *reinterpret_cast<const float2*>(&V.head_w[l][8 * nt + 2 * t]);
                         dA[nt][0] = fmaf(dl0[l], w.x, dA[nt][0]); dA[nt][1] = fmaf(dl0[l], w.y, dA[nt][1]);
                         dA[nt][2] = fmaf(dl1[l], w.x, dA[nt][2]); dA[nt][3] = fmaf(dl1[l], w.y, dA[nt][3]);
-                        tf_red(&gg[L.head_w + l * RH + 8 * nt + 2 * t], dl0[l] * a3[nt][0] + dl1[l] * a3[nt][2]);
-                        tf_red(&gg[L.head_w + l * RH + 8 * nt + 2 * t + 1], dl0[l] * a3[nt][1] + dl1[l] * a3[nt][3]);
+                        hv[nt][0] = dl0[l] * a3[nt][0] + dl1[l] * a3[nt][2];
+                        hv[nt][1] = dl0[l] * a3[nt][1] + dl1[l] * a3[nt][3];
                     }
+                    tf_red16(ACC.v[TF_SLOT_HEAD + l], lane, hv);
                 }
             }
             float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+            {
+                float gv[8][2];
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    gv[nt][0] = dA[nt][0] * xh3[nt][0] + dA[nt][2] * xh3[nt][2];
+                    gv[nt][1] = dA[nt][1] * xh3[nt][1] + dA[nt][3] * xh3[nt][3];
+                }
+                tf_red16(ACC.v[TF_SLOT_LN3], lane, gv);
+            }
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
                 const int c = 8 * nt + 2 * t;
                 const float2 g2 = *reinterpret_cast<const float2*>(V.ln3_g + c);
-                tf_red(&gg[L.ln3_w + c], dA[nt][0] * xh3[nt][0] + dA[nt][2] * xh3[nt][2]);
-                tf_red(&gg[L.ln3_w + c + 1], dA[nt][1] * xh3[nt][1] + dA[nt][3] * xh3[nt][3]);
                 dA[nt][0] *= g2.x; dA[nt][1] *= g2.y; dA[nt][2] *= g2.x; dA[nt][3] *= g2.y;
                 a0 += dA[nt][0] + dA[nt][1]; a1 += dA[nt][2] + dA[nt][3];
                 c0 = fmaf(dA[nt][0], xh3[nt][0], c0); c0 = fmaf(dA[nt][1], xh3[nt][1], c0);
@@ -544,7 +587,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
         {
             float xh2[8][4], tmp[8][4], rs2[2];                             // x_hat of LN2 again (cheaper than keeping 32 registers alive)
             tf_ln_relu(z2, V.ln2_g, V.ln2_b, t, xh2, tmp, rs2);
-            tf_ln_relu_bwd(z2, xh2, rs2, V.ln2_g, t, da2, gg + L.ln2_w, nullptr, nullptr, live0, live1);   // da2 = dZ2 now
+            tf_ln_relu_bwd(z2, xh2, rs2, V.ln2_g, t, lane, da2, ACC.v[TF_SLOT_LN2], nullptr, live0, live1);   // da2 = dZ2 now
         }
         {
             float* o0 = A.z2.row(a, type, q0);
@@ -576,22 +619,48 @@ __global__ void __launch_bounds__(TF_THREADS, 1) tail_fused_kernel(TfArgs A) {
                 z[nt][0] = v0.x; z[nt][1] = v0.y; z[nt][2] = v1.x; z[nt][3] = v1.y;
             }
             tf_ln_relu(z, V.ln1_g, V.ln1_b, t, xh, tmp, rs1);
-            tf_ln_relu_bwd(z, xh, rs1, V.ln1_g, t, da1, gg + L.ln1_w, gg + L.fc1_b, smS, live0, live1);  // da1 = dZ1 now; S = colsum
+            tf_ln_relu_bwd(z, xh, rs1, V.ln1_g, t, lane, da1, ACC.v[TF_SLOT_LN1], ACC.v[TF_SLOT_S], live0, live1);  // da1 = dZ1 now; S = colsum
         }
         {
             const float mu0 = A.stat[(a * rows + q0) * 2], rs0 = A.stat[(a * rows + q0) * 2 + 1];
             const float mu1 = A.stat[(a * rows + q1) * 2], rs1_ = A.stat[(a * rows + q1) * 2 + 1];
+            float mv[8][2];
 #pragma unroll
             for (int nt = 0; nt < 8; ++nt) {
                 const int c = 8 * nt + 2 * t;
                 const float v00 = da1[nt][0] * rs0, v01 = da1[nt][1] * rs0, v10 = da1[nt][2] * rs1_, v11 = da1[nt][3] * rs1_;
-                tf_red(smM + c, v00 * mu0 + v10 * mu1);
-                tf_red(smM + c + 1, v01 * mu0 + v11 * mu1);
+                mv[nt][0] = v00 * mu0 + v10 * mu1;
+                mv[nt][1] = v01 * mu0 + v11 * mu1;
                 if (live0) *reinterpret_cast<float2*>(z1p0 + c) = make_float2(v00, v01);
                 if (live1) *reinterpret_cast<float2*>(z1p1 + c) = make_float2(v10, v11);
             }
+            tf_red16(ACC.v[TF_SLOT_M], lane, mv);
         }
     }
+    // ---- the warp's accumulated small gradients -> global memory -----------------------------------------------------------
+    __syncwarp();
+    auto flush = [&](int slot, float* dst, float* dst2) {
+        const float2 c = reinterpret_cast<const float2*>(ACC.v[slot])[lane];
+        atomicAdd(dst + 2 * lane, c.x);
+        atomicAdd(dst + 2 * lane + 1, c.y);
+        if (dst2) { atomicAdd(dst2 + 2 * lane, c.x); atomicAdd(dst2 + 2 * lane + 1, c.y); }
+    };
+    flush(TF_SLOT_LN1, gg + L.ln1_w, nullptr);
+    flush(TF_SLOT_LN2, gg + L.ln2_w, nullptr);
+    flush(TF_SLOT_LN3, gg + L.ln3_w, nullptr);
+    flush(TF_SLOT_S, gg + L.fc1_b, smS);                                    // S = colsum(dZ1) is also the fc1 bias gradient
+    flush(TF_SLOT_M, smM, nullptr);
+    for (int l = 0; l < n_out; ++l) flush(TF_SLOT_HEAD + l, gg + L.head_w + l * RH, nullptr);
+    auto flush_scalar = [&](int k, float* dst) {
+        float v = t == 0 ? ACC.s[k][lane] : 0.0f;                           // one lane per quad: the four hold the same sums
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane == 0) atomicAdd(dst, v);
+    };
+    flush_scalar(0, &h.stats[a * 8 + (type == 0 ? 0 : 1)]);
+    if (type == 0) { flush_scalar(1, &h.stats[a * 8 + 2]); flush_scalar(2, &h.stats[a * 8 + 3]); }
+    for (int l = 0; l < n_out; ++l) flush_scalar(3 + l, &gg[L.head_b + l]);
 }
 
 // LayerNorm beta gradients and the rest of the gate-bias bookkeeping, from the column sums the weight-gradient kernels
