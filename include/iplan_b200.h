@@ -91,6 +91,8 @@ int iplan_gat_set_impl(int impl);
 int iplan_gat_get_impl(void);
 /* Timing experiments only (IPLAN_GAT_DBG=4): clock64() stamps of one CTA's phase boundaries in the last fused launch. */
 int iplan_gat_debug_clocks(long long* out32);
+/* timing experiments (IPLAN_GAT_DBG=64): per-step event clocks of four warps of one CTA, [4][8 steps][8 events] */
+int iplan_gat_debug_trace(long long* out256);
 
 /* iplan_gat_step with optional cudaEvent_t handles (NULL = skip) recorded on `stream` before the recurrence kernel,
  * between the two kernels and after the attention kernel: per-kernel timing of the dominant kernel inside a running

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "iplan_gat_set_impl": (_i, [_i]),
     "iplan_gat_get_impl": (_i, []),
     "iplan_gat_debug_clocks": (_i, [_p]),
+    "iplan_gat_debug_trace": (_i, [_p]),
     "iplan_gat_step": (_i, [_p, _i64, View, View, View, View, _p, _u64, _u64, _f, _p, _p, _i64,
                             _i, _i, _i, _i, _i, _p]),
     "iplan_gat_step_ex": (_i, [_p, _i64, View, View, View, View, _p, _u64, _u64, _f, _p, _p, _i64,

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) fc1_fwd_tc5_kernel(
     const float* __restrict__ ws, const float* __restrict__ cc, const float* __restrict__ stat, float* __restrict__ Z1) {
     extern __shared__ unsigned char t5_raw[];
     const int a = blockIdx.y, m0 = blockIdx.x * T5_BM;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     const uint32_t base = (smem_u32(t5_raw) + 1023u) & ~1023u;            // swizzle atoms are 1024-byte aligned
     const uint32_t bars = base + T5_STAGES * T5_STAGE_BYTES;              // full[3] | empty[3] | tfull[2] | tempty[2] | tmem ptr
     auto full = [&](int s) { return bars + 8u * s; };
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) fc1_fwd_tc5_kernel(
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % T5_STAGES, it = kb / T5_STAGES;
                 if (it > 0) mbar_wait(empty(s), (it - 1) & 1);
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) fc1_fwd_tc5_kernel(
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % T5_STAGES, buf = kb & 1, ib = kb >> 1;
                 if (ib > 0) mbar_wait(tempty(buf), (ib - 1) & 1);          // the drain warps have emptied this accumulator
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) fc1_bwd_tc5_kernel(
     const int a = blockIdx.z, f0 = blockIdx.x * T5_BN;
     const int kb0 = blockIdx.y * kb_per_chunk;
     const int nkb = min(kb_per_chunk, (rows + T5_BK - 1) / T5_BK - kb0);       // 64-row blocks of this chunk
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
     const uint32_t base = (smem_u32(t5_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + T5_STAGES * T5_STAGE_BYTES;
     auto full = [&](int s) { return bars + 8u * s; };
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) fc1_bwd_tc5_kernel(
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % T5_STAGES, it = kb / T5_STAGES;
                 if (it > 0) mbar_wait(empty(s), (it - 1) & 1);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(T5_THREADS, 1) fc1_bwd_tc5_kernel(
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % T5_STAGES, buf = kb & 1, ib = kb >> 1;
                 if (ib > 0) mbar_wait(tempty(buf), (ib - 1) & 1);

@@ -80,7 +80,9 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 
 __global__ void __launch_bounds__(G8_THREADS, 1) gat128_recur_kernel(Gat128Args a) {
     extern __shared__ unsigned char g8_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp index through a shuffle: warp-uniform for the compiler, so the MMA operands stay in uniform registers (no per-operand
+    // register-to-uniform waterfall around each of the 72 tcgen05.mma of an item-step)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int grp = warp >> 2, u = tid & 127;                       // hidden unit = TMEM lane
     const int ag = blockIdx.y, dir = blockIdx.z;
     const uint32_t raw_u = smem_u32(g8_raw);
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(G8_THREADS, 1) gat128_recur_kernel(Gat128Args 
     float* qbuf = reinterpret_cast<float*>(gb + G8_OFF_Q + grp * 2 * G8_Q_BYTES);
     float* plx = reinterpret_cast<float*>(gb + G8_OFF_PL) + grp * (2 * 4 * NB);
     const uint32_t d_col = G8_D_COL + grp * 48;
-    const bool issuer = (warp & 3) == 0 && lane == 0;
+    const bool issuer_warp = (warp & 3) == 0;                       // warp-uniform; one elected lane issues
     constexpr uint32_t IDESC = tc5_idesc(128, NB);
     tc5_fence_before();
     __syncthreads();                                                // W complete in TMEM before any product
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(G8_THREADS, 1) gat128_recur_kernel(Gat128Args 
             }
             tc5_commit(d_full(grp));
         };
-        if (issuer) issue();                                        // step 0 (h = 0)
+        if (issuer_warp) { if (elect_one()) issue(); }              // step 0 (h = 0)
         for (int step = 0; step < STEPS; ++step) {
             const int s = dir ? STEPS - 1 - step : step;
             mbar_wait(d_full(grp), phase & 1);
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(G8_THREADS, 1) gat128_recur_kernel(Gat128Args 
             fence_proxy_async();
             tc5_fence_before();
             asm volatile("barrier.sync %0, 128;" ::"r"(1 + grp) : "memory");
-            if (issuer && step + 1 < STEPS) issue();
+            if (issuer_warp && step + 1 < STEPS) { if (elect_one()) issue(); }
             if (u < NB) {                                           // dl[item][dir][s][i]
                 const float* px = plx + (step & 1) * (4 * NB) + u;
                 a.dl[((((int64_t)ag * a.n_items + item) * 2 + dir) * STEPS + s) * NB + u] = ((px[0] + px[NB]) + px[2 * NB]) + px[3 * NB];

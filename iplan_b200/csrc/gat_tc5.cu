@@ -88,6 +88,15 @@ __device__ __forceinline__ void tc5_wait_ld8(float (&a)[8]) {
 // instructions of the gates are replaced by FMA-pipe stand-ins
 // bit 2 = one CTA stamps clock64() at its phase boundaries into g5_clk (read back with iplan_gat_debug_clocks)
 __device__ long long g5_clk[32];
+// bit 6 (64): per-step event clocks of warps 0 / 4 / 8 / 12 (lane 0) of one CTA for steps 20..27: [warp slot 4][step 8][event 8]
+__device__ long long g5_trace[4 * 8 * 8];
+#define G5_TRACE(ev)                                                                                                   \
+    do {                                                                                                               \
+        if constexpr ((DBG & 64) != 0) {                                                                               \
+            if (blockIdx.x == 3 && blockIdx.y == 0 && lane == 0 && (warp & 3) == 0 && step >= 20 && step < 28)         \
+                g5_trace[((warp >> 2) * 8 + (step - 20)) * 8 + (ev)] = clock64();                                      \
+        }                                                                                                              \
+    } while (0)
 #define G5_STAMP(k)                                                                             \
     do {                                                                                        \
         if constexpr ((DBG & 4) != 0) {                                                         \
@@ -97,7 +106,10 @@ __device__ long long g5_clk[32];
 template <int DBG, bool FUSED>
 __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
     extern __shared__ unsigned char g5_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform, and everything derived from it (tile,
+    // descriptors, TMEM columns) stays in uniform registers — the MMA issue below is a handful of instructions instead of
+    // a register-to-uniform "waterfall" per operand (which cost ~800 cycles per step: tools/k1_trace.py)
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int ag = blockIdx.y, b0 = blockIdx.x * 2;
     const int N = a.n_slots, NM1 = N - 1, in_dim = a.obs_dim + a.latent_dim;
     const float* __restrict__ W = a.params + (int64_t)ag * a.param_stride;
@@ -254,7 +266,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
 
     constexpr uint32_t IDESC_IH = tc5_idesc(128, 2 * G3), IDESC_HH = tc5_idesc(128, G3);
     constexpr int PQ_COL = 128;                               // [P | Q] fwd at TMEM columns 128..319, rev at 320..511
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         tc5_fence_after();
         const uint64_t da = tc5_smem_desc(base + Y.a);
 #pragma unroll
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         tc5_fence_after();
         G5_STAMP(4);
         // the tile's product h . W_hh^T: issued by one lane once the tile's eight warps have written h (named barrier)
-        const bool issuer = (warp & 3) == 0 && hh == 0 && lane == 0;
+        const bool issuer_warp = (warp & 3) == 0 && hh == 0;         // warp-uniform
         const uint64_t mma_a = tc5_smem_desc(a_tile), mma_b = tc5_smem_desc(base + Y.bhh + t * G5_BHH_BYTES);
         // accumulators: tile 0 at columns 0..95; tile 1 takes over the forward Q columns (224..319), free by now
         const uint32_t d_off = t ? (uint32_t)(PQ_COL + G3) : 0u;
@@ -330,7 +342,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
             tc5_mma(mma_d, mma_a + 2, mma_b + 6, IDESC_HH, 1);
             tc5_commit(d_full(t));
         };
-        if (issuer) issue();                                    // step 0 (h = 0)
+        if (issuer_warp) { if (elect_one()) issue(); }          // step 0 (h = 0)
 
         f32x2 h2[8];                                            // this thread's 16 hidden units, fp32
 #pragma unroll
@@ -346,8 +358,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         for (int step = 0; step < ((DBG & 1) && t ? 0 : NM1); ++step) {
             const int s = t ? NM1 - 1 - step : step;
             const float* q = q_env + (s < i ? s : s + 1) * G5_QP;       // neighbour of ego i at position s (:60-66)
+            G5_TRACE(0);
             mbar_wait(d_full(t), step & 1);
             tc5_fence_after();
+            G5_TRACE(1);
             f32x2 pl = pk2(0.0f, 0.0f);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {                               // hidden units 8c .. 8c+7
@@ -356,37 +370,54 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
                 tc5_ld8_nowait(d_col + 8 * c, vr);
                 tc5_ld8_nowait(d_col + H + 8 * c, vz);
                 tc5_ld8_nowait(d_col + 2 * H + 8 * c, vn);
-                tc5_ld8_nowait(p_col + 8 * c, pr);
-                tc5_ld8_nowait(p_col + H + 8 * c, pz);
-                tc5_ld8_nowait(p_col + 2 * H + 8 * c, pn);
+                if constexpr ((DBG & 16) == 0) {
+                    tc5_ld8_nowait(p_col + 8 * c, pr);
+                    tc5_ld8_nowait(p_col + H + 8 * c, pz);
+                    tc5_ld8_nowait(p_col + 2 * H + 8 * c, pn);
+                }
                 const float4 qr0 = *reinterpret_cast<const float4*>(q + 8 * c), qr1 = *reinterpret_cast<const float4*>(q + 8 * c + 4);
                 const float4 qz0 = *reinterpret_cast<const float4*>(q + H + 8 * c), qz1 = *reinterpret_cast<const float4*>(q + H + 8 * c + 4);
                 tc5_wait_ld24(vr, vz, vn);
-                tc5_wait_ld24(pr, pz, pn);
+                if constexpr ((DBG & 16) == 0) tc5_wait_ld24(pr, pz, pn);
+                if (k == 0) G5_TRACE(2);
                 f32x2 r[4], z[4], xx[4];
-                xx[0] = add2(add2(pk2(vr[0], vr[1]), pk2(pr[0], pr[1])), pk2(qr0.x, qr0.y));
-                xx[1] = add2(add2(pk2(vr[2], vr[3]), pk2(pr[2], pr[3])), pk2(qr0.z, qr0.w));
-                xx[2] = add2(add2(pk2(vr[4], vr[5]), pk2(pr[4], pr[5])), pk2(qr1.x, qr1.y));
-                xx[3] = add2(add2(pk2(vr[6], vr[7]), pk2(pr[6], pr[7])), pk2(qr1.z, qr1.w));
+                auto pq = [&](float v0, float v1, float p0, float p1, float q0, float q1) -> f32x2 {   // D + P + Q (timing experiments drop P / Q)
+                    f32x2 acc = pk2(v0, v1);
+                    if constexpr ((DBG & 16) == 0) acc = add2(acc, pk2(p0, p1));
+                    if constexpr ((DBG & 32) == 0) acc = add2(acc, pk2(q0, q1));
+                    return acc;
+                };
+                xx[0] = pq(vr[0], vr[1], pr[0], pr[1], qr0.x, qr0.y);
+                xx[1] = pq(vr[2], vr[3], pr[2], pr[3], qr0.z, qr0.w);
+                xx[2] = pq(vr[4], vr[5], pr[4], pr[5], qr1.x, qr1.y);
+                xx[3] = pq(vr[6], vr[7], pr[6], pr[7], qr1.z, qr1.w);
                 auto sig4 = [&](f32x2 x01, f32x2 x23, f32x2& ia, f32x2& ib) {
-                    if constexpr (DBG & 2) { ia = fma2(x01, x23, one2); ib = fma2(x23, x01, mtwo2); }
+                    if constexpr ((DBG & 2) != 0) { ia = fma2(x01, x23, one2); ib = fma2(x23, x01, mtwo2); }
+                    else if constexpr ((DBG & 8) != 0) sigmoid4_den_noclamp(x01, x23, ia, ib);
                     else sigmoid4_den(x01, x23, ia, ib);
                 };
                 sig4(xx[0], xx[1], r[0], r[1]);                         // r = 1 / (1 + 2^x')
                 sig4(xx[2], xx[3], r[2], r[3]);
-                xx[0] = add2(add2(pk2(vz[0], vz[1]), pk2(pz[0], pz[1])), pk2(qz0.x, qz0.y));
-                xx[1] = add2(add2(pk2(vz[2], vz[3]), pk2(pz[2], pz[3])), pk2(qz0.z, qz0.w));
-                xx[2] = add2(add2(pk2(vz[4], vz[5]), pk2(pz[4], pz[5])), pk2(qz1.x, qz1.y));
-                xx[3] = add2(add2(pk2(vz[6], vz[7]), pk2(pz[6], pz[7])), pk2(qz1.z, qz1.w));
+                xx[0] = pq(vz[0], vz[1], pz[0], pz[1], qz0.x, qz0.y);
+                xx[1] = pq(vz[2], vz[3], pz[2], pz[3], qz0.z, qz0.w);
+                xx[2] = pq(vz[4], vz[5], pz[4], pz[5], qz1.x, qz1.y);
+                xx[3] = pq(vz[6], vz[7], pz[6], pz[7], qz1.z, qz1.w);
                 sig4(xx[0], xx[1], z[0], z[1]);
                 sig4(xx[2], xx[3], z[2], z[3]);
                 const float4 qn0 = *reinterpret_cast<const float4*>(q + 2 * H + 8 * c), qn1 = *reinterpret_cast<const float4*>(q + 2 * H + 8 * c + 4);
                 const float4 bn0 = *reinterpret_cast<const float4*>(bn + 8 * c), bn1 = *reinterpret_cast<const float4*>(bn + 8 * c + 4);
                 // n pre-activation: (W_in x + b_in) + r (W_hn h + b_hn)   (GRU gate order r, z, n)
-                xx[0] = fma2(r[0], add2(pk2(vn[0], vn[1]), pk2(bn0.x, bn0.y)), add2(pk2(pn[0], pn[1]), pk2(qn0.x, qn0.y)));
-                xx[1] = fma2(r[1], add2(pk2(vn[2], vn[3]), pk2(bn0.z, bn0.w)), add2(pk2(pn[2], pn[3]), pk2(qn0.z, qn0.w)));
-                xx[2] = fma2(r[2], add2(pk2(vn[4], vn[5]), pk2(bn1.x, bn1.y)), add2(pk2(pn[4], pn[5]), pk2(qn1.x, qn1.y)));
-                xx[3] = fma2(r[3], add2(pk2(vn[6], vn[7]), pk2(bn1.z, bn1.w)), add2(pk2(pn[6], pn[7]), pk2(qn1.z, qn1.w)));
+                if constexpr ((DBG & 48) == 48) {                      // timing stand-in: both halves of the n pre-activation from the accumulator
+                    xx[0] = fma2(r[0], pk2(vn[0], vn[1]), pk2(vn[1], vn[0]));
+                    xx[1] = fma2(r[1], pk2(vn[2], vn[3]), pk2(vn[3], vn[2]));
+                    xx[2] = fma2(r[2], pk2(vn[4], vn[5]), pk2(vn[5], vn[4]));
+                    xx[3] = fma2(r[3], pk2(vn[6], vn[7]), pk2(vn[7], vn[6]));
+                } else {
+                    xx[0] = fma2(r[0], add2(pk2(vn[0], vn[1]), pk2(bn0.x, bn0.y)), add2(pk2(pn[0], pn[1]), pk2(qn0.x, qn0.y)));
+                    xx[1] = fma2(r[1], add2(pk2(vn[2], vn[3]), pk2(bn0.z, bn0.w)), add2(pk2(pn[2], pn[3]), pk2(qn0.z, qn0.w)));
+                    xx[2] = fma2(r[2], add2(pk2(vn[4], vn[5]), pk2(bn1.x, bn1.y)), add2(pk2(pn[4], pn[5]), pk2(qn1.x, qn1.y)));
+                    xx[3] = fma2(r[3], add2(pk2(vn[6], vn[7]), pk2(bn1.z, bn1.w)), add2(pk2(pn[6], pn[7]), pk2(qn1.z, qn1.w)));
+                }
                 f32x2 in[4];
                 sig4(xx[0], xx[1], in[0], in[1]);
                 sig4(xx[2], xx[3], in[2], in[3]);
@@ -402,6 +433,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
                 }
                 sts128(row_base + (((uint32_t)c ^ rx) << 4), hi[0], hi[1], hi[2], hi[3]);
                 sts128(row_base + (((uint32_t)(4 + c) ^ rx) << 4), lo[0], lo[1], lo[2], lo[3]);
+                if (k == 0) G5_TRACE(3); else G5_TRACE(4);
             }
             float pa, pb;
             upk2(pl, pa, pb);
@@ -409,7 +441,9 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
             fence_proxy_async();                                        // this thread's h stores -> async proxy
             tc5_fence_before();
             asm volatile("barrier.sync %0, 256;" ::"r"(1 + t) : "memory");   // the tile's 8 warps: h tile complete, D consumed
-            if (issuer && step + 1 < NM1) issue();
+            G5_TRACE(5);
+            if (issuer_warp && step + 1 < NM1) { if (elect_one()) issue(); }
+            G5_TRACE(6);
             if (!hh) {
                 const float dlv = (pa + pb) + plb[(step & 1) * 128];
                 if constexpr (FUSED) s_dl[(t * NM1 + s) * 128 + row] = dlv;
@@ -497,7 +531,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
             tc5_mma(dst, da + 0, db + 4, IDESC_HH, 1);
             tc5_mma(dst, da + 2, db + 6, IDESC_HH, 1);
         };
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             product(QKV_COL, base + Y.enc, t_qkv);                             // q | k | v = enc [W_q | W_k | W_v]^T      (:99-103)
             product(GH_COL, t_hx, t_whh);                                      // GRUCell: h_prev W_hh^T                   (:140)
             tc5_commit(att_bar);
@@ -635,7 +669,7 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
         tc5_fence_before();
         __syncthreads();
         tc5_fence_after();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             product(GI_COL, t_hx, t_wih);                                      // GRUCell: x W_ih^T                        (:140)
             tc5_commit(att_bar);
         }
@@ -688,12 +722,16 @@ int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, c
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<56, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e != cudaSuccess) { set_error("gat_step: tcgen05 kernel smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
     if (fused && g5_layout(a.n_slots, true).total > G5_SMEM_MAX) fused = false;
-    if (dbg & 3) fused = false;
+    if (dbg & ~4) fused = false;
     const G5Layout Y = g5_layout(a.n_slots, fused);
     if (Y.total > G5_SMEM_MAX) { set_error("gat_step: n_slots %d needs %u bytes of shared memory", a.n_slots, Y.total); return -1; }
     const dim3 grid((a.n_envs + 1) / 2, n_agents);
@@ -701,6 +739,10 @@ int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, c
     else if (fused) gat_tc5_kernel<0, true><<<grid, G5_THREADS, Y.total, st>>>(a);
     else if (dbg == 1) gat_tc5_kernel<1, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     else if (dbg == 2) gat_tc5_kernel<2, false><<<grid, G5_THREADS, Y.total, st>>>(a);
+    else if (dbg == 64) gat_tc5_kernel<64, false><<<grid, G5_THREADS, Y.total, st>>>(a);
+    else if (dbg == 8) gat_tc5_kernel<8, false><<<grid, G5_THREADS, Y.total, st>>>(a);
+    else if (dbg == 48) gat_tc5_kernel<48, false><<<grid, G5_THREADS, Y.total, st>>>(a);
+    else if (dbg == 56) gat_tc5_kernel<56, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     else gat_tc5_kernel<0, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     count_launch();
     if (did_fuse) *did_fuse = fused;
@@ -710,6 +752,11 @@ int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, c
 }  // namespace iplan
 
 // timing experiments (IPLAN_GAT_DBG=4): the phase-boundary clock stamps of one CTA of the last fused launch
+extern "C" int iplan_gat_debug_trace(long long* out256) {
+    const cudaError_t e = cudaMemcpyFromSymbol(out256, iplan::g5_trace, sizeof(long long) * 256);
+    if (e != cudaSuccess) { iplan::set_error("gat_debug_trace: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
 extern "C" int iplan_gat_debug_clocks(long long* out32) {
     const cudaError_t e = cudaMemcpyFromSymbol(out32, iplan::g5_clk, sizeof(long long) * 32);
     if (e != cudaSuccess) { iplan::set_error("gat_debug_clocks: %s", cudaGetErrorString(e)); return (int)e; }

@@ -60,6 +60,13 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
 // generic-proxy writes to shared memory -> visible to the async proxy (tcgen05.mma / TMA reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp (elect.sync): the issue point of the single-thread tcgen05 / TMA instructions
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 --------------------------------------------------------------------------------------
 __device__ __forceinline__ void tc5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
