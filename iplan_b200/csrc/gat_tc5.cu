@@ -79,6 +79,18 @@ __device__ __forceinline__ void tc5_wait_ld24(float (&a)[8], float (&b)[8], floa
                    "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]), "+f"(c[4]), "+f"(c[5]), "+f"(c[6]), "+f"(c[7])
                  :: "memory");
 }
+// 32 lanes x 4 consecutive 32-bit columns <- registers (thread = TMEM lane): the gate warps write h as packed f16 pairs
+__device__ __forceinline__ void tc5_st4(uint32_t taddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T : the A operand read from tensor memory (no shared-memory traffic for it)
+__device__ __forceinline__ void tc5_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc5_wait_ld8(float (&a)[8]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]) :: "memory");
@@ -88,6 +100,7 @@ __device__ __forceinline__ void tc5_wait_ld8(float (&a)[8]) {
 // instructions of the gates are replaced by FMA-pipe stand-ins
 // bit 2 = one CTA stamps clock64() at its phase boundaries into g5_clk (read back with iplan_gat_debug_clocks)
 __device__ long long g5_clk[32];
+__device__ int g5_stagger;          // experiment: cycles by which tile 1 delays its first product (IPLAN_GAT_STAG)
 // bit 6 (64): per-step event clocks of warps 0 / 4 / 8 / 12 (lane 0) of one CTA for steps 20..27: [warp slot 4][step 8][event 8]
 __device__ long long g5_trace[4 * 8 * 8];
 #define G5_TRACE(ev)                                                                                                   \
@@ -313,35 +326,45 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
                     dst[1] = make_float4(v[4] + pb1.x, v[5] + pb1.y, v[6] + pb1.z, v[7] + pb1.w);
                 }
             }
-        const uint32_t row_base = a_tile + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u;
-        const uint32_t rx = (uint32_t)(row & 7);
-        // h0 = 0: zero this thread's part of the row (tile 0 held enc; its products are complete)
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            sts128(row_base + (((uint32_t)(2 * hh + k) ^ rx) << 4), 0u, 0u, 0u, 0u);
-            sts128(row_base + (((uint32_t)(4 + 2 * hh + k) ^ rx) << 4), 0u, 0u, 0u, 0u);
-        }
-        fence_proxy_async();
         tc5_fence_before();
         __syncthreads();                                        // Q tables complete, TMEM Q columns free
         tc5_fence_after();
+        // The hidden state is the A operand of the step's product and lives in TENSOR MEMORY: 32 columns per tile, column c = the
+        // f16 pair of units (2c, 2c+1) for c < 16 (hi parts), their lo parts at 16 + c.  The gate warps write it with tcgen05.st
+        // (thread = TMEM lane = chain): no shared-memory store, no proxy fence, and the product reads only W_hh from shared memory
+        // (an A tile in shared memory made each of the six MMAs fetch 4 KB + 3 KB: they ran at the shared-memory bandwidth).
+        const uint32_t h_col = t ? (uint32_t)(PQ_COL + 3 * G3) : (uint32_t)G3;   // tile 0: columns 96..127; tile 1: 416..447 (reverse Q, spilled)
+        const uint32_t h_st = tlane + h_col + 8 * hh;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {                            // h0 = 0 (:77)
+            tc5_st4(h_st + 4 * k, 0u, 0u, 0u, 0u);
+            tc5_st4(h_st + 16 + 4 * k, 0u, 0u, 0u, 0u);
+        }
+        tc5_wait_st();
+        tc5_fence_before();
+        asm volatile("barrier.sync %0, 256;" ::"r"(1 + t) : "memory");
         G5_STAMP(4);
         // the tile's product h . W_hh^T: issued by one lane once the tile's eight warps have written h (named barrier)
         const bool issuer_warp = (warp & 3) == 0 && hh == 0;         // warp-uniform
-        const uint64_t mma_a = tc5_smem_desc(a_tile), mma_b = tc5_smem_desc(base + Y.bhh + t * G5_BHH_BYTES);
+        const uint32_t mma_a = tmem_base + h_col;
+        const uint64_t mma_b = tc5_smem_desc(base + Y.bhh + t * G5_BHH_BYTES);
         // accumulators: tile 0 at columns 0..95; tile 1 takes over the forward Q columns (224..319), free by now
         const uint32_t d_off = t ? (uint32_t)(PQ_COL + G3) : 0u;
         const uint32_t mma_d = tmem_base + d_off;
         auto issue = [&]() {
             tc5_fence_after();
-            tc5_mma(mma_d, mma_a + 0, mma_b + 0, IDESC_HH, 0);      // hi * hi
-            tc5_mma(mma_d, mma_a + 2, mma_b + 2, IDESC_HH, 1);
-            tc5_mma(mma_d, mma_a + 4, mma_b + 0, IDESC_HH, 1);      // lo * hi
-            tc5_mma(mma_d, mma_a + 6, mma_b + 2, IDESC_HH, 1);
-            tc5_mma(mma_d, mma_a + 0, mma_b + 4, IDESC_HH, 1);      // hi * lo
-            tc5_mma(mma_d, mma_a + 2, mma_b + 6, IDESC_HH, 1);
+            tc5_mma_ts(mma_d, mma_a + 0, mma_b + 0, IDESC_HH, 0);   // hi * hi   (A: 8 columns per K = 16 block)
+            tc5_mma_ts(mma_d, mma_a + 8, mma_b + 2, IDESC_HH, 1);
+            tc5_mma_ts(mma_d, mma_a + 16, mma_b + 0, IDESC_HH, 1);  // lo * hi
+            tc5_mma_ts(mma_d, mma_a + 24, mma_b + 2, IDESC_HH, 1);
+            tc5_mma_ts(mma_d, mma_a + 0, mma_b + 4, IDESC_HH, 1);   // hi * lo
+            tc5_mma_ts(mma_d, mma_a + 8, mma_b + 6, IDESC_HH, 1);
             tc5_commit(d_full(t));
         };
+        if (t == 1 && g5_stagger > 0) {                         // start the two tiles out of phase
+            const long long c0 = clock64();
+            while (clock64() - c0 < g5_stagger) {}
+        }
         if (issuer_warp) { if (elect_one()) issue(); }          // step 0 (h = 0)
 
         f32x2 h2[8];                                            // this thread's 16 hidden units, fp32
@@ -431,14 +454,14 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
                     pl = fma2(lwp[p], h2[4 * k + p], pl);
                     split_f16p(h2[4 * k + p], hi[p], lo[p]);
                 }
-                sts128(row_base + (((uint32_t)c ^ rx) << 4), hi[0], hi[1], hi[2], hi[3]);
-                sts128(row_base + (((uint32_t)(4 + c) ^ rx) << 4), lo[0], lo[1], lo[2], lo[3]);
+                tc5_st4(h_st + 4 * k, hi[0], hi[1], hi[2], hi[3]);
+                tc5_st4(h_st + 16 + 4 * k, lo[0], lo[1], lo[2], lo[3]);
                 if (k == 0) G5_TRACE(3); else G5_TRACE(4);
             }
             float pa, pb;
             upk2(pl, pa, pb);
             if (hh) plb[(step & 1) * 128] = pa + pb;                    // the other half's thread adds it after the barrier
-            fence_proxy_async();                                        // this thread's h stores -> async proxy
+            tc5_wait_st();                                              // this thread's h stores have landed in tensor memory
             tc5_fence_before();
             asm volatile("barrier.sync %0, 256;" ::"r"(1 + t) : "memory");   // the tile's 8 warps: h tile complete, D consumed
             G5_TRACE(5);
@@ -718,6 +741,9 @@ int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, c
     if (!configured) {
         const char* ev = getenv("IPLAN_GAT_DBG");
         dbg = ev ? atoi(ev) : 0;
+        const char* sg = getenv("IPLAN_GAT_STAG");
+        const int stag = sg ? atoi(sg) : 0;
+        cudaMemcpyToSymbol(g5_stagger, &stag, sizeof(int));
         cudaError_t e = cudaFuncSetAttribute(gat_tc5_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
