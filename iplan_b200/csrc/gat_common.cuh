@@ -74,21 +74,6 @@ __device__ __forceinline__ void sigmoid4_den(f32x2 x01, f32x2 x23, f32x2& ia, f3
     ia = mul2(b, q);
     ib = fma2(ea, q, q);
 }
-// the same without the clamp: only valid when the caller has bounded the pre-activations (sum of four <= 120)
-__device__ __forceinline__ void sigmoid4_den_noclamp(f32x2 x01, f32x2 x23, f32x2& ia, f32x2& ib) {
-    float x0, x1, x2, x3;
-    upk2(x01, x0, x1); upk2(x23, x2, x3);
-    const f32x2 ea = pk2(ex2_approx(x0), ex2_approx(x1));
-    const f32x2 eb = pk2(ex2_approx(x2), ex2_approx(x3));
-    const f32x2 b = add2(eb, pk2(1.0f, 1.0f));
-    const f32x2 p = fma2(ea, b, b);
-    float p0, p1;
-    upk2(p, p0, p1);
-    const float inv = rcp_approx(p0 * p1);
-    const f32x2 q = pk2(inv * p1, inv * p0);
-    ia = mul2(b, q);
-    ib = fma2(ea, q, q);
-}
 // pair -> packed f16 hi pair and f16 lo (residual) pair
 __device__ __forceinline__ void split_f16p(f32x2 v, uint32_t& hi, uint32_t& lo) {
     float x, y;

@@ -1,5 +1,6 @@
-// K1 recurrence on the 5th-generation tensor cores: the hard-attention bidirectional GRU of GAT_Net.forward
-// (reference nova/GAT_Net.py:57-97) with the hidden-state product on tcgen05.mma, accumulators in TMEM.
+// K1 on the 5th-generation tensor cores: the whole GAT step of GAT_Net.forward (reference nova/GAT_Net.py:41-142) in ONE launch;
+// its core is the hard-attention bidirectional GRU (:57-97) with the hidden-state product on tcgen05.mma, accumulators AND the
+// hidden state itself in tensor memory.
 //
 // One CTA = two environments x one agent-net, BOTH directions.  A direction is one M = 128 tile: TMEM lane / tile row
 // r = 64 e + i is the chain of ego slot i of environment e (rows i >= N are padding and never stored).  Per step and tile
@@ -7,26 +8,35 @@
 //     D[128 x 96] = h[128 x 32] . W_hh^T            six tcgen05.mma.kind::f16 (M 128, N 96, K 16):
 //                                                   hi*hi (2 k-blocks) + lo*hi (2) + hi*lo (2)  -> fp32-class accuracy
 //
-// with h kept in shared memory as a K-major SWIZZLE_128B operand tile [128 rows][hi(32) | lo(32)] f16 that the gate
-// warps rewrite every step (generic-proxy stores + fence.proxy.async + mbarrier), and W_hh (gate-activation scale
-// folded in) as a [96 rows][hi | lo] tile written once.  Eight gate warps per tile (warp -> TMEM lane quarter and one
-// half of the hidden units; thread = one chain x 16 units): tcgen05.ld the r|z|n pre-activations AND the chain's ego
-// part P (which the prologue's product left in TMEM) 8 hidden units at a time, add the neighbour part Q (shared memory,
-// broadcast: a step touches two Q rows; the biases are folded into the Q table), sigmoid / tanh through ex2 + a shared
-// rcp, new h -> f16 hi/lo -> the operand tile, the per-step hard-attention logit difference -> dl.
-// The two tiles (directions) interleave on the SM: while one tile's gates run on the MUFU / FMA pipes the other
-// tile's product runs on the tensor core.  16 warps = 4 per scheduler at <= 128 registers: the step of a warp is a long
-// dependent chain (tcgen05.ld -> ex2 -> rcp -> ...), and the MUFU pipe — the unit this loop is bound by — only stays
-// busy with several warps per scheduler in different phases (2 warps per scheduler measured 1.00 ms per launch at
-// B = 512, half the MUFU bound).  No separate issuer warps: once the eight warps of a tile have passed their named
-// barrier (h tile written), lane 0 of the tile's first warp issues the six MMAs and commits them to the tile's
-// mbarrier, which all eight warps then wait on.
+// The A operand h is read FROM TENSOR MEMORY (32 columns per tile: f16 pairs of the hi parts, then of the lo parts), written
+// every step by the gate warps with tcgen05.st (thread = TMEM lane = chain); only W_hh (a [96 rows][hi | lo] SWIZZLE_128B tile,
+// gate-activation scale folded in, written once) comes from shared memory.  An h tile in shared memory made each MMA fetch
+// 4 KB + 3 KB of operands and the six of them ran at the shared-memory bandwidth: ~1000 cycles from "h written" to
+// "pre-activations ready"; with A in tensor memory ~530 (tools/k1_trace.py, profiles/r2_k1_trace_*.txt).
+// Eight gate warps per tile (warp -> TMEM lane quarter and one half of the hidden units; thread = one chain x 16 units):
+// tcgen05.ld the r|z|n pre-activations AND the chain's ego part P (which the prologue's product left in TMEM) 8 hidden units
+// at a time, add the neighbour part Q (shared memory, broadcast: a step touches two Q rows; the biases are folded into the Q
+// table), sigmoid / tanh through ex2 + a shared rcp, new h -> f16 hi/lo -> tensor memory, the per-step hard-attention logit
+// difference -> dl.  16 warps = 4 per scheduler at <= 128 registers.  Once the eight warps of a tile have passed their named
+// barrier one ELECTED lane of the tile's first warp issues the six MMAs and commits them to the tile's mbarrier, which all eight
+// warps then wait on.  The warp index comes from a shuffle so that the compiler knows it is warp-uniform: descriptors and TMEM
+// addresses then stay in uniform registers and the issue is ~25 instructions (with a per-thread predicate the compiler wrapped
+// every MMA operand in a register-to-uniform "waterfall" loop: ~800 cycles per step).
 //
-// Prologue, also on the tensor core: enc = ReLU(W_e x + b) per row (thread = row, fp32 FMA, K <= 16), then
-// [P | Q] = enc . [W_ih[:, :H] | W_ih[:, H:]]^T as ONE M 128 x N 192 product per direction; P lands in the TMEM lane of
-// the thread that owns the chain (-> registers), Q is spilled once to a [row][96] table in shared memory.
+// What bounds the loop (measured, B = 512): the XU pipe (ex2 / rcp: 60 MUFU per warp-step = 1920 cycles per step of both tiles)
+// under a step period of ~2950 cycles: gate phase ~2600 (both tiles drift into lock-step and share the XU pipe) + ~530 of MMA
+// round trip.  Tried and measured, not kept: all P / Q / bias adds as extra MMAs with 13 of 19 issued a step ahead (0.82 ms but
+// shared-memory-bandwidth bound: 19 x 7 KB of operands per tile-step); a dedicated issuer warp (17 warps cap the kernel at 96
+// registers); a coupling that holds the tiles half a phase apart (the MMA then contends with the other tile's tcgen05.ld/st);
+// 2^x of the z gate as an FMA-pipe polynomial (correct to 2e-6, 7 % slower: the extra instructions cost more than the MUFU slots).
 //
-// Output: dl[dir][s][i] (same scratch layout as gat_recur_kernel), consumed by gat_attend_kernel.
+// Prologue, also on the tensor core: enc = ReLU(W_e x + b) per row (4 threads per row, fp32 FMA, K <= 16), then
+// [P | Q] = enc . [W_ih[:, :H] | W_ih[:, H:]]^T as ONE M 128 x N 192 product per direction; P stays in the TMEM lane of
+// the thread that owns the chain, Q is spilled once to a [row][96] table in shared memory.
+//
+// FUSED: attention + GRUCell (:99-142) in the same kernel, q|k|v, h_prev W_hh^T and x W_ih^T as three more tcgen05 products over the
+// dead operand tiles; the per-edge logits stay in shared memory.  FUSED = false: dl scratch (layout of gat_recur_kernel) for
+// gat_attend_kernel (n_slots too large for the fused shared-memory map, and the cross-check path impl 2).
 #include "common.cuh"
 #include "gat_common.cuh"
 #include "tc5.cuh"
@@ -100,7 +110,6 @@ __device__ __forceinline__ void tc5_wait_ld8(float (&a)[8]) {
 // instructions of the gates are replaced by FMA-pipe stand-ins
 // bit 2 = one CTA stamps clock64() at its phase boundaries into g5_clk (read back with iplan_gat_debug_clocks)
 __device__ long long g5_clk[32];
-__device__ int g5_stagger;          // experiment: cycles by which tile 1 delays its first product (IPLAN_GAT_STAG)
 // bit 6 (64): per-step event clocks of warps 0 / 4 / 8 / 12 (lane 0) of one CTA for steps 20..27: [warp slot 4][step 8][event 8]
 __device__ long long g5_trace[4 * 8 * 8];
 #define G5_TRACE(ev)                                                                                                   \
@@ -361,10 +370,6 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
             tc5_mma_ts(mma_d, mma_a + 8, mma_b + 6, IDESC_HH, 1);
             tc5_commit(d_full(t));
         };
-        if (t == 1 && g5_stagger > 0) {                         // start the two tiles out of phase
-            const long long c0 = clock64();
-            while (clock64() - c0 < g5_stagger) {}
-        }
         if (issuer_warp) { if (elect_one()) issue(); }          // step 0 (h = 0)
 
         f32x2 h2[8];                                            // this thread's 16 hidden units, fp32
@@ -393,22 +398,17 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
                 tc5_ld8_nowait(d_col + 8 * c, vr);
                 tc5_ld8_nowait(d_col + H + 8 * c, vz);
                 tc5_ld8_nowait(d_col + 2 * H + 8 * c, vn);
-                if constexpr ((DBG & 16) == 0) {
-                    tc5_ld8_nowait(p_col + 8 * c, pr);
-                    tc5_ld8_nowait(p_col + H + 8 * c, pz);
-                    tc5_ld8_nowait(p_col + 2 * H + 8 * c, pn);
-                }
+                tc5_ld8_nowait(p_col + 8 * c, pr);
+                tc5_ld8_nowait(p_col + H + 8 * c, pz);
+                tc5_ld8_nowait(p_col + 2 * H + 8 * c, pn);
                 const float4 qr0 = *reinterpret_cast<const float4*>(q + 8 * c), qr1 = *reinterpret_cast<const float4*>(q + 8 * c + 4);
                 const float4 qz0 = *reinterpret_cast<const float4*>(q + H + 8 * c), qz1 = *reinterpret_cast<const float4*>(q + H + 8 * c + 4);
                 tc5_wait_ld24(vr, vz, vn);
-                if constexpr ((DBG & 16) == 0) tc5_wait_ld24(pr, pz, pn);
+                tc5_wait_ld24(pr, pz, pn);
                 if (k == 0) G5_TRACE(2);
                 f32x2 r[4], z[4], xx[4];
-                auto pq = [&](float v0, float v1, float p0, float p1, float q0, float q1) -> f32x2 {   // D + P + Q (timing experiments drop P / Q)
-                    f32x2 acc = pk2(v0, v1);
-                    if constexpr ((DBG & 16) == 0) acc = add2(acc, pk2(p0, p1));
-                    if constexpr ((DBG & 32) == 0) acc = add2(acc, pk2(q0, q1));
-                    return acc;
+                auto pq = [&](float v0, float v1, float p0, float p1, float q0, float q1) -> f32x2 {   // D + P + Q
+                    return add2(add2(pk2(v0, v1), pk2(p0, p1)), pk2(q0, q1));
                 };
                 xx[0] = pq(vr[0], vr[1], pr[0], pr[1], qr0.x, qr0.y);
                 xx[1] = pq(vr[2], vr[3], pr[2], pr[3], qr0.z, qr0.w);
@@ -416,7 +416,6 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
                 xx[3] = pq(vr[6], vr[7], pr[6], pr[7], qr1.z, qr1.w);
                 auto sig4 = [&](f32x2 x01, f32x2 x23, f32x2& ia, f32x2& ib) {
                     if constexpr ((DBG & 2) != 0) { ia = fma2(x01, x23, one2); ib = fma2(x23, x01, mtwo2); }
-                    else if constexpr ((DBG & 8) != 0) sigmoid4_den_noclamp(x01, x23, ia, ib);
                     else sigmoid4_den(x01, x23, ia, ib);
                 };
                 sig4(xx[0], xx[1], r[0], r[1]);                         // r = 1 / (1 + 2^x')
@@ -430,17 +429,10 @@ __global__ void __launch_bounds__(G5_THREADS, 1) gat_tc5_kernel(GatArgs a) {
                 const float4 qn0 = *reinterpret_cast<const float4*>(q + 2 * H + 8 * c), qn1 = *reinterpret_cast<const float4*>(q + 2 * H + 8 * c + 4);
                 const float4 bn0 = *reinterpret_cast<const float4*>(bn + 8 * c), bn1 = *reinterpret_cast<const float4*>(bn + 8 * c + 4);
                 // n pre-activation: (W_in x + b_in) + r (W_hn h + b_hn)   (GRU gate order r, z, n)
-                if constexpr ((DBG & 48) == 48) {                      // timing stand-in: both halves of the n pre-activation from the accumulator
-                    xx[0] = fma2(r[0], pk2(vn[0], vn[1]), pk2(vn[1], vn[0]));
-                    xx[1] = fma2(r[1], pk2(vn[2], vn[3]), pk2(vn[3], vn[2]));
-                    xx[2] = fma2(r[2], pk2(vn[4], vn[5]), pk2(vn[5], vn[4]));
-                    xx[3] = fma2(r[3], pk2(vn[6], vn[7]), pk2(vn[7], vn[6]));
-                } else {
-                    xx[0] = fma2(r[0], add2(pk2(vn[0], vn[1]), pk2(bn0.x, bn0.y)), add2(pk2(pn[0], pn[1]), pk2(qn0.x, qn0.y)));
-                    xx[1] = fma2(r[1], add2(pk2(vn[2], vn[3]), pk2(bn0.z, bn0.w)), add2(pk2(pn[2], pn[3]), pk2(qn0.z, qn0.w)));
-                    xx[2] = fma2(r[2], add2(pk2(vn[4], vn[5]), pk2(bn1.x, bn1.y)), add2(pk2(pn[4], pn[5]), pk2(qn1.x, qn1.y)));
-                    xx[3] = fma2(r[3], add2(pk2(vn[6], vn[7]), pk2(bn1.z, bn1.w)), add2(pk2(pn[6], pn[7]), pk2(qn1.z, qn1.w)));
-                }
+                xx[0] = fma2(r[0], add2(pk2(vn[0], vn[1]), pk2(bn0.x, bn0.y)), add2(pk2(pn[0], pn[1]), pk2(qn0.x, qn0.y)));
+                xx[1] = fma2(r[1], add2(pk2(vn[2], vn[3]), pk2(bn0.z, bn0.w)), add2(pk2(pn[2], pn[3]), pk2(qn0.z, qn0.w)));
+                xx[2] = fma2(r[2], add2(pk2(vn[4], vn[5]), pk2(bn1.x, bn1.y)), add2(pk2(pn[4], pn[5]), pk2(qn1.x, qn1.y)));
+                xx[3] = fma2(r[3], add2(pk2(vn[6], vn[7]), pk2(bn1.z, bn1.w)), add2(pk2(pn[6], pn[7]), pk2(qn1.z, qn1.w)));
                 f32x2 in[4];
                 sig4(xx[0], xx[1], in[0], in[1]);
                 sig4(xx[2], xx[3], in[2], in[3]);
@@ -741,17 +733,11 @@ int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, c
     if (!configured) {
         const char* ev = getenv("IPLAN_GAT_DBG");
         dbg = ev ? atoi(ev) : 0;
-        const char* sg = getenv("IPLAN_GAT_STAG");
-        const int stag = sg ? atoi(sg) : 0;
-        cudaMemcpyToSymbol(g5_stagger, &stag, sizeof(int));
         cudaError_t e = cudaFuncSetAttribute(gat_tc5_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<48, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<56, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gat_tc5_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G5_SMEM_MAX);
         if (e != cudaSuccess) { set_error("gat_step: tcgen05 kernel smem attr: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
@@ -766,9 +752,6 @@ int launch_gat_tc5(const GatArgs& a, int n_agents, bool fused, bool* did_fuse, c
     else if (dbg == 1) gat_tc5_kernel<1, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     else if (dbg == 2) gat_tc5_kernel<2, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     else if (dbg == 64) gat_tc5_kernel<64, false><<<grid, G5_THREADS, Y.total, st>>>(a);
-    else if (dbg == 8) gat_tc5_kernel<8, false><<<grid, G5_THREADS, Y.total, st>>>(a);
-    else if (dbg == 48) gat_tc5_kernel<48, false><<<grid, G5_THREADS, Y.total, st>>>(a);
-    else if (dbg == 56) gat_tc5_kernel<56, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     else gat_tc5_kernel<0, false><<<grid, G5_THREADS, Y.total, st>>>(a);
     count_launch();
     if (did_fuse) *did_fuse = fused;
