@@ -219,6 +219,11 @@ int iplan_pred_learn(const float* gat_params, int64_t gat_stride, const float* d
 #define IPLAN_BDEC_NTENSORS 8     /* nova/behavior_net.py:25-38 (DecoderRNN inside Behavior_Latent_Decoder), hidden = IPLAN_RNN */
 int64_t iplan_bdec_layout(int obs_dim, int latent_dim, int64_t* offsets);
 int64_t iplan_beh_learn_scratch_floats(int n_agents, int n_eps, int n_pos, int n_slots, int obs_dim, int latent_dim, int hist_len);
+/* 0 (default) = three register-tiled launches (csrc/beh_learn_tile.cu: encoder forward, decoder forward + backward, encoder
+ * backward; a CTA walks 64 chains in lock step), 1 = the one-warp-per-chain draft (csrc/beh_learn.cu), kept as the cross-check.
+ * Returns the previous setting; iplan_beh_learn_scratch_floats answers for the active implementation.  With keep == NULL the
+ * two draw different (equally distributed) Philox dropout masks. */
+int iplan_beh_learn_set_impl(int impl);
 int iplan_beh_learn(const float* enc_params, int64_t enc_stride, const float* dec_params, int64_t dec_stride,
                     float* g_enc, float* g_dec, const float* hist, const float* mask, const float* scale, const uint8_t* keep,
                     float* b_loss, float* s_loss, float* scratch, int64_t scratch_floats,

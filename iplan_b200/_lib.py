@@ -60,6 +60,7 @@ _SIGNATURES = {
                               _i, _i, _i, _i, _i, _i, _p]),
     "iplan_bdec_layout": (_i64, [_i, _i, _p]),
     "iplan_beh_learn_scratch_floats": (_i64, [_i, _i, _i, _i, _i, _i, _i]),
+    "iplan_beh_learn_set_impl": (_i, [_i]),
     "iplan_beh_learn": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _u64, _u64, _f, _f, _f,
                              _i, _i, _i, _i, _i, _i, _i, _p]),
     "iplan_learner_row_stats": (_i, [_p, _i64, _i, _i, _i64, _i, _p, _p]),

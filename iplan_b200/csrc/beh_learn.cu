@@ -362,12 +362,28 @@ extern "C" int64_t iplan_bdec_layout(int obs_dim, int latent_dim, int64_t* offse
     return L.total;
 }
 
-extern "C" int64_t iplan_beh_learn_scratch_floats(int n_agents, int n_eps, int n_pos, int n_slots, int obs_dim, int latent_dim, int hist_len) {
+extern "C" int64_t iplan_beh_learn_tile_scratch_floats(int n_agents, int n_eps, int n_pos, int n_slots, int obs_dim, int latent_dim, int hist_len);
+extern "C" int iplan_beh_learn_tile(const float* enc_params, int64_t enc_stride, const float* dec_params, int64_t dec_stride,
+                                    float* g_enc, float* g_dec, const float* hist, const float* mask, const float* scale, const uint8_t* keep,
+                                    float* b_loss, float* s_loss, float* scratch, int64_t scratch_floats,
+                                    uint64_t seed, uint64_t counter, float p_drop, float soft_coef, float thres_small_variation,
+                                    int n_agents, int n_eps, int n_steps, int n_slots, int obs_dim, int latent_dim, int hist_len, void* stream);
+
+// 0 = the register-tiled kernels of beh_learn_tile.cu (default), 1 = this file's one-warp-per-chain draft (the cross-check)
+static int g_beh_learn_impl = 0;
+extern "C" int iplan_beh_learn_set_impl(int impl) { const int old = g_beh_learn_impl; if (impl == 0 || impl == 1) g_beh_learn_impl = impl; return old; }
+
+static int64_t draft_scratch_floats(int n_agents, int n_eps, int n_pos, int n_slots, int obs_dim, int latent_dim, int hist_len) {
     const int64_t N = n_slots, W = hist_len, o = obs_dim, L = latent_dim, D = IPLAN_RNN, E = IPLAN_HID;
     const int64_t per = (n_pos + 1) * N * (D + E + L) + W * N * (o + L) + W * N * D + (W + 1) * N * D + W * N * D + W * N * o
                         + W * N * E + (W + 1) * N * E + N * L + W * N * o + 2 * W * N * 3 * D + W * N * D + 2 * W * N * 3 * E + W * N * E
                         + N * L + N * (D + E + L);
     return (int64_t)n_agents * n_eps * ((per + 3) & ~int64_t(3));
+}
+
+extern "C" int64_t iplan_beh_learn_scratch_floats(int n_agents, int n_eps, int n_pos, int n_slots, int obs_dim, int latent_dim, int hist_len) {
+    return g_beh_learn_impl == 0 ? iplan_beh_learn_tile_scratch_floats(n_agents, n_eps, n_pos, n_slots, obs_dim, latent_dim, hist_len)
+                                 : draft_scratch_floats(n_agents, n_eps, n_pos, n_slots, obs_dim, latent_dim, hist_len);
 }
 
 extern "C" int iplan_beh_learn(const float* enc_params, int64_t enc_stride, const float* dec_params, int64_t dec_stride,
@@ -376,12 +392,15 @@ extern "C" int iplan_beh_learn(const float* enc_params, int64_t enc_stride, cons
                                uint64_t seed, uint64_t counter, float p_drop, float soft_coef, float thres_small_variation,
                                int n_agents, int n_eps, int n_steps, int n_slots, int obs_dim, int latent_dim, int hist_len, void* stream) {
     using namespace iplan;
+    if (g_beh_learn_impl == 0)
+        return iplan_beh_learn_tile(enc_params, enc_stride, dec_params, dec_stride, g_enc, g_dec, hist, mask, scale, keep, b_loss, s_loss, scratch, scratch_floats,
+                                    seed, counter, p_drop, soft_coef, thres_small_variation, n_agents, n_eps, n_steps, n_slots, obs_dim, latent_dim, hist_len, stream);
     IPLAN_REQUIRE(enc_params && dec_params && g_enc && g_dec && hist && mask && scale && b_loss && s_loss && scratch, "beh_learn: null pointer");
     const int n_pos = n_steps - 1 - hist_len;
     IPLAN_REQUIRE(n_pos > 0, "beh_learn: episode of %d steps is shorter than the window of %d", n_steps, hist_len);
     IPLAN_REQUIRE(obs_dim > 0 && latent_dim > 0 && obs_dim + latent_dim <= 32 && latent_dim <= 32 && n_slots > 0, "beh_learn: bad sizes");
     IPLAN_REQUIRE(n_agents > 0 && n_eps > 0 && p_drop >= 0.f && p_drop < 1.f, "beh_learn: bad arguments");
-    const int64_t need = iplan_beh_learn_scratch_floats(n_agents, n_eps, n_pos, n_slots, obs_dim, latent_dim, hist_len);
+    const int64_t need = draft_scratch_floats(n_agents, n_eps, n_pos, n_slots, obs_dim, latent_dim, hist_len);
     IPLAN_REQUIRE(scratch_floats >= need, "beh_learn: scratch too small (%lld floats, need %lld)", (long long)scratch_floats, (long long)need);
     BehLearnArgs a;
     a.enc = enc_params; a.enc_stride = enc_stride; a.dec = dec_params; a.dec_stride = dec_stride; a.g_enc = g_enc; a.g_dec = g_dec;

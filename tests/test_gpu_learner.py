@@ -216,6 +216,17 @@ def test_behavior_learn_vs_reference_golden(case):
     assert mod.run(case)
 
 
+def test_behavior_learn_tiled_kernels_match_the_draft_on_ragged_tiles():
+    """csrc/beh_learn_tile.cu (the default: 64-chain CTA tiles, three launches) against csrc/beh_learn.cu (one warp per
+    chain, pinned to the reference by the test above) on the same inputs and dropout masks: 6 episodes x 55 slots = 330
+    chains per agent-net = five full tiles and a ragged one, agents terminating inside the episode."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import importlib
+    mod = importlib.import_module("tools.check_beh_learn_tile")
+    assert mod.run(envs=6, steps=25)
+
+
 def test_packed_batch_last_action_with_list_bs_and_popart_checkpoint_formats(tmp_path):
     """(a) ``update(..., bs=[0, 2])`` (the pymarl ``envs_not_terminated`` pattern) must reach the packed
     rows' last-action columns; (b) critic checkpoints in the CUDA reference's format (no ``v_out.*`` keys, 20 optimiser
