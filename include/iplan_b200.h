@@ -149,6 +149,29 @@ int iplan_behavior_step_ex(const float* beh_params, int64_t param_stride,
                            int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int hist_len,
                            void* stream);
 
+/* ---- host-buffer entry points of the rollout step (csrc/host_api.cu) -----------------------------------------------------
+ * What a binding of the reference's numpy API calls: Prediction_policy.GAT_latent_update (nova/prediction_policy.py:92-118)
+ * and Behavior_policy.latent_update (nova/stable_behavior_policy.py:83-123) with HOST arrays in the reference's own layout
+ * ([B][A][N][*], C order).  The env dimension is cut into n_chunks (<= 16) pieces: piece c goes host -> device on a copy stream,
+ * its kernel runs on `stream` when it has landed, its result goes device -> host on a second copy stream while piece c + 1
+ * computes; the call returns when host_out is complete (synchronous, like the reference).  A NULL host pointer means the
+ * device buffer already holds that array (e.g. the previous call's result, still resident): nothing is uploaded for it.
+ * dev_* are caller-owned device buffers of the full [B][A][N][*] size (staging for the uploaded arrays; dev_out / dev_new
+ * receive the result and stay valid).  Host buffers may be pageable; page-locked ones overlap with the kernels.
+ * The GAT noise counter of piece c is counter + c. */
+int iplan_gat_latent_update_host(const float* gat_params, int64_t param_stride,
+                                 const float* host_hist, float* dev_hist, const float* host_h, float* dev_h,
+                                 const float* host_beh, float* dev_beh, float* dev_out, float* host_out,
+                                 uint64_t seed, uint64_t counter, float tau, float* scratch, int64_t scratch_floats,
+                                 int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int n_chunks, void* stream);
+/* host_window [B][A][N][hist_len][o], host_prev / host_new [B][A][N][L], dev_hid_io [B][A][N][32] (updated in place) */
+int iplan_behavior_latent_update_host(const float* beh_params, int64_t param_stride,
+                                      const float* host_window, float* dev_window, const float* host_prev, float* dev_prev,
+                                      float* dev_hid_io, float* dev_new, float* host_new, float soft_coef,
+                                      int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int hist_len, int n_chunks, void* stream);
+/* n device -> host copies on `stream`, then one synchronize (select_actions_ippo returns four small arrays) */
+int iplan_d2h_batch(void* const* dst_host, const void* const* src_dev, const int64_t* bytes, int n, void* stream);
+
 /* ---- K1c: controller step (actor + critic, one timestep) -------------------------
  * replaces DcntrlMAC.select_actions_ippo (controllers/dcntrl_controller.py:27-58):
  * LayerNorm(F) -> fc1 -> ReLU -> LN -> fc2 -> ReLU -> LN -> 1-step GRU -> LN ->

@@ -50,6 +50,9 @@ _SIGNATURES = {
     "iplan_gat128_gates": (_i, [_p, _p, _p, _p, _i64, _p]),
     "iplan_behavior_step": (_i, [_p, _i64, View, View, View, View, _f, _i, _i, _i, _i, _i, _i, _p]),
     "iplan_behavior_step_ex": (_i, [_p, _i64, View, _i64, _i, View, View, View, _f, _i, _i, _i, _i, _i, _i, _p]),
+    "iplan_gat_latent_update_host": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _u64, _u64, _f, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
+    "iplan_behavior_latent_update_host": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "iplan_d2h_batch": (_i, [_p, _p, _p, _i, _p]),
     "iplan_controller_step": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64,
                                    _p, _p, _u64, _u64, _i, _p, _p, _p, _p, _p, _p,
                                    _i, _i, _i, _i, _p]),
@@ -201,14 +204,7 @@ def to_host(t, shadow=False):
     the copy runs at PCIe speed and a later ``to_device`` of the same array does too).
     ``shadow=True``: `t` will not be written again by the caller; the returned array is read-only and ``to_device``
     of that same array object returns `t` without a copy (see ``device_shadow``)."""
-    io_bytes["d2h"] += t.numel() * t.element_size()
-    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-    h.copy_(t, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
-    arr = h.numpy()
-    if shadow and SHADOW:
-        _register_shadow(arr, t)
-    return arr
+    return to_host_many([t], shadows=(0,) if shadow else ())[0]
 
 
 def adopt_host(h, dev_t):
@@ -228,15 +224,71 @@ def pinned_numpy(t):
     return h.numpy()
 
 
+_device_index = None
+
+
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current CUDA stream of this process's device as a raw handle.  (``torch.cuda.current_stream()`` costs ~13 us
+    of interpreter time per call; this is the same lookup without the wrapper object.  One device per process.)"""
+    global _device_index
+    if _device_index is None:
+        _device_index = torch.cuda.current_device()
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(_device_index))
+
+
+def host_ptr(t):
+    """Address of a CPU tensor's storage (None -> NULL)."""
+    if t is None:
+        return None
+    assert not t.is_cuda and t.is_contiguous() and t.dtype == torch.float32, (t.device, t.dtype)
+    return C.c_void_p(t.data_ptr())
+
+
+def to_host_many(tensors, shadows=()):
+    """Several small CUDA tensors -> fresh page-locked numpy arrays with ONE stream synchronize
+    (csrc/host_api.cu iplan_d2h_batch).  ``shadows``: indices whose arrays are registered as device shadows."""
+    n = len(tensors)
+    tensors = [t.contiguous() for t in tensors]
+    hosts = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+    dst = (C.c_void_p * n)(*[h.data_ptr() for h in hosts])
+    src = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    nb = (C.c_int64 * n)(*[t.numel() * t.element_size() for t in tensors])
+    check(lib.iplan_d2h_batch(dst, src, nb, n, stream()), "d2h_batch")
+    out = []
+    for i, (h, t) in enumerate(zip(hosts, tensors)):
+        io_bytes["d2h"] += t.numel() * t.element_size()
+        arr = h.numpy()
+        if i in shadows and SHADOW:
+            _register_shadow(arr, t)
+        out.append(arr)
+    return out
 
 
 # ---- chunk-pipelined host <-> device calls (the reference-facing numpy API) --------------------
-_h2d_stream = None
-_d2h_stream = None
-PIPELINE_CHUNKS = 4          # env-dimension chunks per call
 PIPELINE_MIN_ROWS = 128      # below this many envs a call is one copy-in / launch / copy-out
+
+
+MAX_PIPELINE_CHUNKS = 16     # csrc/host_api.cu MAX_CHUNKS
+_sm_count = None
+
+
+def wave_chunks(n_envs, ctas_per_env, out_bytes, round_ms=0.111, pcie_gbs=50.0, max_chunks=6):
+    """How many env pieces a pipelined call of a one-CTA-per-SM kernel should use.  Consecutive launches on one stream do
+    not overlap, so every piece pays for a whole last wave: pick the count that minimises (sum of the pieces' waves) x the
+    time of one wave + the copy-out of the last piece, which nothing overlaps."""
+    global _sm_count
+    if _sm_count is None:
+        _sm_count = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    best, best_cost = 1, None
+    for n in range(1, max_chunks + 1):
+        waves = 0
+        for c in range(n):
+            envs = n_envs * (c + 1) // n - n_envs * c // n
+            waves += -(-int(envs * ctas_per_env + 0.999) // _sm_count)
+        cost = waves * round_ms + out_bytes / n / (pcie_gbs * 1e6)
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = n, cost
+    return best
 
 
 def as_host(x, dtype=torch.float32):
@@ -245,44 +297,6 @@ def as_host(x, dtype=torch.float32):
     t = x if torch.is_tensor(x) else torch.as_tensor(np.asarray(x))
     assert not t.is_cuda
     return t.to(dtype)
-
-
-def can_pipeline(host_tensors, rows):
-    return rows >= PIPELINE_MIN_ROWS and all(t.is_pinned() and t.is_contiguous() for t in host_tensors)
-
-
-def run_pipelined(host_in, dev_in, host_out, dev_out, launch, n_chunks=None):
-    """Overlap PCIe with compute inside ONE synchronous API call.  The leading (env) dimension is cut into
-    chunks; chunk c's inputs go host -> device on a copy stream, ``launch(lo, hi)`` runs on the current stream
-    as soon as they have landed, and its rows of ``dev_out`` go device -> host on a second copy stream while
-    the next chunk computes.  Host tensors must be page-locked.  Returns when ``host_out`` is complete, so the
-    caller's numpy-in / numpy-out contract (and the reusability of its input buffers) is unchanged."""
-    global _h2d_stream, _d2h_stream
-    if _h2d_stream is None:
-        _h2d_stream, _d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
-    main = torch.cuda.current_stream()
-    n = n_chunks or PIPELINE_CHUNKS
-    B = host_out.shape[0]
-    _h2d_stream.wait_stream(main)            # the staging buffers may still be in use by earlier launches
-    for c in range(n):
-        lo, hi = B * c // n, B * (c + 1) // n
-        if hi <= lo:
-            continue
-        with torch.cuda.stream(_h2d_stream):
-            for h, d in zip(host_in, dev_in):
-                d[lo:hi].copy_(h[lo:hi], non_blocking=True)
-                io_bytes["h2d"] += h[lo:hi].numel() * h.element_size()
-            landed = torch.cuda.Event()
-            landed.record(_h2d_stream)
-        main.wait_event(landed)
-        launch(lo, hi)
-        done = torch.cuda.Event()
-        done.record(main)
-        with torch.cuda.stream(_d2h_stream):
-            _d2h_stream.wait_event(done)
-            host_out[lo:hi].copy_(dev_out[lo:hi], non_blocking=True)
-            io_bytes["d2h"] += host_out[lo:hi].numel() * host_out.element_size()
-    _d2h_stream.synchronize()
 
 
 def layout(kind, *dims):

@@ -134,25 +134,35 @@ class Prediction_policy:
         on_dev = [_lib.device_shadow(x) for x in ins]
         host = [None if d is not None else _lib.as_host(x) for x, d in zip(ins, on_dev)]
         B = int(ins[0].shape[0])
-        missing = [h for h in host if h is not None]
-        if gum is None and not self.capture_hard and missing and _lib.can_pipeline(missing, B):
-            # page-locked inputs: copy-in, K1 and copy-out overlap chunk by chunk over the envs
-            key = tuple(tuple(h.shape) if h is not None else None for h in host)
+        if gum is None and not self.capture_hard and B >= _lib.PIPELINE_MIN_ROWS:
+            # one native call (csrc/host_api.cu): copy-in, K1 and copy-out overlap piece by piece over the envs
+            A, N, o = int(ins[0].shape[1]), int(ins[0].shape[2]), int(ins[0].shape[3])
+            D, L = int(ins[1].shape[-1]), int(ins[2].shape[-1])
+            key = (B, A, N, o, D, L)
             if self._stage is None or self._stage[0] != key:
-                self._stage = (key, [torch.empty(h.shape, device=dev) if h is not None else None for h in host])
-            full = [d if d is not None else st for d, st in zip(on_dev, self._stage[1])]
-            for d, sh in zip(on_dev, ins):
+                self._stage = (key, [torch.empty(B, A, N, d, device=dev) for d in (o, D, L)])
+            host = [None if h is None else h.contiguous() for h in host]
+            full = []
+            for d, st, h in zip(on_dev, self._stage[1], host):
                 if d is not None:
                     _lib.io_bytes["h2d_saved"] += d.numel() * d.element_size()
-            hs, eh, bl = (t.to(torch.float32) for t in full)
-            out = torch.empty(eh.shape, device=dev)            # fresh: it becomes the shadow of the returned array
-            out_h = torch.empty(eh.shape, dtype=torch.float32, pin_memory=True)
-
-            def launch(lo, hi):
-                self.gat_step(hs[lo:hi].permute(perm), bl[lo:hi].permute(perm), eh[lo:hi].permute(perm),
-                              out[lo:hi].permute(perm))
-
-            _lib.run_pipelined(missing, [st for st, h in zip(self._stage[1], host) if h is not None], out_h, out, launch)
+                    full.append(d if d.dtype == torch.float32 and d.is_contiguous() else d.to(torch.float32).contiguous())
+                else:
+                    _lib.io_bytes["h2d"] += h.numel() * 4
+                    full.append(st)
+            out = torch.empty(B, A, N, D, device=dev)          # fresh: it becomes the shadow of the returned array
+            out_h = torch.empty(B, A, N, D, dtype=torch.float32, pin_memory=True)
+            need = _lib.lib.iplan_gat_scratch_floats(B, A, N)
+            if self._scratch is None or self._scratch.numel() < need or self._scratch.device != out.device:
+                self._scratch = torch.empty(need, device=dev, dtype=torch.float32)
+            n_chunks = _lib.wave_chunks(B, ctas_per_env=A / 2.0, out_bytes=out.numel() * 4)
+            _lib.check(_lib.lib.iplan_gat_latent_update_host(
+                _lib.ptr(self.stack.flat), self.stack.stride(),
+                _lib.host_ptr(host[0]), _lib.ptr(full[0]), _lib.host_ptr(host[1]), _lib.ptr(full[1]), _lib.host_ptr(host[2]), _lib.ptr(full[2]),
+                _lib.ptr(out), _lib.host_ptr(out_h), self.seed, self.calls, self.tau, _lib.ptr(self._scratch), self._scratch.numel(),
+                B, A, N, o, L, n_chunks, _lib.stream()), "gat_latent_update_host")
+            self.calls += n_chunks
+            _lib.io_bytes["d2h"] += out.numel() * 4
             return _lib.adopt_host(out_h, out)
         hs, eh, bl = (_lib.to_device(x) for x in ins)
         out = torch.empty_like(eh)

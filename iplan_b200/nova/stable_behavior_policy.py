@@ -120,26 +120,29 @@ class Behavior_policy:
         else:
             hid = _lib.to_device(encoder_hidden)
         perm = (1, 0, 2, 3)
-        missing = [hist_h] + ([prev_h] if prev_h is not None else [])
-        if _lib.can_pipeline(missing, B):
-            # page-locked inputs: copy-in, K1b and copy-out overlap chunk by chunk over the envs
-            key = (tuple(hist_h.shape), tuple(prev_latent.shape))
+        if B >= _lib.PIPELINE_MIN_ROWS:
+            # one native call (csrc/host_api.cu): copy-in, K1b and copy-out overlap piece by piece over the envs
+            L = int(prev_latent.shape[-1])
+            key = (B, A, N, W, o, L)
             if self._stage is None or self._stage[0] != key:
-                self._stage = (key, torch.empty(hist_h.shape, device=dev), torch.empty(tuple(prev_latent.shape), device=dev))
+                self._stage = (key, torch.empty(B, A, N, W, o, device=dev), torch.empty(B, A, N, L, device=dev))
             _, hist, prev_stage = self._stage
+            hist_h = hist_h.contiguous()
+            _lib.io_bytes["h2d"] += hist_h.numel() * 4
             if prev_dev is not None:
-                prev = prev_dev.to(torch.float32)
+                prev = prev_dev if prev_dev.dtype == torch.float32 and prev_dev.is_contiguous() else prev_dev.to(torch.float32).contiguous()
                 _lib.io_bytes["h2d_saved"] += prev.numel() * prev.element_size()
             else:
-                prev = prev_stage
-            new = torch.empty(prev.shape, device=dev)           # fresh: the shadow of the returned array
-            new_h = torch.empty(prev.shape, dtype=torch.float32, pin_memory=True)
-
-            def launch(lo, hi):
-                self.behavior_step(hist[lo:hi].reshape(hi - lo, A, N, W * o).permute(perm), hid[lo:hi, 0].permute(perm),
-                                   prev[lo:hi].permute(perm), new[lo:hi].permute(perm))
-
-            _lib.run_pipelined(missing, [hist] + ([prev_stage] if prev_h is not None else []), new_h, new, launch)
+                prev, prev_h = prev_stage, prev_h.contiguous()
+                _lib.io_bytes["h2d"] += prev_h.numel() * 4
+            assert hid.is_contiguous() and hid.numel() == B * A * N * self.args.encoder_rnn_dim, hid.shape
+            new = torch.empty(B, A, N, L, device=dev)           # fresh: the shadow of the returned array
+            new_h = torch.empty(B, A, N, L, dtype=torch.float32, pin_memory=True)
+            _lib.check(_lib.lib.iplan_behavior_latent_update_host(
+                _lib.ptr(self.stack.flat), self.stack.stride(), _lib.host_ptr(hist_h), _lib.ptr(hist), _lib.host_ptr(prev_h), _lib.ptr(prev),
+                _lib.ptr(hid), _lib.ptr(new), _lib.host_ptr(new_h), float(self.soft_update_coef),
+                B, A, N, o, L, W, min(8, _lib.MAX_PIPELINE_CHUNKS), _lib.stream()), "behavior_latent_update_host")
+            _lib.io_bytes["d2h"] += new.numel() * 4
             return _lib.adopt_host(new_h, new), hid
         hist = _lib.to_device(hist_h)
         prev = _lib.to_device(prev_latent)

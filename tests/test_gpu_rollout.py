@@ -285,6 +285,64 @@ def test_device_resident_runner_equals_reference_api_path():
     assert torch.equal(ba["terminated"][:, :T], bb["terminated"][:, :T]) and maxdiff(ba["reward"][:, :T], bb["reward"][:, :T]) == 0.0
 
 
+def test_native_host_pipeline_equals_device_launches():
+    """csrc/host_api.cu (iplan_gat_latent_update_host / iplan_behavior_latent_update_host: copy-in, kernel and copy-out
+    pipelined over env pieces inside one native call) behind GAT_latent_update / latent_update at 130 envs (ragged pieces),
+    with pageable and page-locked inputs and with arrays handed straight back (device shadows): bit-equal to launching the
+    same kernels on device tensors piece by piece with the same noise counters."""
+    _need_gpu()
+    from iplan_b200 import _lib
+    from iplan_b200.config import make_args
+    from iplan_b200.nova.prediction_policy import Prediction_policy
+    from iplan_b200.nova.stable_behavior_policy import Behavior_policy
+    args = make_args("highway", use_cuda=True, device="cuda")
+    B, A, N, o, L, D, W = 130, args.n_agents, args.max_vehicle_num, args.obs_shape_single, args.latent_dim, args.attention_dim, args.max_history_len
+    assert B >= _lib.PIPELINE_MIN_ROWS
+    torch.manual_seed(11)
+    pred, beh = Prediction_policy(args, None), Behavior_policy(args, None)
+    rng = np.random.default_rng(5)
+    perm = (1, 0, 2, 3)
+
+    def device_gat(hist, att, behl, calls0, n):
+        pred.calls = calls0
+        h, a_, b_ = (torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).cuda() for x in (hist, att, behl))
+        ref = torch.empty(B, A, N, D, device="cuda")
+        for c in range(n):
+            lo, hi = B * c // n, B * (c + 1) // n
+            pred.gat_step(h[lo:hi].permute(perm), b_[lo:hi].permute(perm), a_[lo:hi].permute(perm), ref[lo:hi].permute(perm))
+        return ref.cpu().numpy()
+
+    hist = rng.uniform(-1, 1, size=(B, A, N, o))                          # float64, pageable: the reference's wrapper hands this over
+    att = np.zeros((B, A, N, D), dtype=np.float32)
+    behl = rng.dirichlet(np.ones(L), size=(B, A, N)).astype(np.float32)
+    c0 = pred.calls
+    out1 = pred.GAT_latent_update(hist, att, behl)
+    n1 = pred.calls - c0
+    assert n1 >= 2, "the native pipeline should cut 130 envs into pieces"
+    ref1 = device_gat(hist, att, behl, c0, n1)
+    assert np.array_equal(out1, ref1)
+    # second call: the returned array handed straight back (device shadow, no upload), page-locked history
+    hist2 = _lib.pinned_numpy(torch.as_tensor(rng.uniform(-1, 1, size=(B, A, N, o)), dtype=torch.float32))
+    before = dict(_lib.io_bytes)
+    c1 = pred.calls
+    out2 = pred.GAT_latent_update(hist2, out1, behl)
+    assert _lib.io_bytes["h2d_saved"] - before["h2d_saved"] == out1.nbytes
+    assert np.array_equal(out2, device_gat(hist2, out1, behl, c1, pred.calls - c1))
+    # behaviour encoder: deterministic, so one launch over all envs is the comparison
+    win = rng.uniform(-1, 1, size=(B, A, N, W, o)).astype(np.float32)
+    hid0 = rng.uniform(-1, 1, size=(B, 1, A, N, args.encoder_rnn_dim)).astype(np.float32)
+    new1, hid1 = beh.latent_update(win, hid0, behl)
+    w_d, p_d = torch.as_tensor(win).cuda(), torch.as_tensor(behl).cuda()
+    h_d = torch.as_tensor(hid0).cuda().clone()
+    n_d = torch.empty(B, A, N, L, device="cuda")
+    beh.behavior_step(w_d.reshape(B, A, N, W * o).permute(perm), h_d[:, 0].permute(perm), p_d.permute(perm), n_d.permute(perm))
+    assert np.array_equal(new1, n_d.cpu().numpy()) and torch.equal(hid1, h_d)
+    new2, hid2 = beh.latent_update(win, hid1, new1)                       # shadowed latent + device hidden handed back
+    n2 = torch.empty(B, A, N, L, device="cuda")
+    beh.behavior_step(w_d.reshape(B, A, N, W * o).permute(perm), h_d[:, 0].permute(perm), n_d.permute(perm), n2.permute(perm))
+    assert np.array_equal(new2, n2.cpu().numpy()) and torch.equal(hid2, h_d)
+
+
 def test_obs_history_kernel_vs_reference_golden(golden_dir):
     """iplan_obs_history_step through the reference-named wrapper class: slot assignment in first-seen order, windows and
     newest rows bit-equal to the reference's wrapper over 14 recorded timesteps; the device window feeds K1b's layout."""
