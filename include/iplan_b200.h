@@ -172,6 +172,15 @@ int iplan_behavior_latent_update_host(const float* beh_params, int64_t param_str
 /* n device -> host copies on `stream`, then one synchronize (select_actions_ippo returns four small arrays) */
 int iplan_d2h_batch(void* const* dst_host, const void* const* src_dev, const int64_t* bytes, int n, void* stream);
 
+/* Which kernel runs K1b: 0 = behavior_tc5_kernel (tcgen05.mma with both A operands, h and u_w, in tensor memory; chains as
+ * TMEM lanes; csrc/behavior_tc5.cu), 1 = behavior_step_kernel (mma.sync m16n8k16, one warp per 16 chains: the cross-check, and
+ * the fallback for obs_dim > 8, windows longer than 64 values or hidden-state strides that are not multiples of 4).
+ * Returns the previous setting. */
+int iplan_behavior_set_impl(int impl);
+int iplan_behavior_get_impl(void);
+/* timing experiments (IPLAN_BEH_DBG=1): clock64() stamps of one CTA of the last tcgen05 K1b launch, 64 values */
+int iplan_behavior_debug_clocks(long long* out64);
+
 /* ---- K1c: controller step (actor + critic, one timestep) -------------------------
  * replaces DcntrlMAC.select_actions_ippo (controllers/dcntrl_controller.py:27-58):
  * LayerNorm(F) -> fc1 -> ReLU -> LN -> fc2 -> ReLU -> LN -> 1-step GRU -> LN ->

@@ -48,6 +48,9 @@ _SIGNATURES = {
     "iplan_gat128_recur": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _p]),
     "iplan_gat128_attend": (_i, [_p, _p, _p, _p, _p, _u64, _u64, _f, _p, _i, _i64, _p]),
     "iplan_gat128_gates": (_i, [_p, _p, _p, _p, _i64, _p]),
+    "iplan_behavior_set_impl": (_i, [_i]),
+    "iplan_behavior_get_impl": (_i, []),
+    "iplan_behavior_debug_clocks": (_i, [_p]),
     "iplan_behavior_step": (_i, [_p, _i64, View, View, View, View, _f, _i, _i, _i, _i, _i, _i, _p]),
     "iplan_behavior_step_ex": (_i, [_p, _i64, View, _i64, _i, View, View, View, _f, _i, _i, _i, _i, _i, _i, _p]),
     "iplan_gat_latent_update_host": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _u64, _u64, _f, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
@@ -165,37 +168,25 @@ def device_shadow(x):
     return None
 
 
-_copy_stream = None
-
-
 def to_device(x, dtype=torch.float32, device="cuda"):
     """numpy / CPU tensor -> CUDA tensor of `dtype`, counting the bytes that cross PCIe.
 
-    The host buffer is reusable when this returns (the reference's ``th.tensor(x).to(device)``
-    semantics).  Page-locked sources (e.g. arrays handed out by ``to_host``) are copied on a side
-    stream, so the copy does not queue behind kernels already in flight on the compute stream."""
+    The host buffer is reusable when this returns (the reference's ``th.tensor(x).to(device)`` semantics).  Every call of
+    the numpy API returns with the compute stream drained, so the copy is simply issued on it."""
     import numpy as np
-    global _copy_stream
     sh = device_shadow(x)
     if sh is not None:                       # an array we returned, handed straight back: already on the device
         io_bytes["h2d_saved"] += sh.numel() * sh.element_size()
-        return sh.to(dtype)
+        return sh if sh.dtype == dtype else sh.to(dtype)
     if torch.is_tensor(x):
         if x.is_cuda:
             return x.to(dtype)
         t = x
     else:
         t = torch.as_tensor(np.asarray(x))
-    t = t.to(dtype)
+    if t.dtype != dtype:
+        t = t.to(dtype)
     io_bytes["h2d"] += t.numel() * t.element_size()
-    if t.numel() >= (1 << 16) and t.is_contiguous() and t.is_pinned():
-        if _copy_stream is None:
-            _copy_stream = torch.cuda.Stream()
-        with torch.cuda.stream(_copy_stream):
-            d = t.to(device, non_blocking=True)
-        _copy_stream.synchronize()
-        d.record_stream(torch.cuda.current_stream())
-        return d
     return t.to(device)
 
 

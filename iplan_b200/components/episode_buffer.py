@@ -37,6 +37,7 @@ class EpisodeBatch:
         self.max_seq_length = max_seq_length
         self.preprocess = {} if preprocess is None else preprocess
         self.device = device
+        self._on_cuda = str(device).startswith("cuda")
         self.packed = None
         if data is not None:
             self.data = data
@@ -105,12 +106,16 @@ class EpisodeBatch:
             for k, v in store.items():
                 store[k] = v.to(device)
         self.device = device
+        self._on_cuda = str(device).startswith("cuda")
 
     # -------------------------------------------------------------------------------
     def update(self, data, bs=slice(None), ts=slice(None), mark_filled=True):
         """Same contract as the reference's update (:87-112): values are converted to the
         scheme dtype on the batch's device and written with ``view_as`` semantics."""
         slices = self._parse_slices((bs, ts))
+        basic = all(isinstance(x, slice) for x in slices)
+        if self._on_cuda:
+            from .. import _lib
         for k, v in data.items():
             if k in self.data.transition_data:
                 target = self.data.transition_data
@@ -124,8 +129,7 @@ class EpisodeBatch:
             else:
                 raise KeyError("{} not found in transition or episode data".format(k))
             dtype = self.scheme[k].get("dtype", th.float32)
-            if str(self.device).startswith("cuda"):
-                from .. import _lib
+            if self._on_cuda:
                 v = _lib.to_device(v, dtype=dtype, device=self.device)      # counts PCIe bytes
             elif th.is_tensor(v):
                 v = v.to(device=self.device, dtype=dtype)
@@ -133,13 +137,20 @@ class EpisodeBatch:
                 v = th.as_tensor(np.asarray(v)).to(device=self.device, dtype=dtype)
             dest = target[k][_slices]
             self._check_safe_view(v, dest)
-            target[k][_slices] = v.reshape(dest.shape)
+            if basic:
+                dest.copy_(v.reshape(dest.shape))          # basic indexing: `dest` is a view of the store
+            else:
+                target[k][_slices] = v.reshape(dest.shape)
             if k in self.preprocess:
                 new_k = self.preprocess[k][0]
-                w = target[k][_slices]
+                w = dest if basic else target[k][_slices]
                 for tr in self.preprocess[k][1]:
                     w = tr.transform(w)
-                target[new_k][_slices] = w.view_as(target[new_k][_slices])
+                if basic:
+                    nd = target[new_k][_slices]
+                    nd.copy_(w.view_as(nd))
+                else:
+                    target[new_k][_slices] = w.view_as(target[new_k][_slices])
                 if self.packed is not None and new_k == "actions_onehot":
                     self._store_last_action(w, slices)
 

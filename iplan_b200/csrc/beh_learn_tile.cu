@@ -94,7 +94,7 @@ __device__ __forceinline__ void gru_gates(const float* __restrict__ Wf, const fl
         for (int c = 0; c < 4; ++c) { ar[c][i] = b0; az[c][i] = b1; ai[c][i] = b2; ah[c][i] = b3; }
     }
     const float* wrow = Wf + t.ug * UPT;
-#pragma unroll 2
+#pragma unroll 4
     for (int k = 0; k < H; ++k) {
         float uv[4], hv[4], wir[UPT], wiz[UPT], win[UPT], whr[UPT], whz[UPT], whn[UPT];
         ld4(us + k * RS + t.c0, uv); ld4(hs + k * RS + t.c0, hv);

@@ -15,7 +15,12 @@
 // The B fragments of W_l, W_ih, W_hh (hi and lo) are staged once per CTA in shared memory.
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "behavior_common.cuh"
+
+#define IPLAN_BEH_IMPL_DEFAULT 0
 
 namespace iplan {
 
@@ -27,15 +32,6 @@ constexpr int NODES_W = 16;        // nodes per warp (one MMA m-tile)
 constexpr int WIN_MAX = 64;        // hist_len * obs_dim upper bound per node
 constexpr int LAT_MAX = 8;         // latent_dim upper bound (one MMA n-tile)
 constexpr int NT3 = E3 / 8;        // 12 gate n-tiles
-
-struct BehArgs {
-    const float* params; int64_t param_stride;
-    iplan_view window, hid, lat_prev, lat_out;
-    float coef;
-    int n_envs, n_slots, obs_dim, latent_dim, hist_len;
-    int64_t win_step;      // 0: window rows are contiguous ([hist_len][obs_dim] per node); else element stride between rows
-    int win_pad;           // (win_step != 0) leading window rows that are zero padding; window.ptr = the first real row
-};
 
 struct BehSmem {
     uint2 wih[2][NT3][2][32];       // [hi|lo][n-tile][k-block][lane] B fragments of W_ih
@@ -327,6 +323,19 @@ __global__ void __launch_bounds__(BEH_THREADS, 2) behavior_step_kernel(BehArgs a
 
 }  // namespace iplan
 
+// 0 = behavior_tc5_kernel (tcgen05 / TMEM, csrc/behavior_tc5.cu), 1 = behavior_step_kernel (mma.sync, this file: the
+// cross-check, and the fallback for shapes the tcgen05 kernel does not take).  IPLAN_BEH_IMPL overrides the default at start-up.
+static int g_beh_impl = -1;
+static int beh_impl() {
+    if (g_beh_impl < 0) {
+        const char* ev = getenv("IPLAN_BEH_IMPL");
+        g_beh_impl = ev ? (atoi(ev) != 0) : IPLAN_BEH_IMPL_DEFAULT;
+    }
+    return g_beh_impl;
+}
+extern "C" int iplan_behavior_set_impl(int impl) { const int old = beh_impl(); if (impl == 0 || impl == 1) g_beh_impl = impl; return old; }
+extern "C" int iplan_behavior_get_impl(void) { return beh_impl(); }
+
 extern "C" int iplan_behavior_step(const float* beh_params, int64_t param_stride,
                                    iplan_view window, iplan_view hid_io, iplan_view lat_prev, iplan_view lat_out,
                                    float soft_coef,
@@ -357,6 +366,7 @@ extern "C" int iplan_behavior_step_ex(const float* beh_params, int64_t param_str
     a.coef = soft_coef;
     a.n_envs = n_envs; a.n_slots = n_slots; a.obs_dim = obs_dim; a.latent_dim = latent_dim; a.hist_len = hist_len;
     a.win_step = win_stride_step; a.win_pad = win_stride_step ? win_pad : 0;
+    if (beh_impl() == 0 && behavior_tc5_supports(a)) return launch_behavior_tc5(a, n_agents, (cudaStream_t)stream);
     const size_t smem = sizeof(BehSmem);
     static bool configured = false;
     if (!configured) {

@@ -78,34 +78,6 @@ __host__ __device__ inline G5Layout g5_layout(int N, bool fused) {
 }
 constexpr size_t G5_SMEM_MAX = 227 * 1024;
 
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-// tcgen05.wait::ld that also names the loaded registers, so that no use of them can be scheduled above the wait
-__device__ __forceinline__ void tc5_wait_ld24(float (&a)[8], float (&b)[8], float (&c)[8]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]),
-                   "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]),
-                   "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]), "+f"(c[4]), "+f"(c[5]), "+f"(c[6]), "+f"(c[7])
-                 :: "memory");
-}
-// 32 lanes x 4 consecutive 32-bit columns <- registers (thread = TMEM lane): the gate warps write h as packed f16 pairs
-__device__ __forceinline__ void tc5_st4(uint32_t taddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem]^T : the A operand read from tensor memory (no shared-memory traffic for it)
-__device__ __forceinline__ void tc5_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc5_wait_ld8(float (&a)[8]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]), "+f"(a[6]), "+f"(a[7]) :: "memory");
-}
-
 // DBG (timing experiments only, results are garbage): bit 0 = tile 1 (reverse direction) does nothing; bit 1 = the MUFU
 // instructions of the gates are replaced by FMA-pipe stand-ins
 // bit 2 = one CTA stamps clock64() at its phase boundaries into g5_clk (read back with iplan_gat_debug_clocks)

@@ -285,6 +285,18 @@ def test_device_resident_runner_equals_reference_api_path():
     assert torch.equal(ba["terminated"][:, :T], bb["terminated"][:, :T]) and maxdiff(ba["reward"][:, :T], bb["reward"][:, :T]) == 0.0
 
 
+def test_behavior_tcgen05_kernel_matches_mma_sync_kernel():
+    """K1b: csrc/behavior_tc5.cu (tcgen05.mma, hidden state and input-layer output as tensor-memory operands; the default)
+    against csrc/behavior_step.cu (mma.sync; pinned to the reference's golden outputs by the tests above, which run the
+    default kernel too) on contiguous windows and on windows read in place from a time-strided store with leading zero
+    rows, 7 .. 512 envs (ragged last tiles): latents within 2e-6, hidden states within 5e-6 (both kernels use approximate
+    exponentials: ex2.approx + rcp.approx vs __expf + __fdividef)."""
+    _need_gpu()
+    import importlib
+    mod = importlib.import_module("tools.check_behavior_tc5")
+    assert mod.run()
+
+
 def test_native_host_pipeline_equals_device_launches():
     """csrc/host_api.cu (iplan_gat_latent_update_host / iplan_behavior_latent_update_host: copy-in, kernel and copy-out
     pipelined over env pieces inside one native call) behind GAT_latent_update / latent_update at 130 envs (ragged pieces),
