@@ -158,12 +158,15 @@ int iplan_behavior_step_ex(const float* beh_params, int64_t param_stride,
  * device buffer already holds that array (e.g. the previous call's result, still resident): nothing is uploaded for it.
  * dev_* are caller-owned device buffers of the full [B][A][N][*] size (staging for the uploaded arrays; dev_out / dev_new
  * receive the result and stay valid).  Host buffers may be pageable; page-locked ones overlap with the kernels.
- * The GAT noise counter of piece c is counter + c. */
+ * The GAT noise counter of piece c is counter + c.  chunk_end: NULL (equal pieces) or the n_chunks increasing end indices of
+ * the pieces (last = n_envs): K1 runs one CTA per SM, so pieces sized in whole waves with a short last piece (whose copy-out
+ * nothing overlaps) cost no extra wave. */
 int iplan_gat_latent_update_host(const float* gat_params, int64_t param_stride,
                                  const float* host_hist, float* dev_hist, const float* host_h, float* dev_h,
                                  const float* host_beh, float* dev_beh, float* dev_out, float* host_out,
                                  uint64_t seed, uint64_t counter, float tau, float* scratch, int64_t scratch_floats,
-                                 int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int n_chunks, void* stream);
+                                 int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int n_chunks, const int32_t* chunk_end,
+                                 void* stream);
 /* host_window [B][A][N][hist_len][o], host_prev / host_new [B][A][N][L], dev_hid_io [B][A][N][32] (updated in place) */
 int iplan_behavior_latent_update_host(const float* beh_params, int64_t param_stride,
                                       const float* host_window, float* dev_window, const float* host_prev, float* dev_prev,

@@ -53,7 +53,7 @@ _SIGNATURES = {
     "iplan_behavior_debug_clocks": (_i, [_p]),
     "iplan_behavior_step": (_i, [_p, _i64, View, View, View, View, _f, _i, _i, _i, _i, _i, _i, _p]),
     "iplan_behavior_step_ex": (_i, [_p, _i64, View, _i64, _i, View, View, View, _f, _i, _i, _i, _i, _i, _i, _p]),
-    "iplan_gat_latent_update_host": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _u64, _u64, _f, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
+    "iplan_gat_latent_update_host": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _u64, _u64, _f, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _p]),
     "iplan_behavior_latent_update_host": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _i, _i, _i, _p]),
     "iplan_d2h_batch": (_i, [_p, _p, _p, _i, _p]),
     "iplan_controller_step": (_i, [_p, _i64, _p, _i64, _p, _i64, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64,
@@ -263,23 +263,34 @@ MAX_PIPELINE_CHUNKS = 16     # csrc/host_api.cu MAX_CHUNKS
 _sm_count = None
 
 
-def wave_chunks(n_envs, ctas_per_env, out_bytes, round_ms=0.111, pcie_gbs=50.0, max_chunks=6):
-    """How many env pieces a pipelined call of a one-CTA-per-SM kernel should use.  Consecutive launches on one stream do
-    not overlap, so every piece pays for a whole last wave: pick the count that minimises (sum of the pieces' waves) x the
-    time of one wave + the copy-out of the last piece, which nothing overlaps."""
+def wave_chunks(n_envs, ctas_of):
+    """End indices of the env pieces of a pipelined call of a one-CTA-per-SM kernel (K1); ``ctas_of(envs)`` = its grid size.
+    Consecutive launches on one stream do not overlap, so every piece pays for a whole last wave.  The pieces therefore hold
+    whole waves (never more waves in total than a single launch), the LAST piece is what does not fill the other waves (its
+    copy-out is the part of the call nothing overlaps, so it should be short), and the rest is cut in two."""
     global _sm_count
     if _sm_count is None:
         _sm_count = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-    best, best_cost = 1, None
-    for n in range(1, max_chunks + 1):
-        waves = 0
-        for c in range(n):
-            envs = n_envs * (c + 1) // n - n_envs * c // n
-            waves += -(-int(envs * ctas_per_env + 0.999) // _sm_count)
-        cost = waves * round_ms + out_bytes / n / (pcie_gbs * 1e6)
-        if best_cost is None or cost < best_cost - 1e-9:
-            best, best_cost = n, cost
-    return best
+    sm = _sm_count
+    waves = lambda e: -(-ctas_of(e) // sm) if e > 0 else 0
+
+    def cap(w):                                                  # most envs whose grid fits in w waves
+        lo, hi = 0, n_envs
+        while lo < hi:
+            mid = (lo + hi + 1) // 2
+            lo, hi = (mid, hi) if waves(mid) <= w else (lo, mid - 1)
+        return lo
+
+    total = waves(n_envs)
+    if total <= 2:
+        return [n_envs]
+    rest = cap(total - 1)                                        # fills total - 1 waves; the tail goes last
+    if rest <= 0 or rest >= n_envs:
+        return [n_envs]
+    first = cap((total - 1 + 1) // 2)
+    if 0 < first < rest and waves(first) + waves(rest - first) + waves(n_envs - rest) <= total:
+        return [first, rest, n_envs]
+    return [rest, n_envs]
 
 
 def as_host(x, dtype=torch.float32):

@@ -57,7 +57,8 @@ extern "C" int iplan_gat_latent_update_host(const float* gat_params, int64_t par
                                             const float* host_hist, float* dev_hist, const float* host_h, float* dev_h,
                                             const float* host_beh, float* dev_beh, float* dev_out, float* host_out,
                                             uint64_t seed, uint64_t counter, float tau, float* scratch, int64_t scratch_floats,
-                                            int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int n_chunks, void* stream) {
+                                            int n_envs, int n_agents, int n_slots, int obs_dim, int latent_dim, int n_chunks, const int32_t* chunk_end,
+                                            void* stream) {
     using namespace iplan;
     IPLAN_REQUIRE(gat_params && dev_hist && dev_h && dev_beh && dev_out && host_out && scratch, "gat_latent_update_host: null pointer");
     IPLAN_REQUIRE(n_chunks >= 1 && n_chunks <= MAX_CHUNKS && n_envs > 0, "gat_latent_update_host: 1..%d chunks", MAX_CHUNKS);
@@ -67,7 +68,9 @@ extern "C" int iplan_gat_latent_update_host(const float* gat_params, int64_t par
     CU(cudaEventRecord(g_pipe.ev_main, main));                       // the staging buffers may still be read by earlier launches
     CU(cudaStreamWaitEvent(g_pipe.h2d, g_pipe.ev_main, 0));
     for (int c = 0; c < n_chunks; ++c) {
-        const int64_t lo = (int64_t)n_envs * c / n_chunks, hi = (int64_t)n_envs * (c + 1) / n_chunks;
+        const int64_t lo = chunk_end ? (c ? chunk_end[c - 1] : 0) : (int64_t)n_envs * c / n_chunks;
+        const int64_t hi = chunk_end ? chunk_end[c] : (int64_t)n_envs * (c + 1) / n_chunks;
+        IPLAN_REQUIRE(lo >= 0 && hi <= n_envs && (c + 1 < n_chunks || hi == n_envs), "gat_latent_update_host: piece %d = [%lld, %lld) of %d envs", c, (long long)lo, (long long)hi, n_envs);
         if (hi <= lo) continue;
         const int64_t rows = (hi - lo) * A * N, r0 = lo * A * N;
         bool copied = false;

@@ -155,12 +155,13 @@ class Prediction_policy:
             need = _lib.lib.iplan_gat_scratch_floats(B, A, N)
             if self._scratch is None or self._scratch.numel() < need or self._scratch.device != out.device:
                 self._scratch = torch.empty(need, device=dev, dtype=torch.float32)
-            n_chunks = _lib.wave_chunks(B, ctas_per_env=A / 2.0, out_bytes=out.numel() * 4)
+            ends = _lib.wave_chunks(B, lambda e: ((e + 1) // 2) * A)      # K1: one CTA per (2 envs, agent-net)
+            n_chunks = len(ends)
             _lib.check(_lib.lib.iplan_gat_latent_update_host(
                 _lib.ptr(self.stack.flat), self.stack.stride(),
                 _lib.host_ptr(host[0]), _lib.ptr(full[0]), _lib.host_ptr(host[1]), _lib.ptr(full[1]), _lib.host_ptr(host[2]), _lib.ptr(full[2]),
                 _lib.ptr(out), _lib.host_ptr(out_h), self.seed, self.calls, self.tau, _lib.ptr(self._scratch), self._scratch.numel(),
-                B, A, N, o, L, n_chunks, _lib.stream()), "gat_latent_update_host")
+                B, A, N, o, L, n_chunks, (_lib.C.c_int32 * n_chunks)(*ends), _lib.stream()), "gat_latent_update_host")
             self.calls += n_chunks
             _lib.io_bytes["d2h"] += out.numel() * 4
             return _lib.adopt_host(out_h, out)

@@ -22,6 +22,27 @@ def test_library_exports_every_declared_symbol():
     assert _lib.ABI_VERSION == int(re.search(r"#define IPLAN_ABI_VERSION (\d+)", header).group(1))
 
 
+def test_pipeline_pieces_are_whole_waves_with_a_short_last_piece():
+    """_lib.wave_chunks: the env pieces of the native GAT_latent_update pipeline cover [0, n_envs), are whole waves of a
+    one-CTA-per-SM kernel (their waves add up to those of a single launch) and end with the shortest piece."""
+    from iplan_b200 import _lib
+    _lib._sm_count = 148
+    try:
+        for n_envs in (1, 59, 60, 128, 130, 256, 512, 513, 1024, 4096):
+            for agents in (1, 3, 5, 8, 16):
+                ctas = lambda e: ((e + 1) // 2) * agents                      # K1's grid
+                waves = lambda e: -(-ctas(e) // 148) if e else 0
+                ends = _lib.wave_chunks(n_envs, ctas)
+                assert ends[-1] == n_envs and all(b > a for a, b in zip([0] + ends, ends)) and 1 <= len(ends) <= 3
+                sizes = [b - a for a, b in zip([0] + ends, ends)]
+                assert sum(waves(x) for x in sizes) <= waves(n_envs), (n_envs, agents, ends)
+                if len(ends) > 1:
+                    assert waves(sizes[-1]) == 1 and sizes[-1] == min(sizes), (n_envs, agents, ends)
+        assert _lib.wave_chunks(512, lambda e: ((e + 1) // 2) * 5) == [236, 472, 512]
+    finally:
+        _lib._sm_count = None
+
+
 def test_layouts_match_module_specs():
     from iplan_b200.modules.flat import ParamStack
     for kind, dims in (("gat", (13,)), ("beh", (5, 8)), ("actor", (2485, 5)), ("critic", (2485,)),

@@ -315,12 +315,15 @@ def test_native_host_pipeline_equals_device_launches():
     rng = np.random.default_rng(5)
     perm = (1, 0, 2, 3)
 
+    ends = _lib.wave_chunks(B, lambda e: ((e + 1) // 2) * A)                     # the pieces the native call cuts the envs into
+
     def device_gat(hist, att, behl, calls0, n):
+        assert n == len(ends)
         pred.calls = calls0
         h, a_, b_ = (torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).cuda() for x in (hist, att, behl))
         ref = torch.empty(B, A, N, D, device="cuda")
         for c in range(n):
-            lo, hi = B * c // n, B * (c + 1) // n
+            lo, hi = (ends[c - 1] if c else 0), ends[c]
             pred.gat_step(h[lo:hi].permute(perm), b_[lo:hi].permute(perm), a_[lo:hi].permute(perm), ref[lo:hi].permute(perm))
         return ref.cpu().numpy()
 
