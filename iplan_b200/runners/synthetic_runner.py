@@ -174,7 +174,11 @@ class ParallelRunner:
         # strided device copy (a live simulator would write row t each step through observation_wrapper.step()).  K1 reads
         # row t, K1b reads its W-step window in place from rows t-W+1..t of the store: no shifted window copy per step.
         hist_v.copy_(env.history.permute(2, 1, 0, 3, 4))
-        step_stride = packed.stride(2)
+        # K1b's window rows come from the simulator's dense history [T+1,B,A,N,o] (what the observation wrapper's device window
+        # is): 20 contiguous bytes per slot and row next to its neighbours', instead of 20 of every 180 bytes of the packed store
+        # (ncu: 227 MB of DRAM reads per launch for 28 MB of window)
+        hist_src = env.history.permute(0, 2, 1, 3, 4)                   # [T+1,A,B,N,o] view
+        hist_step = env.history.stride(0)
 
         events = getattr(self, "gat_events", None)
         noise = getattr(self, "noise_hook", None)      # parity tests: noise(kind, index) -> explicit noise tensor or None
@@ -215,8 +219,8 @@ class ParallelRunner:
                   out=(actions_steps[t], logp_steps[t], value_steps[t]))
             gat(hist_v[:, :, t + 1], beh_v[:, :, t], att_v[:, :, t], att_v[:, :, t + 1])
             first = max(0, t + 2 - W)                                   # oldest time inside the window of time t+1
-            timed("beh", self.behavior_learner.behavior_step, hist_v[:, :, first], enc_hid, beh_v[:, :, t], beh_v[:, :, t + 1],
-                  win_stride_step=step_stride, win_pad=max(0, W - (t + 2)))
+            timed("beh", self.behavior_learner.behavior_step, hist_src[first], enc_hid, beh_v[:, :, t], beh_v[:, :, t + 1],
+                  win_stride_step=hist_step, win_pad=max(0, W - (t + 2)))
         actions_all = actions_steps.permute(1, 2, 0)                    # [A,B,T+1]
         self.last_logp, self.last_values = logp_steps, value_steps      # [T,A,B] of the episode just run (parity tests)
         # episode-level stores in the reference's layout [B,T+1,A,*]
