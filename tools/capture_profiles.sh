@@ -17,3 +17,16 @@ ncu --set full --clock-control none -k regex:fc1_fwd_tc5 -s 12 -c 1 -f -o "$OUT/
     python tools/check_fc1_tc5.py > "$OUT/tc5_fwd_ncu.log" 2>&1
 ncu --set full --clock-control none -k regex:fc1_bwd_tc5 -s 12 -c 1 -f -o "$OUT/tc5_bwd_full" \
     python tools/check_fc1_tc5.py > "$OUT/tc5_bwd_ncu.log" 2>&1
+
+# Round 2, third session:
+# 4. K1b (tcgen05) / K1c / the decoder kernel of Behavior_policy.learn, one launch each
+ncu --set full --clock-control none --import-source on -k regex:behavior_tc5 -s 60 -c 1 -f -o "$OUT/k1b_tc5_full" \
+    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > "$OUT/k1b_ncu.log" 2>&1
+ncu --set full --clock-control none --import-source on -k regex:controller_step -s 60 -c 1 -f -o "$OUT/k1c_full" \
+    python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > "$OUT/k1c_ncu.log" 2>&1
+ncu --set full --clock-control none --import-source on -k regex:dec_kernel -s 1 -c 1 -f -o "$OUT/beh_dec_full" \
+    python tools/check_beh_learn_tile.py --envs 2 --steps 14 --time-envs 128 > "$OUT/beh_ncu.log" 2>&1
+# 5. K1b phase stamps, host-side profile of the numpy API path, the auxiliary learners inside the iteration
+IPLAN_BEH_DBG=1 python tools/check_behavior_tc5.py --time-envs 512 > "$OUT/k1b_trace.log" 2>&1
+python tools/profile_e2e.py > "$OUT/e2e_profile.log" 2>&1
+python bench.py --with-aux --no-e2e --no-cpu-baseline > "$OUT/bench_aux.json" 2> "$OUT/bench_aux.err"
