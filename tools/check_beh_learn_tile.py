@@ -21,7 +21,7 @@ from tools.check_pred_learn import scheme_for                            # noqa:
 
 
 def make_batch(args, B, T1, seed):
-    A, N, o, L = args.n_agents, args.max_vehicle_num, args.obs_shape_single, args.latent_dim
+    A, N, o = args.n_agents, args.max_vehicle_num, args.obs_shape_single
     g = torch.Generator().manual_seed(seed)
     scheme, groups, pre = scheme_for(args)
     batch = EpisodeBatch(scheme, groups, B, T1, preprocess=pre, device="cuda")
