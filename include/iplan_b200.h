@@ -245,8 +245,9 @@ int iplan_pred_learn(const float* gat_params, int64_t gat_stride, const float* d
 
 /* ---- Behavior_policy.learn (nova/stable_behavior_policy.py:161-279) -----------------------------
  * Arithmetic specified line by line by oracle/iplan_oracle.py::behavior_learn_agent.
- * One launch = the reconstruction loss over every window position of every episode and its gradients (one BPTT through
- * the encoder GRU, the decoder GRU and the latent recursion), ADDED into g_enc / g_dec (zero them first; layouts
+ * One call = the reconstruction loss over every window position of every episode and its gradients (one BPTT through
+ * the encoder GRU, the decoder GRU and the latent recursion; three launches with the default implementation: encoder
+ * forward, decoder forward + backward, encoder backward), ADDED into g_enc / g_dec (zero them first; layouts
  * iplan_beh_layout / iplan_bdec_layout).  behavior_variation_penalty = 0 only (the stability term is reported, not
  * differentiated).
  *   hist [A][B][T][N][o] (the batch without its last step), mask [A][B][T], scale [A][T-1-W] = o N / (unmasked elements
